@@ -1,0 +1,1118 @@
+// TEST INFRASTRUCTURE - CPU restatement of the reference search core (lib/fsearch.py).
+//
+// This file is the parity ORACLE for swiftortho_b200.  It restates, function by function and
+// quirk by quirk, the live path of the reference's RPython core `/root/reference/lib/fsearch.py`
+// (entry_point -> blastp -> Fasta.build_msav / find_msav_m / kswat_st ...).  It is deliberately
+// sequential and shaped like the reference (ordered dictionaries, one query at a time, shared
+// 4100x4100 DP matrices), not like the product.  Every function cites the reference lines it
+// follows.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// leg may build or call it; the product (swiftortho_b200/) never does.
+//
+// Parity pin: validated row-for-row against the reference source itself executed under CPython
+// (oracle/ref_shim/run_reference.py) on the fixtures under tests/golden/ (see
+// tests/golden/make_golden.py) and against the reference README's known answer
+// (README.md:52: 450-aa self hit -> identity 100.00, length 450, bit 897).
+//
+// Build: see oracle/Makefile (g++ -O2, no -ffast-math so control-flow doubles are reproducible).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace orc {
+
+typedef long long i64;
+
+// ---------------------------------------------------------------------------------------------
+// BLOSUM62 on ASCII, both cases, -4 for everything else (fsearch.py:330-346 `B62`, `dict2mat`).
+// The 23-letter matrix below is the standard NCBI BLOSUM62 restricted to the letters the
+// reference dictionary holds (ABCDEFGHIKLMNPQRSTVWXYZ; no '*', J, O, U).
+// ---------------------------------------------------------------------------------------------
+static const char B62_LETTERS[] = "ARNDCQEGHILKMFPSTWYVBZX";
+static const signed char B62_TABLE[23][23] = {
+    /*A*/ {4, -1, -2, -2, 0, -1, -1, 0, -2, -1, -1, -1, -1, -2, -1, 1, 0, -3, -2, 0, -2, -1, 0},
+    /*R*/ {-1, 5, 0, -2, -3, 1, 0, -2, 0, -3, -2, 2, -1, -3, -2, -1, -1, -3, -2, -3, -1, 0, -1},
+    /*N*/ {-2, 0, 6, 1, -3, 0, 0, 0, 1, -3, -3, 0, -2, -3, -2, 1, 0, -4, -2, -3, 3, 0, -1},
+    /*D*/ {-2, -2, 1, 6, -3, 0, 2, -1, -1, -3, -4, -1, -3, -3, -1, 0, -1, -4, -3, -3, 4, 1, -1},
+    /*C*/ {0, -3, -3, -3, 9, -3, -4, -3, -3, -1, -1, -3, -1, -2, -3, -1, -1, -2, -2, -1, -3, -3, -2},
+    /*Q*/ {-1, 1, 0, 0, -3, 5, 2, -2, 0, -3, -2, 1, 0, -3, -1, 0, -1, -2, -1, -2, 0, 3, -1},
+    /*E*/ {-1, 0, 0, 2, -4, 2, 5, -2, 0, -3, -3, 1, -2, -3, -1, 0, -1, -3, -2, -2, 1, 4, -1},
+    /*G*/ {0, -2, 0, -1, -3, -2, -2, 6, -2, -4, -4, -2, -3, -3, -2, 0, -2, -2, -3, -3, -1, -2, -1},
+    /*H*/ {-2, 0, 1, -1, -3, 0, 0, -2, 8, -3, -3, -1, -2, -1, -2, -1, -2, -2, 2, -3, 0, 0, -1},
+    /*I*/ {-1, -3, -3, -3, -1, -3, -3, -4, -3, 4, 2, -3, 1, 0, -3, -2, -1, -3, -1, 3, -3, -3, -1},
+    /*L*/ {-1, -2, -3, -4, -1, -2, -3, -4, -3, 2, 4, -2, 2, 0, -3, -2, -1, -2, -1, 1, -4, -3, -1},
+    /*K*/ {-1, 2, 0, -1, -3, 1, 1, -2, -1, -3, -2, 5, -1, -3, -1, 0, -1, -3, -2, -2, 0, 1, -1},
+    /*M*/ {-1, -1, -2, -3, -1, 0, -2, -3, -2, 1, 2, -1, 5, 0, -2, -1, -1, -1, -1, 1, -3, -1, -1},
+    /*F*/ {-2, -3, -3, -3, -2, -3, -3, -3, -1, 0, 0, -3, 0, 6, -4, -2, -2, 1, 3, -1, -3, -3, -1},
+    /*P*/ {-1, -2, -2, -1, -3, -1, -1, -2, -2, -3, -3, -1, -2, -4, 7, -1, -1, -4, -3, -2, -2, -1, -2},
+    /*S*/ {1, -1, 1, 0, -1, 0, 0, 0, -1, -2, -2, 0, -1, -2, -1, 4, 1, -3, -2, -2, 0, 0, 0},
+    /*T*/ {0, -1, 0, -1, -1, -1, -1, -2, -2, -1, -1, -1, -1, -2, -1, 1, 5, -2, -2, 0, -1, -1, 0},
+    /*W*/ {-3, -3, -4, -4, -2, -2, -3, -2, -2, -3, -2, -3, -1, 1, -4, -3, -2, 11, 2, -3, -4, -3, -2},
+    /*Y*/ {-2, -2, -2, -3, -2, -1, -2, -3, 2, -1, -1, -2, -1, 3, -3, -2, -2, 2, 7, -1, -3, -2, -1},
+    /*V*/ {0, -3, -3, -3, -1, -2, -2, -3, -3, 3, 1, -2, 1, -1, -2, -2, 0, -3, -1, 4, -3, -2, -1},
+    /*B*/ {-2, -1, 3, 4, -3, 0, 1, -1, 0, -3, -4, 0, -3, -3, -2, 0, -1, -4, -3, -3, 4, 1, -1},
+    /*Z*/ {-1, 0, 0, 1, -3, 3, 4, -2, 0, -3, -3, 1, -1, -3, -1, 0, -1, -3, -2, -2, 1, 4, -1},
+    /*X*/ {0, -1, -1, -1, -2, -1, -1, -1, -1, -1, -1, -1, -1, -1, -2, 0, 0, -2, -1, -1, -1, -1, -1},
+};
+
+static int b62[256][256];
+static bool b62_ready = false;
+
+static void init_b62() {
+    if (b62_ready) return;
+    for (int i = 0; i < 256; i++)
+        for (int j = 0; j < 256; j++) b62[i][j] = -4;
+    for (int a = 0; a < 23; a++)
+        for (int b = 0; b < 23; b++) {
+            int A[2] = {B62_LETTERS[a], B62_LETTERS[a] + 32};
+            int B[2] = {B62_LETTERS[b], B62_LETTERS[b] + 32};
+            for (int x = 0; x < 2; x++)
+                for (int y = 0; y < 2; y++) b62[A[x]][B[y]] = B62_TABLE[a][b];
+        }
+    b62_ready = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// qsort / quicksort / partition / insort (fsearch.py:260-327; `_u` twins 189-256 are identical).
+// Rand.init_genrand(42) is executed on EVERY quicksort call, so random() always returns the
+// first MT19937 double of seed 42.
+// ---------------------------------------------------------------------------------------------
+static const double QS_RANDOM = 0.3745401188473625;
+
+template <class T, class K>
+static void insort(std::vector<T> &x, i64 l, i64 r, K key) {  // fsearch.py:266-277
+    for (i64 i = l; i < r; i++) {
+        T v = x[i];
+        i64 pivot = key(v);
+        i64 j = i - 1;
+        while (j >= l) {
+            if (key(x[j]) <= pivot) break;
+            x[j + 1] = x[j];
+            j--;
+        }
+        x[j + 1] = v;
+    }
+}
+
+template <class T, class K>
+static i64 partition(std::vector<T> &x, i64 l, i64 r, K key) {  // fsearch.py:281-297
+    i64 pivot = key(x[l]);
+    i64 i = l, j = r + 1;
+    while (true) {
+        i++;
+        while (i <= r && key(x[i]) < pivot) i++;
+        j--;
+        while (key(x[j]) > pivot) j--;
+        if (i > j) break;
+        std::swap(x[i], x[j]);
+    }
+    std::swap(x[l], x[j]);
+    return j;
+}
+
+template <class T, class K>
+static void quicksort(std::vector<T> &x, i64 l, i64 r, K key) {  // fsearch.py:302-321
+    if (r <= l) return;
+    i64 gap = r - l + 1;
+    i64 m;
+    if (gap < 7) {
+        insort(x, l, r + 1, key);
+        return;
+    } else if (gap == 7) {
+        m = l + gap / 2;
+    } else {
+        m = l + (i64)(QS_RANDOM * (double)gap);
+    }
+    std::swap(x[l], x[m]);
+    i64 med = partition(x, l, r, key);
+    quicksort(x, l, med - 1, key);
+    quicksort(x, med + 1, r, key);
+}
+
+template <class T, class K>
+static void qsort_ref(std::vector<T> &x, K key) {  // fsearch.py:326-327
+    quicksort(x, 0, (i64)x.size() - 1, key);
+}
+
+// ---------------------------------------------------------------------------------------------
+// score2bit, bit2e, f2s (fsearch.py:1066-1071, 1086, 43-61)
+// ---------------------------------------------------------------------------------------------
+static i64 score2bit(i64 score) {
+    double bit = (.267 * (double)score + 3.1941832122778293) / 0.69314718055994529;
+    return (i64)bit;
+}
+
+static std::string fmt6(double x) {  // RPython str(float) == '%.6f'
+    char buf[512];
+    snprintf(buf, sizeof buf, "%.6f", x);
+    return std::string(buf);
+}
+
+static std::string f2s(double e) {
+    if (e <= 0) return "0";
+    if (e < 1e-3) {
+        double a = log10(e);
+        a -= (double)(i64)a;
+        a = a < 0 ? 1 + a : a;          // `a < 0 and 1 + a or a` (1+a is never 0 here)
+        double b = pow(10, a);
+        std::string s = fmt6(log10(e / b));
+        size_t p = s.find('.');
+        s = s.substr(0, p == std::string::npos ? 0 : p);
+        std::string pp = fmt6(b);
+        size_t q = pp.find('.');
+        pp = pp.substr(0, q == std::string::npos ? 2 : q + 3);
+        return pp + "e" + s;
+    }
+    return fmt6(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// generate_nr_tbl (fsearch.py:406-422): identity on 0..511, each group letter (both cases) maps to
+// the minimum ASCII code of the (upper-cased) group.
+// ---------------------------------------------------------------------------------------------
+static std::vector<std::string> split(const std::string &s, char c) {
+    std::vector<std::string> out;
+    size_t st = 0;
+    while (true) {
+        size_t p = s.find(c, st);
+        if (p == std::string::npos) {
+            out.push_back(s.substr(st));
+            break;
+        }
+        out.push_back(s.substr(st, p - st));
+        st = p + 1;
+    }
+    return out;
+}
+
+static std::vector<int> generate_nr_tbl(const std::string &gaa) {
+    std::string up = gaa;
+    for (auto &c : up) c = (char)toupper((unsigned char)c);
+    std::vector<int> tbl(512);
+    for (int i = 0; i < 512; i++) tbl[i] = i;
+    for (const std::string &grp : split(up, ',')) {
+        int flag = 1024;
+        for (unsigned char c : grp)
+            if (c < flag) flag = c;
+        for (unsigned char c : grp) {
+            tbl[c] = flag;
+            tbl[(unsigned char)tolower(c)] = flag;
+        }
+    }
+    return tbl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// spseeds_fnv (fsearch.py:519-556): alphabet -> pattern -> position; whole-span x/X veto;
+// FNV-1a-32 over the care positions, then one more round with the pattern ordinal; % mod;
+// per-alphabet (bucket, pos) dedup.
+// ---------------------------------------------------------------------------------------------
+struct Seed {
+    uint32_t bucket;
+    int pos;
+};
+
+static void spseeds_fnv(const std::string &seq, int step, const std::vector<std::vector<int>> &codes,
+                        const std::vector<std::string> &spaces, uint32_t mod, std::vector<Seed> &out) {
+    out.clear();
+    i64 L = (i64)seq.size();
+    for (const auto &code : codes) {
+        std::unordered_map<uint64_t, char> visit;
+        const bool need_visit = spaces.size() > 1;  // one pattern: (bucket, i) cannot repeat
+        for (size_t s = 0; s < spaces.size(); s++) {
+            const std::string &space = spaces[s];
+            i64 k = (i64)space.size();
+            for (i64 i = 0; i < L - k + 1; i += step) {
+                bool seg = true;
+                uint32_t n = 0x811c9dc5u;
+                for (i64 j = 0; j < k; j++) {
+                    unsigned char ch = (unsigned char)seq[i + j];
+                    if (ch == 'x' || ch == 'X') {
+                        seg = false;
+                        break;
+                    } else if (space[j] != '0') {
+                        n ^= (uint32_t)code[ch];
+                        n *= 0x01000193u;
+                    }
+                }
+                n ^= (uint32_t)s;
+                n *= 0x01000193u;
+                uint32_t nmod = n % mod;
+                if (seg) {
+                    if (!need_visit) {
+                        out.push_back(Seed{nmod, (int)i});
+                        continue;
+                    }
+                    uint64_t key = ((uint64_t)nmod << 32) | (uint32_t)i;
+                    if (visit.find(key) == visit.end()) {
+                        visit[key] = 0;
+                        out.push_back(Seed{nmod, (int)i});
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// seg + entropy + Counter (fsearch.py:2872-2928, 2854-2868, 157-177)
+// ---------------------------------------------------------------------------------------------
+static std::string seg(const std::string &S) {
+    const double window = 12.;
+    const double minent = 2.2;
+    std::string s = S;
+    for (auto &c : s)
+        if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+    double log2v = log(2);
+    i64 n = (i64)s.size();
+    const int winsize = 12;
+    // entropy(s[:12]); Counter starts a new key at 0 and the loop adds every occurrence again
+    // => 2*occ-1; the entropy sum runs over the keys in first-appearance order.
+    double counts[256];
+    bool seen[256];
+    for (int i = 0; i < 256; i++) counts[i] = 0, seen[i] = false;
+    std::vector<int> order;
+    i64 wl = std::min<i64>(n, winsize);
+    for (i64 i = 0; i < wl; i++) {
+        unsigned char c = (unsigned char)s[i];
+        if (seen[c])
+            counts[c] += 1;
+        else {
+            seen[c] = true;
+            counts[c] = 0;
+            order.push_back(c);
+        }
+    }
+    for (i64 i = 0; i < wl; i++) counts[(unsigned char)s[i]] += 1.;
+    double nn = (double)wl * 1.;
+    double ent = 0;
+    for (int c : order) {
+        double freq = counts[c] / nn;
+        ent -= freq * log(freq);
+    }
+    ent /= log(2);
+
+    std::vector<char> mask((size_t)std::max<i64>(n, 1), 0);
+    if (ent < minent) mask[0] = 1;
+    for (i64 i = 1; i < n - winsize + 1; i++) {
+        unsigned char pre = (unsigned char)s[i - 1];
+        unsigned char cur = (unsigned char)s[i + 11];
+        if (pre == cur) {
+            mask[i] = mask[i - 1];
+            continue;
+        }
+        double pre_count = counts[pre];
+        counts[pre] -= 1;
+        double cur_count = seen[cur] ? counts[cur] : 0.0;
+        if (!seen[cur]) {
+            seen[cur] = true;
+            counts[cur] = 0;
+        }
+        counts[cur] += 1;
+        double a = pre_count / window, b = counts[pre] / window;
+        {
+            double Y = a * log(a) / log2v;
+            double add;
+            if (b != 0) {
+                double X = (a * log(a) - b * log(b)) / log2v;
+                add = (X != 0) ? X : Y;
+            } else
+                add = Y;
+            ent += add;
+        }
+        a = cur_count / window;
+        b = counts[cur] / window;
+        {
+            double Y = -b * log(b) / log2v;
+            double add;
+            if (a != 0) {
+                double X = (a * log(a) - b * log(b)) / log2v;
+                add = (X != 0) ? X : Y;
+            } else
+                add = Y;
+            ent += add;
+        }
+        if (ent < minent) mask[i] = 1;
+    }
+    i64 Nws = std::max<i64>(0, n - winsize);
+    if (n > 0 && mask[Nws] == 1)
+        for (i64 i = Nws; i < n; i++) mask[i] = 1;
+    std::string output;
+    i64 st = 0;
+    for (i64 i = 0; i < n; i++) {
+        if (st >= n) break;
+        if (mask[st] == 0) {
+            output += s[st];
+            st += 1;
+        } else {
+            output += "xxxxxxxxxxxx";
+            st += 12;
+        }
+    }
+    return output.substr(0, (size_t)n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// FASTA container (fsearch.py:1543-1553 `index`, 2180-2202 `Fasta`)
+// ---------------------------------------------------------------------------------------------
+struct Fasta {
+    std::string data;
+    std::vector<size_t> idx;
+    i64 N;
+    bool load(const char *fn) {
+        FILE *f = fopen(fn, "rb");
+        if (!f) return false;
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        data.resize((size_t)sz);
+        if (sz > 0 && fread(&data[0], 1, (size_t)sz, f) != (size_t)sz) {
+            fclose(f);
+            return false;
+        }
+        fclose(f);
+        idx.clear();
+        idx.push_back(0);
+        for (size_t i = 1; i < data.size(); i++)
+            if (data[i] == '>' && data[i - 1] == '\n') idx.push_back(i);
+        N = (i64)idx.size();
+        return true;
+    }
+    void get(i64 x, std::string &hd, std::string &sq) const {
+        hd.clear();
+        sq.clear();
+        if (x < 0) x += N;
+        if (!(0 <= x && x < N)) return;
+        size_t start = idx[(size_t)x];
+        size_t end = (x == N - 1) ? data.size() : idx[(size_t)x + 1];
+        size_t p = data.find('\n', start);
+        if (p == std::string::npos || p >= end) {
+            if (end > start) hd = data.substr(start + 1, end - start - 1);
+            return;
+        }
+        hd = data.substr(start + 1, p - start - 1);
+        sq.reserve(end - p);
+        for (size_t i = p + 1; i < end; i++)
+            if (data[i] != '\n') sq += data[i];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// kswat_st (fsearch.py:1357-1476): banded single-matrix local alignment with trace-state gap
+// costs, traceback and statistics.  The score/trace matrices are shared between calls, exactly
+// like score_mat / trace_mat of blastp (fsearch.py:2982-2983).
+// ---------------------------------------------------------------------------------------------
+struct Matrices {
+    int dim;
+    std::vector<int> score;
+    std::vector<char> trace;
+    explicit Matrices(int d = 4100) : dim(d), score((size_t)d * d, 0), trace((size_t)d * d, '*') {}
+    int &S(i64 i, i64 j) { return score[(size_t)i * dim + j]; }
+    char &T(i64 i, i64 j) { return trace[(size_t)i * dim + j]; }
+};
+
+struct Aln {
+    double idy;
+    i64 AL, mis, gap, qst, qed, sst, sed, bit, raw;
+    std::string al0, al1;
+};
+
+static Aln kswat_st(const std::string &S0, const std::string &S1, i64 qst, i64 sst, Matrices &mat) {
+    const i64 go = -11, ge = -1, kbound = 16;
+    i64 qed = -1, sed = -1;
+    qst = std::min<i64>(std::max<i64>(qst, 0), (i64)S0.size());
+    // `qed < 0 and len(S0) or qed`: an EMPTY S0 leaves qed at -1
+    qed = (qed < 0 && S0.size() != 0) ? (i64)S0.size() : qed;
+    sst = std::min<i64>(std::max<i64>(sst, 0), (i64)S1.size());
+    sed = (sed < 0 && S1.size() != 0) ? (i64)S1.size() : sed;
+    const std::string *s0, *s1;
+    bool swap;
+    if (std::llabs(qed - qst) < std::llabs(sed - sst)) {
+        s0 = &S0, s1 = &S1, swap = false;
+    } else {
+        s0 = &S1, s1 = &S0, swap = true;
+        std::swap(qst, sst);
+        std::swap(qed, sed);
+    }
+    i64 qsp = qst < qed ? 1 : -1;
+    i64 ssp = sst < sed ? 1 : -1;
+    i64 l0 = std::llabs(qed - qst) + 1;
+    i64 l1 = std::llabs(sed - sst) + 1;
+    for (i64 i = 1; i < l0; i++) mat.S(0, i) = 0, mat.T(0, i) = '-';
+    for (i64 i = 1; i < l1; i++) {
+        mat.S(i, 0) = 0;
+        mat.T(i, 0) = '|';
+        i64 start = std::max<i64>(0, i - kbound - 1), end = std::min<i64>(i + kbound + 1, l0 - 1);
+        mat.T(i, start) = '|';
+        mat.T(i, end) = '-';
+        mat.S(i, start) = 0;
+        mat.S(i, end) = 0;
+    }
+    i64 i_max = 0, j_max = 0, maxscore = 0;
+    for (i64 i = 1; i < l1; i++) {
+        i64 start = std::max<i64>(1, i - kbound), end = std::min<i64>(i + kbound, l0);
+        for (i64 j = start; j < end; j++) {
+            i64 I = mat.S(i, j - 1) + (mat.T(i, j - 1) == '-' ? ge : go);
+            unsigned char c1 = (unsigned char)(*s1)[(size_t)((i - 1) * ssp + sst)];
+            unsigned char c0 = (unsigned char)(*s0)[(size_t)((j - 1) * qsp + qst)];
+            i64 M = mat.S(i - 1, j - 1) + b62[c1][c0];
+            i64 D = mat.S(i - 1, j) + (mat.T(i - 1, j) == '|' ? ge : go);
+            i64 B = 0;
+            if (I > B) B = I;
+            if (M > B) B = M;
+            if (D > B) B = D;
+            mat.S(i, j) = (int)B;
+            if (B > maxscore) i_max = i, j_max = j, maxscore = B;
+            if (B == M)
+                mat.T(i, j) = '\\';
+            else if (B == I)
+                mat.T(i, j) = '-';
+            else if (B == D)
+                mat.T(i, j) = '|';
+            else
+                mat.T(i, j) = '*';
+        }
+    }
+    Aln r;
+    i64 i = i_max, j = j_max;
+    while (i > 0 || j > 0) {
+        char t = mat.T(i, j);
+        if (t == '\\') {
+            r.al0 += (*s0)[(size_t)((j - 1) * qsp + qst)];
+            r.al1 += (*s1)[(size_t)((i - 1) * ssp + sst)];
+            i--, j--;
+        } else if (t == '-') {
+            r.al0 += (*s0)[(size_t)((j - 1) * qsp + qst)];
+            r.al1 += '-';
+            j--;
+        } else if (t == '|') {
+            r.al1 += (*s1)[(size_t)((i - 1) * ssp + sst)];
+            r.al0 += '-';
+            i--;
+        } else
+            break;
+    }
+    if (qst < qed)
+        std::reverse(r.al0.begin(), r.al0.end());
+    else
+        std::swap(i, i_max);
+    if (sst < sed)
+        std::reverse(r.al1.begin(), r.al1.end());
+    else
+        std::swap(j, j_max);
+    i64 AL = (i64)r.al0.size();
+    double idy = 0;
+    i64 mis = 0, gap = 0;
+    int op = -1;
+    for (i64 k = 0; k < AL; k++) {
+        if (r.al0[k] == r.al1[k])
+            idy += 1.;
+        else
+            mis += 1;
+        if (r.al0[k] == '-' && op != 0)
+            gap += 1, op = 0;
+        else if (r.al1[k] == '-' && op != 1)
+            gap += 1, op = 1;
+        else
+            op = -1;
+    }
+    idy = AL ? idy * (100. / (double)AL) : NAN;
+    r.idy = idy, r.AL = AL, r.mis = mis, r.gap = gap, r.raw = maxscore, r.bit = score2bit(maxscore);
+    if (swap) {
+        r.qst = i * ssp + sst, r.qed = i_max * ssp + sst, r.sst = j * qsp + qst, r.sed = j_max * qsp + qst;
+        std::swap(r.al0, r.al1);  // the reference swaps the output lists so al0 is always the query side
+    } else {
+        r.qst = j * qsp + qst, r.qed = j_max * qsp + qst, r.sst = i * qsp + sst, r.sed = i_max * qsp + sst;
+    }
+    return r;
+}
+
+// kswat_st_long (fsearch.py:1480-1498): 4096-tiles marching down the diagonal, one row per tile.
+// A tile whose target slice is empty indexes an empty string in the reference (undefined in the
+// translated binary, IndexError under CPython); this restatement defines it as "tile skipped".
+static std::vector<Aln> kswat_st_long(const std::string &sqi, const std::string &sqj, i64 qi, i64 qj,
+                                      Matrices &mat) {
+    std::vector<Aln> out;
+    const i64 chk = 4096;
+    i64 li = (i64)sqi.size();
+    i64 j = qj;
+    for (i64 i0 = qi; i0 < li; i0 += chk) {
+        i64 i = std::max<i64>(0, i0), ied = std::max<i64>(0, i0 + chk);
+        j = std::max<i64>(0, j);
+        i64 jed = std::max<i64>(0, j + chk);
+        std::string a = i < (i64)sqi.size() ? sqi.substr((size_t)i, (size_t)(ied - i)) : std::string();
+        std::string b = j < (i64)sqj.size() ? sqj.substr((size_t)j, (size_t)(jed - j)) : std::string();
+        if (!a.empty() && !b.empty()) {
+            Aln r = kswat_st(a, b, 0, 0, mat);
+            r.qst += i, r.qed += i, r.sst += j, r.sed += j;
+            out.push_back(r);
+        }
+        j += chk;
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Target chunk index: Fasta.build_msav (fsearch.py:2208-2280), get_mu_sd (746-761),
+// get_bin_mem (2530-2541), get_locs_m (2638-2642), bisect (134-153)
+// ---------------------------------------------------------------------------------------------
+struct Params {
+    std::vector<std::vector<int>> codes;
+    std::vector<std::string> spaces;
+    int mink;
+    uint32_t NC;
+    int step;
+};
+
+struct ChunkIndex {
+    i64 offset, offend;
+    std::vector<uint32_t> start, locus, soas;
+    i64 L;
+    i64 threshold;
+    std::vector<std::string> hd, sq;  // hdseqs: records offset..offend-1 (one extra record)
+
+    void build(const Fasta &db, const Params &P, i64 start_, i64 end_) {
+        offset = start_;
+        offend = end_ + 1;
+        i64 s = std::min<i64>(std::max<i64>(0, start_), db.N);
+        i64 e = std::min<i64>(end_ < 0 ? db.N : end_, db.N);
+        i64 M = e - s;
+        start.assign(P.NC, 0);
+        soas.assign((size_t)M + 1, 0);
+        std::vector<Seed> seeds;
+        std::string h, q;
+        for (i64 i = s; i < e; i++) {
+            db.get(i, h, q);
+            i64 j = i - s;
+            soas[(size_t)j + 1] = (uint32_t)(soas[(size_t)j] + q.size());
+            spseeds_fnv(q, P.step, P.codes, P.spaces, P.NC, seeds);
+            for (const Seed &sd : seeds) start[sd.bucket] += 1;
+        }
+        // get_mu_sd: N starts at 1; sequential float64 in bucket order
+        {
+            double N = 1, mu = 0.;
+            for (uint32_t c : start)
+                if (c > 0) mu += (double)c, N += 1;
+            mu /= N;
+            double sd = 0.;
+            for (uint32_t c : start)
+                if (c > 0) sd += pow((double)c - mu, 2);
+            sd = sqrt(sd / N);
+            threshold = (i64)(mu + 2 * sd);
+        }
+        for (size_t i = 1; i < start.size(); i++) start[i] = start[i - 1] + start[i];
+        locus.assign(start[start.size() - 1], 0);
+        for (i64 i = s; i < e; i++) {
+            db.get(i, h, q);
+            i64 j = i - s;
+            uint32_t off = soas[(size_t)j];
+            spseeds_fnv(q, P.step, P.codes, P.spaces, P.NC, seeds);
+            for (const Seed &sd : seeds) {
+                start[sd.bucket] -= 1;
+                locus[start[sd.bucket]] = (uint32_t)sd.pos + off;
+            }
+        }
+        L = (i64)locus.size() - 1;
+        hd.clear();
+        sq.clear();
+        for (i64 x = offset; x < offend; x++) {
+            db.get(x >= db.N ? db.N + 1 : x, h, q);  // out of range -> ['', '']
+            hd.push_back(h);
+            sq.push_back(q);
+        }
+    }
+
+    void get_bin_mem(i64 i, i64 &st, i64 &ed) const {
+        i = i > 0 ? i : 0;
+        i64 a, b;
+        if ((size_t)i + 1 < start.size())
+            a = start[(size_t)i], b = start[(size_t)i + 1];
+        else
+            a = b = start[(size_t)i];
+        st = std::max<i64>(a, 0);
+        ed = std::min<i64>(std::max<i64>(b, 0), L);
+    }
+
+    // bisect(self.soas, x) with l=-1: `l < 0 and 0 or l` evaluates to -1
+    i64 bisect(i64 x) const {
+        i64 l = -1, r = (i64)soas.size();
+        while (r - l > 1) {
+            i64 m = (l + r) >> 1;  // floor division; l+r >= 0 whenever the loop runs
+            if ((i64)soas[(size_t)m] < x)
+                l = m;
+            else
+                r = m;
+        }
+        return l;
+    }
+
+    const std::string &get_seq(i64 hdx) const {  // get_hdseq(i)[1] with python negative indexing
+        i64 k = hdx - offset;
+        if (k < 0) k += (i64)sq.size();
+        return sq[(size_t)k];
+    }
+};
+
+// ungap (fsearch.py:2454-2494)
+struct Ungap {
+    i64 score, qst, qed, sst, sed;
+};
+static Ungap ungap(const std::string &qseq, const std::string &sseq, i64 Qst, i64 Sst, i64 qlo = -1,
+                   i64 slo = -1) {
+    const i64 dropX = 30;
+    qlo = qlo > -1 ? qlo : 0;
+    slo = slo > -1 ? slo : 0;
+    i64 ql = (i64)qseq.size(), sl = (i64)sseq.size();
+    i64 qup = ql, sup = sl;
+    i64 off = std::max<i64>(std::max<i64>(qlo - Qst, slo - Sst), 0);
+    Qst += off;
+    Sst += off;
+    i64 qst = Qst, sst = Sst;
+    i64 score = 0, max_score = 0, max_qed = qst, max_sed = sst;
+    while (qlo < qst && qst < qup && slo < sst && sst < sup) {
+        score += b62[(unsigned char)qseq[(size_t)qst]][(unsigned char)sseq[(size_t)sst]];
+        if (score > max_score)
+            max_score = score, max_qed = qst, max_sed = sst;
+        else if (score + dropX < max_score)
+            break;
+        qst++, sst++;
+    }
+    qst = Qst - 1, sst = Sst - 1;
+    score = max_score;
+    i64 max_qst = qst, max_sst = sst;
+    while (qup > qst && qst > qlo && sup > sst && sst > slo) {
+        score += b62[(unsigned char)qseq[(size_t)qst]][(unsigned char)sseq[(size_t)sst]];
+        if (score > max_score)
+            max_score = score, max_qst = qst, max_sst = sst;
+        else if (score + dropX < max_score)
+            break;
+        qst--, sst--;
+    }
+    return Ungap{max_score, max_qst, max_qed, max_sst, max_sed};
+}
+
+struct Cand {
+    uint32_t hd, score, qi, qj;
+};
+
+// find_msav_m (fsearch.py:2645-2724) with sort=False
+struct Searcher {
+    // ordered dict (hd, diag) -> list of [qst, sst]
+    std::unordered_map<uint64_t, uint32_t> key2grp;
+    std::vector<uint64_t> grp_key;
+    std::vector<std::vector<int>> grp_qst;
+
+    void find(const ChunkIndex &ix, const Params &P, const std::string &seq, std::vector<Cand> &out,
+              i64 *n_seedhits = nullptr, i64 *n_groups = nullptr) {
+        out.clear();
+        i64 ql = (i64)seq.size();
+        if (ql < P.mink) return;  // reference: out-of-bounds; defined here as "no hits"
+        std::vector<i64> kscs((size_t)(ql - P.mink + 1), 0);
+        i64 sc = 0;
+        for (int i = 0; i < P.mink; i++) {
+            unsigned char c = (unsigned char)seq[(size_t)i];
+            sc += b62[c][c];
+        }
+        kscs[0] = sc;
+        for (i64 i = 1; i < ql - P.mink + 1; i++) {
+            unsigned char c0 = (unsigned char)seq[(size_t)i - 1], c1 = (unsigned char)seq[(size_t)(i - 1 + P.mink)];
+            kscs[(size_t)i] = kscs[(size_t)i - 1] - b62[c0][c0] + b62[c1][c1];
+        }
+        std::vector<Seed> s2a;
+        spseeds_fnv(seq, 1, P.codes, P.spaces, P.NC, s2a);
+        struct H {
+            i64 ksc, qst, ct;
+        };
+        std::vector<H> hist(kscs.size());
+        for (size_t q = 0; q < kscs.size(); q++) hist[q] = H{kscs[q], (i64)q, 0};
+        for (const Seed &sd : s2a) {
+            i64 st, ed;
+            ix.get_bin_mem(sd.bucket, st, ed);
+            i64 count = ed - st;
+            hist[(size_t)sd.pos].ct += (count > 0 ? count : 0);
+        }
+        i64 thr = ix.threshold * ql;
+        qsort_ref(hist, [](const H &h) { return -h.ksc; });
+        std::vector<int> hist_c((size_t)ql, -1);
+        i64 cum = 0;
+        for (size_t i = 0; i < hist.size(); i++) {
+            if (cum > thr) break;
+            cum += hist[i].ct;
+            hist_c[(size_t)hist[i].qst] = 1;
+        }
+        key2grp.clear();
+        grp_key.clear();
+        size_t ngrp = 0;
+        i64 nhits = 0;
+        for (const Seed &sd : s2a) {
+            i64 st, ed;
+            ix.get_bin_mem(sd.bucket, st, ed);
+            if (hist_c[(size_t)sd.pos] > 0) {
+                for (i64 p = st; p < ed; p++) {
+                    i64 x = (i64)ix.locus[(size_t)p];
+                    i64 idx = ix.bisect(x);
+                    i64 hd = idx + ix.offset;
+                    i64 sst = x - (i64)(idx < 0 ? ix.soas[ix.soas.size() + idx] : ix.soas[(size_t)idx]);
+                    i64 k0 = sd.pos - sst;
+                    uint64_t key = ((uint64_t)(uint32_t)(int32_t)hd << 32) | (uint32_t)(int32_t)k0;
+                    auto it = key2grp.find(key);
+                    uint32_t g;
+                    if (it == key2grp.end()) {
+                        g = (uint32_t)ngrp++;
+                        key2grp.emplace(key, g);
+                        grp_key.push_back(key);
+                        if (grp_qst.size() < ngrp) grp_qst.emplace_back();
+                        grp_qst[g].clear();
+                    } else
+                        g = it->second;
+                    grp_qst[g].push_back(sd.pos);
+                    nhits++;
+                }
+            }
+        }
+        if (n_seedhits) *n_seedhits += nhits;
+        if (n_groups) *n_groups += (i64)ngrp;
+        // per (hd, diag) in dict order
+        std::unordered_map<int32_t, uint32_t> sc_idx;  // Scores dict: hd -> position in out
+        struct Best {
+            i64 score, qst, sst, qed, sed;
+        };
+        std::vector<Best> best;
+        std::vector<int32_t> hd_order;
+        std::vector<std::pair<i64, i64>> loc0, loc1;
+        for (size_t g = 0; g < ngrp; g++) {
+            int32_t hd = (int32_t)(uint32_t)(grp_key[g] >> 32);
+            int32_t k0 = (int32_t)(uint32_t)(grp_key[g] & 0xffffffffu);
+            const std::string &sseq = ix.get_seq(hd);
+            loc0.clear();
+            for (int q : grp_qst[g]) loc0.push_back(std::make_pair((i64)q, (i64)q - k0));
+            qsort_ref(loc0, [](const std::pair<i64, i64> &p) { return p.first; });
+            // lis(loc0, key = sst) (fsearch.py:688-724): on one diagonal the input is non-decreasing,
+            // the strictly increasing subsequence is the list of distinct points.
+            loc1.clear();
+            for (const auto &p : loc0)
+                if (loc1.empty() || loc1.back().second < p.second) loc1.push_back(p);
+            // get_ungap_scores (fsearch.py:2497-2509)
+            Ungap u = ungap(seq, sseq, loc1[0].first, loc1[0].second);
+            i64 scores = u.score, x0 = u.qst, y0 = u.sst, x = u.qed, y = u.sed;
+            for (size_t k = 1; k < loc1.size(); k++) {
+                Ungap v = ungap(seq, sseq, loc1[k].first, loc1[k].second, x, y);
+                x = v.qed, y = v.sed;
+                scores += v.score;
+            }
+            if (scores < 25) continue;
+            auto it = sc_idx.find(hd);
+            if (it == sc_idx.end()) {
+                sc_idx.emplace(hd, (uint32_t)best.size());
+                best.push_back(Best{scores, x0, y0, x, y});
+                hd_order.push_back(hd);
+            } else if (scores > best[it->second].score) {
+                best[it->second] = Best{scores, x0, y0, x, y};
+            }
+        }
+        for (size_t k = 0; k < best.size(); k++) {
+            // guess_start (fsearch.py:2544-2553) over the two points [qst,sst],[qed,sed]
+            i64 dist = (best[k].sst - best[k].qst) + (best[k].sed - best[k].qed);
+            dist = (dist >= 0) ? dist / 2 : -((-dist + 1) / 2);  // python floor division by 2
+            i64 qi, qj;
+            if (dist > 0)
+                qi = 0, qj = dist;
+            else
+                qi = -dist, qj = 0;
+            out.push_back(Cand{(uint32_t)hd_order[k], (uint32_t)best[k].score, (uint32_t)qi, (uint32_t)qj});
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// blastp (fsearch.py:2968-3121) + row formatting of entry_point (fsearch.py:3231-3256)
+// ---------------------------------------------------------------------------------------------
+struct Options {
+    std::string qry, ref, out, ssd = "111111", nr = "AST,CFILMVY,DN,EQ,G,H,KR,P,W", flt = "T", wrt = "wb";
+    double expect = 1e-3, max_miss = 1e-3;
+    i64 v = 500, st = -1, ed = -1, rst = -1, red = -1, thr = -1, step = 4, ht = -1, chk = 50000;
+};
+
+struct Stats {
+    i64 queries = 0, seed_hits = 0, groups = 0, candidates = 0, alignments = 0, dp_cells = 0, rows = 0;
+};
+
+struct Row {
+    i64 i, j, li, lj;
+    std::string hi, hj;
+    double idy;
+    i64 aln, mis, gap, qst, qed, sst, sed;
+    double e;
+    i64 bit;
+    std::string desc;
+};
+
+static i64 dp_cells(i64 qrem, i64 trem) {
+    // cells the reference fills: rows i=1..l1-1, cols [max(1,i-16), min(i+16,l0))
+    i64 l0, l1;
+    if (qrem < trem)
+        l0 = qrem + 1, l1 = trem + 1;
+    else
+        l0 = trem + 1, l1 = qrem + 1;
+    i64 c = 0;
+    for (i64 i = 1; i < l1; i++) {
+        i64 a = std::max<i64>(1, i - 16), b = std::min<i64>(i + 16, l0);
+        if (b > a) c += b - a;
+    }
+    return c;
+}
+
+static std::string format_row(const Row &r) {
+    std::string Idy = std::isnan(r.idy) ? std::string("nan") : fmt6(r.idy);
+    size_t p = Idy.find('.');
+    Idy = Idy.substr(0, p == std::string::npos ? 2 : p + 3);
+    char buf[256];
+    std::string s = r.hi + "\t" + r.hj + "\t" + Idy + "\t";
+    snprintf(buf, sizeof buf, "%lld\t%lld\t%lld\t%lld\t%lld\t%lld\t%lld\t", r.aln, r.mis, r.gap, r.qst, r.qed,
+             r.sst, r.sed);
+    s += buf;
+    s += f2s(r.e);
+    snprintf(buf, sizeof buf, "\t%lld\t%lld\t%lld\t%lld\t", r.bit, r.li, r.lj, r.i);
+    s += buf;
+    s += r.desc;
+    s += "\n";
+    return s;
+}
+
+static int blastp(const Options &o, Stats *stats) {
+    init_b62();
+    Fasta seqs, DB;
+    if (!seqs.load(o.qry.c_str()) || !DB.load(o.ref.c_str())) return 2;
+    i64 N = seqs.N, D = DB.N;
+    double max_miss = std::max(o.max_miss, 1e-3);
+    i64 st = std::min<i64>(std::max<i64>(0, o.st), N);
+    i64 ed = std::min<i64>(o.ed < 0 ? D : o.ed, N);
+    Params P;
+    for (const std::string &a : split(o.nr, '/')) P.codes.push_back(generate_nr_tbl(a));
+    P.spaces = split(o.ssd, ',');
+    P.mink = 1 << 30;
+    for (const auto &s : P.spaces) P.mink = std::min<int>(P.mink, (int)s.size());
+    P.NC = (uint32_t)o.ht;
+    P.step = (int)o.step;
+    Matrices mat(4100);
+
+    std::vector<std::vector<Cand>> kdb((size_t)std::max<i64>(ed - st, 0));
+    std::vector<std::string> masked((size_t)std::max<i64>(ed - st, 0));
+    Searcher S;
+    std::vector<Cand> cands;
+    std::string hdi, Sqi;
+    i64 Start = o.rst == -1 ? 0 : o.rst, End = o.red == -1 ? D : o.red;
+    ChunkIndex ix;
+    i64 last_threshold = 0;
+    for (i64 c = Start; c < End; c += o.chk) {
+        ix.build(DB, P, c, std::min<i64>(c + o.chk, End));
+        // `thr < 1 and DB.threshold or thr`
+        if (!(o.thr < 1 && ix.threshold != 0)) ix.threshold = o.thr;
+        last_threshold = ix.threshold;
+        for (i64 i = st; i < ed; i++) {
+            seqs.get(i, hdi, Sqi);
+            std::string sqi = (o.flt == "T") ? seg(Sqi) : Sqi;
+            if (c == Start) masked[(size_t)(i - st)] = sqi;
+            S.find(ix, P, sqi, cands, stats ? &stats->seed_hits : nullptr, stats ? &stats->groups : nullptr);
+            auto &dst = kdb[(size_t)(i - st)];
+            dst.insert(dst.end(), cands.begin(), cands.end());
+        }
+    }
+    (void)last_threshold;
+
+    FILE *fo = o.out.empty() ? nullptr : fopen(o.out.c_str(), o.wrt.find('a') != std::string::npos ? "a" : "w");
+    std::string hdj, sqj;
+    for (i64 i = st; i < ed; i++) {
+        seqs.get(i, hdi, Sqi);
+        const std::string &sqi = masked[(size_t)(i - st)];
+        std::vector<Cand> &hits = kdb[(size_t)(i - st)];
+        i64 li = (i64)sqi.size();
+        qsort_ref(hits, [](const Cand &c) { return -(i64)c.score; });
+        double mmiss = (double)hits.size() * max_miss + 1;
+        mmiss = std::max(mmiss, 100. / mmiss);
+        mmiss = std::min(std::max(mmiss, 10.), 120.);
+        i64 unmch = 0, bv = 0;
+        double vmaxf = std::max(100., std::max((double)(o.v + 100), (double)o.v * 1.1));
+        i64 vmax = (i64)vmaxf;
+        std::vector<Row> m8s;
+        std::string hi = hdi.substr(0, hdi.find(' '));
+        if (stats) stats->queries++, stats->candidates += (i64)hits.size();
+        for (i64 h = 0; h < std::min<i64>(vmax, (i64)hits.size()); h++) {
+            const Cand &c = hits[(size_t)h];
+            DB.get((i64)c.hd, hdj, sqj);
+            i64 lj = (i64)sqj.size();
+            std::string hj = hdj.substr(0, hdj.find(' '));
+            if (li < 4096 && lj < 4096) {
+                Aln a = kswat_st(sqi, sqj, c.qi, c.qj, mat);
+                if (stats) {
+                    stats->alignments++;
+                    i64 qs = std::min<i64>(c.qi, li), ts = std::min<i64>(c.qj, lj);
+                    stats->dp_cells += dp_cells(li - qs, lj - ts);
+                }
+                double e = (double)(D * li * lj) * pow(2, -(double)a.bit);
+                if (e <= o.expect) {
+                    m8s.push_back(Row{i, (i64)c.hd, li, lj, hi, hj, a.idy, a.AL, a.mis, a.gap, a.qst + 1, a.qed,
+                                      a.sst + 1, a.sed, e, a.bit, hdj});
+                    unmch = 0;
+                    bv++;
+                } else
+                    unmch++;
+            } else {
+                int flag = 1;
+                for (const Aln &a : kswat_st_long(sqi, sqj, c.qi, c.qj, mat)) {
+                    if (stats) stats->alignments++;
+                    double e = (double)(D * li * lj) * pow(2, -(double)a.bit);
+                    if (e <= o.expect) {
+                        m8s.push_back(Row{i, (i64)c.hd, li, lj, hi, hj, a.idy, a.AL, a.mis, a.gap, a.qst + 1,
+                                          a.qed, a.sst + 1, a.sed, e, a.bit, hdj});
+                        flag = 0;
+                        bv++;
+                    }
+                }
+                if (flag == 1)
+                    unmch++;
+                else
+                    unmch = 0;
+            }
+            if ((double)unmch >= mmiss || (double)bv >= (double)o.v + mmiss) break;
+        }
+        qsort_ref(m8s, [](const Row &r) { return -r.bit; });
+        i64 lim = std::min<i64>(std::max<i64>(0, o.v), (i64)m8s.size());
+        for (i64 k = 0; k < lim; k++) {
+            if (m8s[(size_t)k].e <= o.expect) {
+                std::string line = format_row(m8s[(size_t)k]);
+                if (fo)
+                    fputs(line.c_str(), fo);
+                else
+                    fputs(line.c_str(), stdout);
+                if (stats) stats->rows++;
+            }
+        }
+        std::vector<Cand>().swap(hits);
+    }
+    if (fo) fclose(fo);
+    return 0;
+}
+
+}  // namespace orc
+
+// =============================================================================================
+// C entry points (ctypes) for function-level known-answer tests, and the fsearch-c-like CLI.
+// =============================================================================================
+extern "C" {
+
+// kswat_st(S0, S1, qst, sst) with fresh matrices. out[9] = AL, mis, gap, qst, qed, sst, sed, bit, raw;
+// returns identity (percent).
+double orc_kswat_st(const char *s0, int l0, const char *s1, int l1, int qst, int sst, long long *out) {
+    orc::init_b62();
+    static orc::Matrices *mat = nullptr;
+    if (!mat) mat = new orc::Matrices(4100);
+    orc::Aln a = orc::kswat_st(std::string(s0, (size_t)l0), std::string(s1, (size_t)l1), qst, sst, *mat);
+    out[0] = a.AL, out[1] = a.mis, out[2] = a.gap, out[3] = a.qst, out[4] = a.qed, out[5] = a.sst, out[6] = a.sed;
+    out[7] = a.bit, out[8] = a.raw;
+    return a.idy;
+}
+
+// ungap(q, s, Qst, Sst, qlo, slo): out[5] = score, qst, qed, sst, sed
+void orc_ungap(const char *q, int ql, const char *s, int sl, int Qst, int Sst, int qlo, int slo, long long *out) {
+    orc::init_b62();
+    orc::Ungap u = orc::ungap(std::string(q, (size_t)ql), std::string(s, (size_t)sl), Qst, Sst, qlo, slo);
+    out[0] = u.score, out[1] = u.qst, out[2] = u.qed, out[3] = u.sst, out[4] = u.sed;
+}
+
+void orc_seg(const char *s, int n, char *out) {
+    std::string r = orc::seg(std::string(s, (size_t)n));
+    memcpy(out, r.data(), r.size());
+}
+
+long long orc_score2bit(long long score) { return orc::score2bit(score); }
+
+void orc_f2s(double e, char *out, int cap) {
+    std::string s = orc::f2s(e);
+    snprintf(out, (size_t)cap, "%s", s.c_str());
+}
+
+int orc_b62(int a, int b) {
+    orc::init_b62();
+    return orc::b62[a & 255][b & 255];
+}
+
+// the reference quicksort applied to keys[n] (ascending by key); perm receives the final order of
+// the original indices.
+void orc_qsort_perm(const long long *keys, int n, int *perm) {
+    std::vector<std::pair<long long, int>> v((size_t)n);
+    for (int i = 0; i < n; i++) v[(size_t)i] = std::make_pair(keys[i], i);
+    orc::qsort_ref(v, [](const std::pair<long long, int> &p) { return p.first; });
+    for (int i = 0; i < n; i++) perm[i] = v[(size_t)i].second;
+}
+
+// spseeds_fnv: returns number of seeds; buckets/pos sized by caller (>= len * patterns * alphabets)
+int orc_spseeds(const char *seq, int n, int step, const char *nr, const char *ssd, unsigned mod, unsigned *buckets,
+                int *pos) {
+    std::vector<std::vector<int>> codes;
+    for (const std::string &a : orc::split(nr, '/')) codes.push_back(orc::generate_nr_tbl(a));
+    std::vector<orc::Seed> out;
+    orc::spseeds_fnv(std::string(seq, (size_t)n), step, codes, orc::split(ssd, ','), mod, out);
+    for (size_t i = 0; i < out.size(); i++) buckets[i] = out[i].bucket, pos[i] = out[i].pos;
+    return (int)out.size();
+}
+
+// Full search.  stats[7] = queries, seed_hits, groups, candidates, alignments, dp_cells, rows
+int orc_blastp(const char *qry, const char *ref, const char *out, double expect, long long v, double max_miss,
+               long long st, long long ed, long long rst, long long red, long long thr, const char *flt,
+               const char *ssd, const char *nr, long long step, long long ht, long long chk, const char *wrt,
+               long long *stats) {
+    orc::Options o;
+    o.qry = qry, o.ref = ref, o.out = out, o.expect = expect, o.v = v, o.max_miss = max_miss, o.st = st, o.ed = ed;
+    o.rst = rst, o.red = red, o.thr = thr, o.flt = flt, o.ssd = ssd, o.nr = nr, o.step = step, o.ht = ht, o.chk = chk;
+    o.wrt = wrt;
+    orc::Stats s;
+    int rc = orc::blastp(o, &s);
+    if (stats) {
+        stats[0] = s.queries, stats[1] = s.seed_hits, stats[2] = s.groups, stats[3] = s.candidates;
+        stats[4] = s.alignments, stats[5] = s.dp_cells, stats[6] = s.rows;
+    }
+    return rc;
+}
+}
+
+#ifdef ORC_MAIN
+// fsearch-c command line (fsearch.py:3152-3264): same flag letters and defaults.
+int main(int argc, char **argv) {
+    std::unordered_map<std::string, std::string> args = {
+        {"-p", ""}, {"-v", "500"}, {"-s", "111111"}, {"-i", ""}, {"-d", ""}, {"-e", "1e-3"}, {"-l", "-1"},
+        {"-u", "-1"}, {"-m", "1e-3"}, {"-t", "-1"}, {"-r", "AST,CFILMVY,DN,EQ,G,H,KR,P,W"}, {"-j", "4"},
+        {"-F", "T"}, {"-o", ""}, {"-D", ""}, {"-O", "wb"}, {"-L", "-1"}, {"-U", "-1"}, {"-M", "-1"},
+        {"-c", "50000"}, {"-T", "./tmpdir"}};
+    for (int i = 1; i < argc; i++) {
+        std::string k = argv[i];
+        if (args.count(k)) {
+            if (i + 1 < argc) args[k] = argv[i + 1];
+        } else if (k.size() > 2 && args.count(k.substr(0, 2)))
+            args[k.substr(0, 2)] = k.substr(2);
+    }
+    if (args["-p"] != "blastp" || args["-i"].empty() || args["-d"].empty()) {
+        fprintf(stderr, "Usage: fsearch_oracle -p blastp -i qry.fsa -d db.fsa [-o out] ...\n");
+        return 0;
+    }
+    orc::Options o;
+    o.qry = args["-i"], o.ref = args["-d"], o.out = args["-o"], o.expect = atof(args["-e"].c_str());
+    o.v = atoll(args["-v"].c_str()), o.max_miss = atof(args["-m"].c_str()), o.st = atoll(args["-l"].c_str());
+    o.ed = atoll(args["-u"].c_str()), o.rst = atoll(args["-L"].c_str()), o.red = atoll(args["-U"].c_str());
+    o.thr = atoll(args["-t"].c_str()), o.flt = args["-F"], o.ssd = args["-s"], o.nr = args["-r"];
+    o.step = atoll(args["-j"].c_str()), o.ht = atoll(args["-M"].c_str()), o.chk = atoll(args["-c"].c_str());
+    o.wrt = args["-O"];
+    orc::Stats s;
+    int rc = orc::blastp(o, &s);
+    fprintf(stderr,
+            "oracle stats: queries=%lld seed_hits=%lld groups=%lld candidates=%lld alignments=%lld dp_cells=%lld "
+            "rows=%lld\n",
+            s.queries, s.seed_hits, s.groups, s.candidates, s.alignments, s.dp_cells, s.rows);
+    return rc;
+}
+#endif

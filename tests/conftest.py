@@ -1,0 +1,121 @@
+import ctypes
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+def build_oracle():
+    """Compile oracle/fsearch_oracle.cpp (the checker) if it is not built yet."""
+    so = os.path.join(ROOT, 'oracle', '_build', 'liboracle.so')
+    exe = os.path.join(ROOT, 'oracle', '_build', 'fsearch_oracle')
+    src = os.path.join(ROOT, 'oracle', 'fsearch_oracle.cpp')
+    if (not os.path.exists(so) or not os.path.exists(exe)
+            or os.path.getmtime(so) < os.path.getmtime(src)):
+        subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle')], stdout=subprocess.DEVNULL)
+    return so, exe
+
+
+class Oracle:
+    """ctypes view of the CPU oracle (test infrastructure)."""
+
+    def __init__(self):
+        so, self.exe = build_oracle()
+        L = ctypes.CDLL(so)
+        self.L = L
+        L.orc_kswat_st.restype = ctypes.c_double
+        L.orc_kswat_st.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
+        L.orc_ungap.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int] + [ctypes.c_int] * 4 + [
+            ctypes.POINTER(ctypes.c_longlong)]
+        L.orc_seg.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p]
+        L.orc_score2bit.restype = ctypes.c_longlong
+        L.orc_score2bit.argtypes = [ctypes.c_longlong]
+        L.orc_f2s.argtypes = [ctypes.c_double, ctypes.c_char_p, ctypes.c_int]
+        L.orc_qsort_perm.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        L.orc_spseeds.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p,
+                                  ctypes.c_uint, ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_int)]
+        L.orc_blastp.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_double,
+                                 ctypes.c_longlong, ctypes.c_double] + [ctypes.c_longlong] * 5 + [
+            ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_longlong] * 3 + [
+            ctypes.c_char_p, ctypes.POINTER(ctypes.c_longlong)]
+
+    def kswat_st(self, s0, s1, qst=0, sst=0):
+        out = (ctypes.c_longlong * 9)()
+        a, b = s0.encode('latin-1'), s1.encode('latin-1')
+        idy = self.L.orc_kswat_st(a, len(a), b, len(b), qst, sst, out)
+        return idy, list(out)
+
+    def ungap(self, q, s, Q, S, qlo=-1, slo=-1):
+        out = (ctypes.c_longlong * 5)()
+        a, b = q.encode('latin-1'), s.encode('latin-1')
+        self.L.orc_ungap(a, len(a), b, len(b), Q, S, qlo, slo, out)
+        return list(out)
+
+    def seg(self, s):
+        a = s.encode('latin-1')
+        out = ctypes.create_string_buffer(len(a) + 1)
+        self.L.orc_seg(a, len(a), out)
+        return out.raw[:len(a)].decode('latin-1')
+
+    def f2s(self, e):
+        out = ctypes.create_string_buffer(64)
+        self.L.orc_f2s(e, out, 64)
+        return out.value.decode()
+
+    def qsort_perm(self, keys):
+        n = len(keys)
+        k = (ctypes.c_longlong * max(n, 1))(*keys)
+        p = (ctypes.c_int * max(n, 1))()
+        self.L.orc_qsort_perm(k, n, p)
+        return list(p)[:n]
+
+    def spseeds(self, seq, step, nr, ssd, mod):
+        a = seq.encode('latin-1')
+        cap = max(1, len(a) * (ssd.count(',') + 1) * (nr.count('/') + 1))
+        b = (ctypes.c_uint * cap)()
+        p = (ctypes.c_int * cap)()
+        n = self.L.orc_spseeds(a, len(a), step, nr.encode(), ssd.encode(), mod, b, p)
+        return [[b[i], p[i]] for i in range(n)]
+
+    def blastp(self, qry, ref, out, flags):
+        """flags: dict of fsearch-c flag letters (same as the golden cases)."""
+        stats = (ctypes.c_longlong * 7)()
+        f = {'-e': '1e-3', '-v': '500', '-m': '1e-3', '-l': '-1', '-u': '-1', '-L': '-1', '-U': '-1', '-t': '-1',
+             '-F': 'T', '-s': '111111', '-r': 'AST,CFILMVY,DN,EQ,G,H,KR,P,W', '-j': '4', '-M': '-1', '-c': '50000',
+             '-O': 'wb'}
+        f.update(flags)
+        rc = self.L.orc_blastp(qry.encode(), ref.encode(), out.encode(), float(f['-e']), int(f['-v']),
+                               float(f['-m']), int(f['-l']), int(f['-u']), int(f['-L']), int(f['-U']),
+                               int(f['-t']), f['-F'].encode(), f['-s'].encode(), f['-r'].encode(), int(f['-j']),
+                               int(f['-M']), int(f['-c']), f['-O'].encode(), stats)
+        assert rc == 0
+        return dict(zip(['queries', 'seed_hits', 'groups', 'candidates', 'alignments', 'dp_cells', 'rows'],
+                        list(stats)))
+
+
+@pytest.fixture(scope='session')
+def oracle():
+    return Oracle()
+
+
+@pytest.fixture(scope='session')
+def kat():
+    with open(os.path.join(GOLDEN, 'kat.json')) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope='session')
+def golden_cases():
+    with open(os.path.join(GOLDEN, 'cases.json')) as f:
+        return json.load(f)
