@@ -178,7 +178,7 @@ typedef struct so_stats {
     int64_t queries, seed_hits, groups, candidates, alignments, dp_cells, rows;
     int64_t kernel_launches; /* launches of this library's own kernels */
     int64_t lib_launches;    /* CUB (library) launches                 */
-    double ms_seed, ms_sort, ms_ungap, ms_select, ms_align, ms_host, ms_total;
+    double ms_seed, ms_sort, ms_ungap, ms_select, ms_align, ms_dp, ms_traceback, ms_host, ms_total;
     int64_t h2d_bytes, d2h_bytes;
 } so_stats;
 int so_stats_get(const so_ctx *c, so_stats *s);

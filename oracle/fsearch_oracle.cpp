@@ -1062,6 +1062,62 @@ int orc_spseeds(const char *seq, int n, int step, const char *nr, const char *ss
     return (int)out.size();
 }
 
+
+// Candidates of queries [q0, q1) against target chunk [c0, c1) (find_msav_m with sort=False), for
+// stage-level parity tests.  out_off[q1-q0+1]; out receives (hd, score, qi, qj) quadruples up to cap.
+long long orc_candidates(const char *qry, const char *ref, long long c0, long long c1, long long q0, long long q1,
+                         const char *flt, const char *ssd, const char *nr, long long step, long long ht, long long thr,
+                         unsigned long long *out_off, unsigned *out, long long cap, long long *threshold) {
+    orc::init_b62();
+    orc::Fasta seqs, DB;
+    if (!seqs.load(qry) || !DB.load(ref)) return -1;
+    orc::Params P;
+    for (const std::string &a : orc::split(nr, '/')) P.codes.push_back(orc::generate_nr_tbl(a));
+    P.spaces = orc::split(ssd, ',');
+    P.mink = 1 << 30;
+    for (const auto &s : P.spaces) P.mink = std::min<int>(P.mink, (int)s.size());
+    P.NC = (uint32_t)ht;
+    P.step = (int)step;
+    orc::ChunkIndex ix;
+    ix.build(DB, P, c0, c1);
+    if (!(thr < 1 && ix.threshold != 0)) ix.threshold = thr;
+    if (threshold) *threshold = ix.threshold;
+    orc::Searcher S;
+    std::vector<orc::Cand> cands;
+    std::string hd, sq;
+    long long n = 0;
+    out_off[0] = 0;
+    for (long long q = q0; q < q1; q++) {
+        seqs.get(q, hd, sq);
+        std::string m = (std::string(flt) == "T") ? orc::seg(sq) : sq;
+        S.find(ix, P, m, cands);
+        for (const orc::Cand &c : cands) {
+            if (n < cap) out[n * 4] = c.hd, out[n * 4 + 1] = c.score, out[n * 4 + 2] = c.qi, out[n * 4 + 3] = c.qj;
+            n++;
+        }
+        out_off[q - q0 + 1] = (unsigned long long)n;
+    }
+    return n;
+}
+
+// Index of chunk [c0, c1): start[NC] (after the fill pass = bucket starts) and locus; returns len(locus)
+long long orc_index(const char *ref, long long c0, long long c1, const char *ssd, const char *nr, long long step,
+                    long long ht, unsigned *start, unsigned *locus, long long cap) {
+    orc::Fasta DB;
+    if (!DB.load(ref)) return -1;
+    orc::Params P;
+    for (const std::string &a : orc::split(nr, '/')) P.codes.push_back(orc::generate_nr_tbl(a));
+    P.spaces = orc::split(ssd, ',');
+    P.mink = 1;
+    P.NC = (uint32_t)ht;
+    P.step = (int)step;
+    orc::ChunkIndex ix;
+    ix.build(DB, P, c0, c1);
+    if (start) memcpy(start, ix.start.data(), ix.start.size() * 4);
+    for (size_t i = 0; i < ix.locus.size() && (long long)i < cap; i++) locus[i] = ix.locus[i];
+    return (long long)ix.locus.size();
+}
+
 // Full search.  stats[7] = queries, seed_hits, groups, candidates, alignments, dp_cells, rows
 int orc_blastp(const char *qry, const char *ref, const char *out, double expect, long long v, double max_miss,
                long long st, long long ed, long long rst, long long red, long long thr, const char *flt,

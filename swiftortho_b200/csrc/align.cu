@@ -1,0 +1,376 @@
+// K7 / K8 / K9: the reference's banded single-matrix local alignment (kswat_st,
+// lib/fsearch.py:1357-1476) as two sm_100a kernels.
+//
+//   k_banded_dp   one THREAD per alignment (inter-sequence parallelism, tasks sorted by length so
+//                 the 32 lanes of a warp walk similar row counts).  The band of the reference is
+//                 j - i in [-16, +15] (fsearch.py:1393: start=max(1,i-16), end=min(i+16,l0)) =
+//                 32 cells per row, kept entirely in registers: S[d] = score of lane d of the
+//                 previous row, Dc[d] = that cell's contribution as a vertical predecessor
+//                 (score + ge if its trace is '|' else score + go).  Cells are evaluated in the
+//                 reference's row-major order, so "first strict maximum" (fsearch.py:1401) needs
+//                 no reduction.  max(0, I, M, D) is one DPX instruction (__vimax3_s32_relu).
+//                 BLOSUM62 lives in shared memory as a 32x32 int8 table over 5-bit residue classes.
+//                 The 2-bit trace (0 '\', 1 '-', 2 '|', 3 '*'; priority M > I > D as in
+//                 fsearch.py:1404-1411) is written as one 64-bit word per row, laid out
+//                 [warp][row][lane] so a warp's store is one coalesced 256-byte line.
+//   k_traceback   one thread per alignment walks the trace from (i_max, j_max) with the reference's
+//                 `while i > 0 or j > 0` loop (fsearch.py:1418-1443), including the walk along
+//                 row 0 / column 0, and accumulates the statistics of fsearch.py:1454-1469
+//                 (identity on raw bytes, mismatches incl. gap columns, gap count = ceil(run/2)).
+//
+// Guard cells of the reference (fsearch.py:1379-1389) are constants here: left of the band and
+// column 0 contribute I = go; the cell right of the band in the previous row contributes D = go
+// (its score is always 0 and its trace never '|').
+#include <algorithm>
+#include <numeric>
+
+#include "context.h"
+
+namespace so {
+
+__constant__ int8_t c_score[kClasses * kClasses];
+__constant__ uint8_t c_code[256];
+
+int upload_tables() {
+    int8_t tbl[kClasses * kClasses];
+    uint8_t code[256];
+    make_score_table(tbl);
+    make_code_table(code);
+    SO_CUDA(cudaMemcpyToSymbol(c_score, tbl, sizeof tbl));
+    SO_CUDA(cudaMemcpyToSymbol(c_code, code, sizeof code));
+    return SO_OK;
+}
+
+struct AlnTask {
+    const uint8_t *s0;  // columns (the side with the shorter remainder), already offset to its start
+    const uint8_t *s1;  // rows
+    int len0, len1;
+};
+
+struct DpOut {
+    int score, imax, jmax, rows;
+};
+
+struct TbOut {
+    int i0, j0, al, nid, mis, gap, bad, pad;
+};
+
+template <bool EDGE>
+__device__ __forceinline__ void dp_row(int i, int len0, bool live, int c1base, const int8_t *s_tbl, int (&S)[32],
+                                       int (&Dc)[33], const uint32_t (&W)[8], uint32_t &tlo, uint32_t &thi,
+                                       int &best, int &bpos) {
+    int Ic = -11;  // left of lane 0: guard cell / column 0 -> score 0 + go
+    tlo = 0;
+    thi = 0;
+#pragma unroll
+    for (int d = 0; d < 32; d++) {
+        const int c0 = (W[d >> 2] >> ((d & 3) * 8)) & 0xff;
+        const int sub = s_tbl[c1base + c0];
+        const int M = S[d] + sub;
+        const int Dv = Dc[d + 1];
+        int B = __vimax3_s32_relu(Ic, M, Dv);
+        int code = (B == M) ? 0 : ((B == Ic) ? 1 : ((B == Dv) ? 2 : 3));
+        int nI = B + (code == 1 ? -1 : -11);
+        int nD = B + (code == 2 ? -1 : -11);
+        if (EDGE) {
+            const bool valid = live && (unsigned)(i + d - 17) < (unsigned)len0;  // 1 <= j < l0
+            if (!valid) {
+                B = 0;
+                nI = -11;
+                nD = -11;
+                code = 3;
+            }
+        }
+        if (B > best) {
+            best = B;
+            bpos = (i << 5) | d;
+        }
+        S[d] = B;
+        Dc[d] = nD;
+        Ic = nI;
+        if (d < 16)
+            tlo |= (uint32_t)code << (2 * d);
+        else
+            thi |= (uint32_t)code << (2 * (d - 16));
+    }
+}
+
+__global__ void __launch_bounds__(128) k_banded_dp(const AlnTask *__restrict__ tasks, int n,
+                                                   const uint64_t *__restrict__ warp_base,
+                                                   uint64_t *__restrict__ trace, DpOut *__restrict__ out) {
+    __shared__ int8_t s_tbl[kClasses * kClasses];
+    __shared__ uint8_t s_code[256];
+    for (int k = threadIdx.x; k < kClasses * kClasses; k += blockDim.x) s_tbl[k] = c_score[k];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_code[k] = c_code[k];
+    __syncthreads();
+
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool active = t < n;
+    AlnTask tk;
+    if (active)
+        tk = tasks[t];
+    else {
+        tk.s0 = tk.s1 = nullptr;
+        tk.len0 = tk.len1 = 0;
+    }
+    const int len0 = tk.len0;
+    const int nrows = active ? min(tk.len1, len0 + 16) : 0;  // rows that hold at least one band cell
+    int wrows = nrows;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wrows = max(wrows, __shfl_xor_sync(0xffffffffu, wrows, o));
+    uint64_t *tr = trace + warp_base[t >> 5] + lane;
+
+    int S[32], Dc[33];
+#pragma unroll
+    for (int d = 0; d < 32; d++) S[d] = 0, Dc[d] = -11;  // row 0: score 0, trace '-' (never '|')
+    Dc[32] = -11;
+    // window of s0 classes: byte d holds class(s0[i + d - 17]) for the current row i
+    uint32_t W[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) W[k] = 0;
+#pragma unroll
+    for (int d = 16; d < 32; d++) {
+        const int idx = d - 16;  // row 1: s0[d - 16]
+        const uint32_t cls = (idx < len0) ? s_code[tk.s0[idx]] : 0;
+        W[d >> 2] |= cls << ((d & 3) * 8);
+    }
+    int best = 0, bpos = 0;
+    for (int i = 1; i <= wrows; i++) {
+        const bool live = i <= nrows;
+        const int c1base = live ? (int)s_code[tk.s1[i - 1]] * kClasses : 0;
+        uint32_t tlo, thi;
+        const bool interior = live && i >= 17 && i + 15 <= len0;
+        if (__all_sync(0xffffffffu, interior))
+            dp_row<false>(i, len0, live, c1base, s_tbl, S, Dc, W, tlo, thi, best, bpos);
+        else
+            dp_row<true>(i, len0, live, c1base, s_tbl, S, Dc, W, tlo, thi, best, bpos);
+        if (live) tr[(size_t)(i - 1) * 32] = ((uint64_t)thi << 32) | tlo;
+        // slide the window: drop byte 0, append class(s0[i + 15]) for row i + 1
+        const int nidx = i + 15;
+        const uint32_t ncls = (nidx < len0) ? s_code[tk.s0[nidx]] : 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) W[k] = __funnelshift_r(W[k], W[k + 1], 8);
+        W[7] = (W[7] >> 8) | (ncls << 24);
+    }
+    if (active) {
+        DpOut o;
+        o.score = best;
+        o.imax = best > 0 ? (bpos >> 5) : 0;
+        o.jmax = best > 0 ? ((bpos >> 5) + (bpos & 31) - 16) : 0;
+        o.rows = nrows;
+        out[t] = o;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_traceback(const AlnTask *__restrict__ tasks, int n,
+                                                   const uint64_t *__restrict__ warp_base,
+                                                   const uint64_t *__restrict__ trace,
+                                                   const DpOut *__restrict__ dp, TbOut *__restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const AlnTask tk = tasks[t];
+    const uint64_t *tr = trace + warp_base[t >> 5] + (threadIdx.x & 31);
+    int i = dp[t].imax, j = dp[t].jmax;
+    int al = 0, nid = 0, mis = 0, gap = 0, bad = 0;
+    int run_type = 0, run_len = 0;  // 1: trace '-', 2: trace '|'
+    int cached_row = -1;
+    uint64_t word = 0;
+    while (i > 0 || j > 0) {
+        int code;
+        if (i == 0)
+            code = 1;  // row 0 holds '-' (fsearch.py:1379-1382)
+        else if (j == 0)
+            code = 2;  // column 0 holds '|' (fsearch.py:1383-1386)
+        else {
+            const int d = j - i + 16;
+            if (d < 0 || d > 31) {
+                bad = 1;
+                break;
+            }
+            if (i != cached_row) {
+                word = tr[(size_t)(i - 1) * 32];
+                cached_row = i;
+            }
+            code = (int)((word >> (2 * d)) & 3);
+        }
+        if (code == 3) break;
+        al++;
+        if (code == 0) {
+            if (tk.s0[j - 1] == tk.s1[i - 1])
+                nid++;
+            else
+                mis++;
+            i--;
+            j--;
+            gap += (run_len + 1) >> 1;
+            run_len = 0;
+            run_type = 0;
+        } else {
+            mis++;
+            if (run_type != code) {
+                gap += (run_len + 1) >> 1;
+                run_len = 0;
+                run_type = code;
+            }
+            run_len++;
+            if (code == 1)
+                j--;
+            else
+                i--;
+        }
+    }
+    gap += (run_len + 1) >> 1;
+    TbOut o;
+    o.i0 = i, o.j0 = j, o.al = al, o.nid = nid, o.mis = mis, o.gap = gap, o.bad = bad, o.pad = 0;
+    out[t] = o;
+}
+
+// -----------------------------------------------------------------------------------------------
+// Host driver: resolves pairs to device tasks, sorts by length, launches, converts coordinates.
+// -----------------------------------------------------------------------------------------------
+int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
+    if (n <= 0) return SO_OK;
+    if (!c->d_tres || !c->d_qres) {
+        set_error("so_align_batch: targets and queries must be loaded first");
+        return SO_EINVAL;
+    }
+    Timer tm;
+    struct Prep {
+        int len0, len1;
+        int qst, sst;  // clamped starts inside the slices
+        bool swap;
+    };
+    std::vector<Prep> prep((size_t)n);
+    std::vector<AlnTask> tasks((size_t)n);
+    std::vector<int> order((size_t)n);
+    for (i64 k = 0; k < n; k++) {
+        const so_pair &p = pairs[k];
+        if (p.query < 0 || p.query >= c->n_q || p.target < 0 || p.target >= c->n_t) {
+            set_error("so_align_batch: pair %lld addresses a sequence out of range", (long long)k);
+            return SO_EINVAL;
+        }
+        i64 ql_full = (i64)(c->q_off[p.query + 1] - c->q_off[p.query]);
+        i64 tl_full = (i64)(c->t_off[p.target + 1] - c->t_off[p.target]);
+        i64 qo = std::min<i64>(std::max<i64>(p.q_off, 0), ql_full), to = std::min<i64>(std::max<i64>(p.t_off, 0), tl_full);
+        i64 qlen = std::min<i64>(std::max<i64>(p.q_len, 0), ql_full - qo), tlen = std::min<i64>(std::max<i64>(p.t_len, 0), tl_full - to);
+        // kswat_st argument clamping (fsearch.py:1359-1362)
+        i64 qst = std::min<i64>(std::max<i64>(p.qst, 0), qlen), sst = std::min<i64>(std::max<i64>(p.sst, 0), tlen);
+        i64 qrem = qlen - qst, trem = tlen - sst;
+        if (qrem > 4096 || trem > 4096) {
+            set_error("so_align_batch: slice remainder above 4096 (tile the pair like kswat_st_long)");
+            return SO_ELIMIT;
+        }
+        Prep &r = prep[(size_t)k];
+        r.qst = (int)qst, r.sst = (int)sst;
+        const uint8_t *qp = c->d_qres + c->q_off[p.query] + qo + qst;
+        const uint8_t *tp = c->d_tres + c->t_off[p.target] + to + sst;
+        // s0 (columns) is the query iff its remainder is strictly shorter (fsearch.py:1364-1369)
+        if (qrem < trem) {
+            r.swap = false, r.len0 = (int)qrem, r.len1 = (int)trem;
+            tasks[(size_t)k] = AlnTask{qp, tp, r.len0, r.len1};
+        } else {
+            r.swap = true, r.len0 = (int)trem, r.len1 = (int)qrem;
+            tasks[(size_t)k] = AlnTask{tp, qp, r.len0, r.len1};
+        }
+        order[(size_t)k] = (int)k;
+    }
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        if (prep[(size_t)a].len0 != prep[(size_t)b].len0) return prep[(size_t)a].len0 > prep[(size_t)b].len0;
+        if (prep[(size_t)a].len1 != prep[(size_t)b].len1) return prep[(size_t)a].len1 > prep[(size_t)b].len1;
+        return a < b;
+    });
+    std::vector<AlnTask> sorted((size_t)n);
+    for (i64 k = 0; k < n; k++) sorted[(size_t)k] = tasks[(size_t)order[(size_t)k]];
+    const i64 nwarps = (n + 31) / 32;
+    const i64 nwarps_pad = ((n + 127) / 128) * 4;
+    std::vector<uint64_t> wbase((size_t)nwarps_pad + 1, 0);
+    i64 cells = 0;
+    for (i64 w = 0; w < nwarps_pad; w++) {
+        int rows = 0;
+        for (i64 k = w * 32; k < std::min<i64>(n, w * 32 + 32); k++) {
+            const AlnTask &t = sorted[(size_t)k];
+            rows = std::max(rows, std::min(t.len1, t.len0 + 16));
+        }
+        wbase[(size_t)w + 1] = wbase[(size_t)w] + (uint64_t)rows * 32;
+    }
+    (void)nwarps;
+    for (i64 k = 0; k < n; k++) {
+        const Prep &r = prep[(size_t)k];
+        // cells the reference fills: rows 1..l1-1, columns [max(1,i-16), min(i+16,l0))
+        i64 l0 = r.len0 + 1, l1 = r.len1 + 1;
+        for (i64 i = 1; i < l1 && i <= l0 + 15; i++) {
+            i64 a = std::max<i64>(1, i - 16), b = std::min<i64>(i + 16, l0);
+            if (b > a) cells += b - a;
+        }
+    }
+    size_t need_trace = (size_t)wbase[(size_t)nwarps_pad] + 64;
+    int rc;
+    if ((rc = c->trace.reserve(need_trace)) != SO_OK) return rc;
+    size_t b_tasks = (size_t)n * sizeof(AlnTask), b_wb = wbase.size() * sizeof(uint64_t);
+    if ((rc = c->scratch[0].reserve(b_tasks)) != SO_OK) return rc;
+    if ((rc = c->scratch[1].reserve(b_wb)) != SO_OK) return rc;
+    if ((rc = c->scratch[2].reserve((size_t)n * sizeof(DpOut))) != SO_OK) return rc;
+    if ((rc = c->scratch[3].reserve((size_t)n * sizeof(TbOut))) != SO_OK) return rc;
+    AlnTask *d_tasks = (AlnTask *)c->scratch[0].p;
+    uint64_t *d_wb = (uint64_t *)c->scratch[1].p;
+    DpOut *d_dp = (DpOut *)c->scratch[2].p;
+    TbOut *d_tb = (TbOut *)c->scratch[3].p;
+    SO_CUDA(cudaMemcpyAsync(d_tasks, sorted.data(), b_tasks, cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA(cudaMemcpyAsync(d_wb, wbase.data(), b_wb, cudaMemcpyHostToDevice, c->stream));
+    const int grid = (int)((n + 127) / 128);
+    SO_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    k_banded_dp<<<grid, 128, 0, c->stream>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp);
+    SO_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    k_traceback<<<grid, 128, 0, c->stream>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp, d_tb);
+    SO_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    SO_CUDA(cudaGetLastError());
+    std::vector<DpOut> h_dp((size_t)n);
+    std::vector<TbOut> h_tb((size_t)n);
+    SO_CUDA(cudaMemcpyAsync(h_dp.data(), d_dp, (size_t)n * sizeof(DpOut), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA(cudaMemcpyAsync(h_tb.data(), d_tb, (size_t)n * sizeof(TbOut), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA(cudaStreamSynchronize(c->stream));
+    float ms_dp = 0, ms_tb = 0;
+    cudaEventElapsedTime(&ms_dp, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&ms_tb, c->ev[1], c->ev[2]);
+    c->stats.ms_align += ms_dp + ms_tb;
+    c->stats.ms_dp += ms_dp;
+    c->stats.ms_traceback += ms_tb;
+    c->stats.kernel_launches += 2;
+    c->stats.alignments += n;
+    c->stats.dp_cells += cells;
+    c->stats.h2d_bytes += (i64)(b_tasks + b_wb);
+    c->stats.d2h_bytes += (i64)((size_t)n * (sizeof(DpOut) + sizeof(TbOut)));
+    for (i64 s = 0; s < n; s++) {
+        const int k = order[(size_t)s];
+        const Prep &r = prep[(size_t)k];
+        const DpOut &d = h_dp[(size_t)s];
+        const TbOut &b = h_tb[(size_t)s];
+        if (b.bad) {
+            set_error("traceback left the band (internal error) for pair %d", k);
+            return SO_EINVAL;
+        }
+        so_aln &o = out[k];
+        o.raw_score = d.score;
+        o.aln_len = b.al;
+        o.n_ident = b.nid;
+        o.mismatch = b.mis;
+        o.gaps = b.gap;
+        // (i, j) = rows / columns.  fsearch.py:1473-1476
+        if (r.swap) {  // rows are the query
+            o.qst = b.i0 + r.qst, o.qed = d.imax + r.qst, o.sst = b.j0 + r.sst, o.sed = d.jmax + r.sst;
+        } else {
+            o.qst = b.j0 + r.qst, o.qed = d.jmax + r.qst, o.sst = b.i0 + r.sst, o.sed = d.imax + r.sst;
+        }
+        i64 l0 = r.len0 + 1, l1 = r.len1 + 1, cl = 0;
+        for (i64 i = 1; i < l1 && i <= l0 + 15; i++) {
+            i64 a = std::max<i64>(1, i - 16), e = std::min<i64>(i + 16, l0);
+            if (e > a) cl += e - a;
+        }
+        o.cells = (int32_t)cl;
+    }
+    c->stats.ms_host += tm.ms() - (ms_dp + ms_tb);
+    return SO_OK;
+}
+
+}  // namespace so

@@ -1,0 +1,613 @@
+// C ABI entry points (include/swiftortho_b200.h) and the host side of the search:
+// context set-up, query preparation (H1 seg mask, S3 position order), the candidate merge / sort /
+// stop rule of blastp (H3, lib/fsearch.py:3039-3106) driving the alignment kernels in rounds, the
+// e-value filter and the final per-query order (F, lib/fsearch.py:3071-3072, 3108-3110), and the
+// 16-column text writer (lib/fsearch.py:3233-3243).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <thread>
+
+#include "context.h"
+
+struct so_fasta;  // fasta.cpp
+
+namespace so {
+
+template <class F>
+static void parallel_for(i64 n, F f) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > 32) nt = 32;
+    if (n < 64 || nt == 1) {
+        for (i64 i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::atomic<i64> next(0);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([&]() {
+            for (;;) {
+                i64 i0 = next.fetch_add(16);
+                if (i0 >= n) return;
+                for (i64 i = i0; i < std::min<i64>(n, i0 + 16); i++) f(i);
+            }
+        });
+    for (auto &t : th) t.join();
+}
+
+int ensure_pinned(so_ctx *c, size_t bytes) {
+    if (bytes <= c->h_pinned_cap) return SO_OK;
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    c->h_pinned = nullptr;
+    c->h_pinned_cap = 0;
+    SO_CUDA(cudaMallocHost(&c->h_pinned, bytes + bytes / 4));
+    c->h_pinned_cap = bytes + bytes / 4;
+    return SO_OK;
+}
+
+static int check_offsets(const uint64_t *off, i64 n, uint32_t &maxlen, const char *what) {
+    maxlen = 0;
+    for (i64 i = 0; i < n; i++) {
+        if (off[i + 1] < off[i]) {
+            set_error("%s offsets are not monotone", what);
+            return SO_EINVAL;
+        }
+        uint64_t L = off[i + 1] - off[i];
+        if (L >= 65536) {
+            set_error("%s %lld has %llu residues; the limit is 65535", what, (long long)i, (unsigned long long)L);
+            return SO_ELIMIT;
+        }
+        maxlen = std::max<uint32_t>(maxlen, (uint32_t)L);
+    }
+    return SO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// H3 + F: one query's candidate list -> alignment requests -> rows
+// ---------------------------------------------------------------------------------------------
+struct QueryState {
+    std::vector<uint64_t> order;  // candidates in the reference's sorted order (prefix of length `limit`)
+    std::vector<so_cand> cands;   // concatenated over chunks, reference order
+    i64 limit = 0;                // min(vmax, len(hits))
+    i64 next = 0;                 // next candidate (in sorted order) to align
+    double mmiss = 0;
+    i64 unmch = 0, bv = 0;
+    bool done = false;
+    std::vector<so_hit> rows;
+    // requests of the current round
+    i64 req_first = 0, req_count = 0;  // candidates covered
+};
+
+static const i64 kRound = 64;
+
+}  // namespace so
+
+using namespace so;
+
+extern "C" {
+
+int so_abi_version(void) { return SO_ABI_VERSION; }
+const char *so_last_error(void) { return so::get_error(); }
+
+int so_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int so_seg(const uint8_t *seq, int64_t n, uint8_t *out) {
+    if (n < 0 || (n > 0 && (!seq || !out))) {
+        set_error("so_seg: bad argument");
+        return SO_EINVAL;
+    }
+    so::seg_mask(seq, n, out);
+    return SO_OK;
+}
+
+int so_qsort_perm(const int64_t *keys, int64_t n, int32_t *perm) {
+    if (n < 0 || (n > 0 && (!keys || !perm))) {
+        set_error("so_qsort_perm: bad argument");
+        return SO_EINVAL;
+    }
+    so::qsort_perm((const so::i64 *)keys, n, perm);
+    return SO_OK;
+}
+
+int64_t so_score2bit(int64_t raw) { return so::score2bit(raw); }
+double so_bit2e(int64_t D, int64_t ql, int64_t tl, int64_t bit) { return so::bit2e(D, ql, tl, bit); }
+int so_f2s(double e, char *out, int cap) {
+    if (!out || cap < 2) return SO_EINVAL;
+    std::string s = so::f2s(e);
+    snprintf(out, (size_t)cap, "%s", s.c_str());
+    return SO_OK;
+}
+
+void so_free(void *p) { free(p); }
+
+int so_ctx_create(int device, const so_params *p, so_ctx **out) {
+    if (!out) {
+        set_error("so_ctx_create: null out");
+        return SO_EINVAL;
+    }
+    Params P;
+    int rc = parse_params(p, P);
+    if (rc != SO_OK) return rc;
+    int ndev = so_device_count();
+    if (ndev <= 0) {
+        set_error("no CUDA device visible: swiftortho_b200 has no CPU fallback");
+        return SO_ENODEV;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("device %d out of range (%d visible)", device, ndev);
+        return SO_EINVAL;
+    }
+    SO_CUDA(cudaSetDevice(device));
+    so_ctx *c = new so_ctx();
+    c->device = device;
+    c->P = P;
+    SO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) SO_CUDA(cudaEventCreate(&e));
+    if ((rc = so::upload_tables()) != SO_OK) {
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return SO_OK;
+}
+
+void so_ctx_destroy(so_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto &ix : c->chunks) so::free_chunk_index(ix);
+    for (auto &s : c->scratch) s.release();
+    c->trace.release();
+    if (c->d_tres) cudaFree(c->d_tres);
+    if (c->d_qres) cudaFree(c->d_qres);
+    if (c->d_toff) cudaFree(c->d_toff);
+    if (c->d_qoff) cudaFree(c->d_qoff);
+    if (c->d_perm) cudaFree(c->d_perm);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (auto &e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int so_set_targets(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, int64_t n) {
+    if (!c || !offsets || n < 0 || (!residues && n > 0 && offsets[n] > 0)) {
+        set_error("so_set_targets: bad argument");
+        return SO_EINVAL;
+    }
+    SO_CUDA(cudaSetDevice(c->device));
+    int rc = check_offsets(offsets, n, c->max_tlen, "target");
+    if (rc != SO_OK) return rc;
+    if (n >= (1 << 24)) {
+        set_error("at most 16777215 target sequences per context");
+        return SO_ELIMIT;
+    }
+    for (auto &ix : c->chunks) so::free_chunk_index(ix);
+    c->chunks.clear();
+    if (c->d_tres) cudaFree(c->d_tres);
+    if (c->d_toff) cudaFree(c->d_toff);
+    c->d_tres = nullptr, c->d_toff = nullptr;
+    c->n_t = n;
+    c->t_off.assign(offsets, offsets + n + 1);
+    const uint64_t base = offsets[0];
+    for (auto &v : c->t_off) v -= base;
+    const size_t bytes = (size_t)c->t_off[(size_t)n];
+    SO_CUDA(cudaMalloc((void **)&c->d_tres, bytes + 64));
+    SO_CUDA(cudaMalloc((void **)&c->d_toff, ((size_t)n + 1) * 8));
+    SO_CUDA(cudaMemcpyAsync(c->d_tres, residues + base, bytes, cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA(cudaMemcpyAsync(c->d_toff, c->t_off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats.h2d_bytes += (i64)bytes + ((i64)n + 1) * 8;
+    return SO_OK;
+}
+
+int so_set_queries(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, int64_t n) {
+    if (!c || !offsets || n < 0 || (!residues && n > 0 && offsets[n] > 0)) {
+        set_error("so_set_queries: bad argument");
+        return SO_EINVAL;
+    }
+    SO_CUDA(cudaSetDevice(c->device));
+    int rc = check_offsets(offsets, n, c->max_qlen, "query");
+    if (rc != SO_OK) return rc;
+    Timer tm;
+    if (c->d_qres) cudaFree(c->d_qres);
+    if (c->d_qoff) cudaFree(c->d_qoff);
+    if (c->d_perm) cudaFree(c->d_perm);
+    c->d_qres = nullptr, c->d_qoff = nullptr, c->d_perm = nullptr;
+    c->n_q = n;
+    c->q_off.assign(offsets, offsets + n + 1);
+    const uint64_t base = offsets[0];
+    for (auto &v : c->q_off) v -= base;
+    const size_t bytes = (size_t)c->q_off[(size_t)n];
+    c->q_masked.assign(bytes, 0);
+    std::vector<uint32_t> perm(bytes, 0);
+    const bool flt = c->P.flt;
+    const int mink = c->P.mink;
+    const uint8_t *src = residues + base;
+    uint8_t *dst = c->q_masked.data();
+    const uint64_t *qo = c->q_off.data();
+    // H1 (seg) and the S3 position order: kscs = sliding BLOSUM62 self score over the shortest seed
+    // span, positions sorted with the reference quicksort by -kscs (fsearch.py:2647-2656, 2668)
+    so::parallel_for(n, [&](i64 q) {
+        const i64 L = (i64)(qo[q + 1] - qo[q]);
+        const uint8_t *s = src + qo[q];
+        uint8_t *m = dst + qo[q];
+        if (flt)
+            so::seg_mask(s, L, m);
+        else if (L > 0)
+            memcpy(m, s, (size_t)L);
+        const i64 P = L - mink + 1;
+        if (P <= 0) return;
+        std::vector<uint64_t> v((size_t)P);
+        i64 sc = 0;
+        for (int i = 0; i < mink; i++) sc += so::score_bytes(m[i], m[i]);
+        for (i64 i = 0; i < P; i++) {
+            if (i > 0) sc = sc - so::score_bytes(m[i - 1], m[i - 1]) + so::score_bytes(m[i - 1 + mink], m[i - 1 + mink]);
+            // key = -kscs, biased into uint32 (order preserving)
+            v[(size_t)i] = ((uint64_t)(uint32_t)(0x40000000 - sc) << 32) | (uint32_t)i;
+        }
+        so::qsort_prefix(v, P);
+        uint32_t *pp = perm.data() + qo[q];
+        for (i64 i = 0; i < P; i++) pp[i] = (uint32_t)v[(size_t)i];
+    });
+    SO_CUDA(cudaMalloc((void **)&c->d_qres, bytes + 64));
+    SO_CUDA(cudaMalloc((void **)&c->d_qoff, ((size_t)n + 1) * 8));
+    SO_CUDA(cudaMalloc((void **)&c->d_perm, (bytes + 16) * 4));
+    SO_CUDA(cudaMemcpyAsync(c->d_qres, dst, bytes, cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA(cudaMemcpyAsync(c->d_qoff, qo, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA(cudaMemcpyAsync(c->d_perm, perm.data(), bytes * 4, cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats.h2d_bytes += (i64)bytes * 5 + ((i64)n + 1) * 8;
+    c->stats.ms_host += tm.ms();
+    return SO_OK;
+}
+
+int so_index_build(so_ctx *c) {
+    if (!c || !c->d_tres) {
+        set_error("so_index_build: load targets first");
+        return SO_EINVAL;
+    }
+    SO_CUDA(cudaSetDevice(c->device));
+    for (auto &ix : c->chunks) so::free_chunk_index(ix);
+    c->chunks.clear();
+    // makedb (fsearch.py:2283-2295): Start = 0 if -L == -1, End = N if -U == -1; chunks of -c sequences
+    i64 Start = c->P.rst == -1 ? 0 : c->P.rst, End = c->P.red == -1 ? c->n_t : c->P.red;
+    Start = std::min<i64>(std::max<i64>(Start, 0), c->n_t);
+    End = std::min<i64>(std::max<i64>(End, 0), c->n_t);
+    for (i64 s = Start; s < End; s += c->P.chunk) {
+        so::ChunkIndex ix;
+        ix.c0 = s;
+        ix.c1 = std::min<i64>(s + c->P.chunk, End);
+        int rc = so::build_chunk_index(c, ix);
+        if (rc != SO_OK) {
+            so::free_chunk_index(ix);
+            return rc;
+        }
+        c->chunks.push_back(ix);
+    }
+    return SO_OK;
+}
+
+int64_t so_index_chunks(const so_ctx *c) { return c ? (int64_t)c->chunks.size() : 0; }
+
+int so_index_info_get(const so_ctx *c, int64_t chunk, so_index_info *info) {
+    if (!c || !info || chunk < 0 || chunk >= (int64_t)c->chunks.size()) {
+        set_error("so_index_info_get: bad chunk");
+        return SO_EINVAL;
+    }
+    const so::ChunkIndex &ix = c->chunks[(size_t)chunk];
+    info->chunk_start = ix.c0, info->chunk_end = ix.c1, info->n_seeds = ix.n_seeds, info->n_buckets_used = ix.n_used;
+    info->threshold = ix.threshold, info->build_ms = ix.build_ms;
+    return SO_OK;
+}
+
+int so_index_export(so_ctx *c, int64_t chunk, uint32_t *start, uint32_t *locus) {
+    if (!c || chunk < 0 || chunk >= (int64_t)c->chunks.size()) {
+        set_error("so_index_export: bad chunk");
+        return SO_EINVAL;
+    }
+    SO_CUDA(cudaSetDevice(c->device));
+    const so::ChunkIndex &ix = c->chunks[(size_t)chunk];
+    if (start) SO_CUDA(cudaMemcpy(start, ix.d_start, ((size_t)c->P.nc + 1) * 4, cudaMemcpyDeviceToHost));
+    if (locus && ix.n_seeds) SO_CUDA(cudaMemcpy(locus, ix.d_locus, (size_t)ix.n_seeds * 4, cudaMemcpyDeviceToHost));
+    return SO_OK;
+}
+
+int so_candidates(so_ctx *c, int64_t chunk, int64_t q_begin, int64_t q_end, uint64_t **cand_offsets, so_cand **cands) {
+    if (!c || !cand_offsets || !cands || chunk < 0 || chunk >= (int64_t)c->chunks.size() || q_begin < 0 ||
+        q_end > c->n_q || q_begin > q_end) {
+        set_error("so_candidates: bad argument");
+        return SO_EINVAL;
+    }
+    SO_CUDA(cudaSetDevice(c->device));
+    so::BlockCands bc;
+    int rc = so::chunk_candidates(c, c->chunks[(size_t)chunk], q_begin, q_end, bc);
+    if (rc != SO_OK) return rc;
+    *cand_offsets = (uint64_t *)malloc(bc.offsets.size() * 8);
+    *cands = (so_cand *)malloc(std::max<size_t>(1, bc.cands.size()) * sizeof(so_cand));
+    if (!*cand_offsets || !*cands) {
+        set_error("out of host memory");
+        return SO_ENOMEM;
+    }
+    memcpy(*cand_offsets, bc.offsets.data(), bc.offsets.size() * 8);
+    if (!bc.cands.empty()) memcpy(*cands, bc.cands.data(), bc.cands.size() * sizeof(so_cand));
+    return SO_OK;
+}
+
+int so_align_batch(so_ctx *c, const so_pair *pairs, int64_t n, so_aln *out) {
+    if (!c || n < 0 || (n > 0 && (!pairs || !out))) {
+        set_error("so_align_batch: bad argument");
+        return SO_EINVAL;
+    }
+    SO_CUDA(cudaSetDevice(c->device));
+    return so::align_pairs(c, pairs, n, out);
+}
+
+int so_stats_get(const so_ctx *c, so_stats *s) {
+    if (!c || !s) return SO_EINVAL;
+    *s = c->stats;
+    return SO_OK;
+}
+
+int so_stats_reset(so_ctx *c) {
+    if (!c) return SO_EINVAL;
+    memset(&c->stats, 0, sizeof c->stats);
+    return SO_OK;
+}
+
+// test / tuning hook (not part of the reference surface): fixed seeding sub-block size
+int so_set_sub_block(so_ctx *c, int64_t n) {
+    if (!c) return SO_EINVAL;
+    c->sub_block = n;
+    return SO_OK;
+}
+
+int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int64_t *n_rows) {
+    if (!c || !rows_out || !n_rows || q_begin < 0 || q_end > c->n_q || q_begin > q_end) {
+        set_error("so_search: bad argument");
+        return SO_EINVAL;
+    }
+    if (!c->d_qres || !c->d_tres) {
+        set_error("so_search: load targets and queries first");
+        return SO_EINVAL;
+    }
+    SO_CUDA(cudaSetDevice(c->device));
+    Timer total;
+    const Params &P = c->P;
+    const i64 D = c->n_t;
+    const double max_miss = std::max(P.max_miss, 1e-3);                      // fsearch.py:2970
+    const i64 vmax = (i64)std::max(100., std::max((double)(P.v + 100), (double)P.v * 1.1));  // fsearch.py:3059
+    std::vector<so_hit> all_rows;
+    const i64 QB = 512;
+    for (i64 b0 = q_begin; b0 < q_end; b0 += QB) {
+        const i64 b1 = std::min<i64>(q_end, b0 + QB);
+        const i64 nq = b1 - b0;
+        std::vector<QueryState> qs((size_t)nq);
+        // PASS 1 (fsearch.py:2990-3016): candidates of every chunk, concatenated in chunk order
+        for (size_t ch = 0; ch < c->chunks.size(); ch++) {
+            so::BlockCands bc;
+            int rc = so::chunk_candidates(c, c->chunks[ch], b0, b1, bc);
+            if (rc != SO_OK) return rc;
+            Timer th;
+            so::parallel_for(nq, [&](i64 k) {
+                auto &dst = qs[(size_t)k].cands;
+                dst.insert(dst.end(), bc.cands.begin() + (i64)bc.offsets[(size_t)k],
+                           bc.cands.begin() + (i64)bc.offsets[(size_t)k + 1]);
+            });
+            c->stats.ms_host += th.ms();
+        }
+        // PASS 2 (fsearch.py:3051-3059): qsort by -score, mmiss, vmax
+        Timer th;
+        so::parallel_for(nq, [&](i64 k) {
+            QueryState &s = qs[(size_t)k];
+            const i64 n = (i64)s.cands.size();
+            s.order.resize((size_t)n);
+            for (i64 i = 0; i < n; i++)
+                s.order[(size_t)i] = ((uint64_t)(0xffffffffu - s.cands[(size_t)i].score) << 32) | (uint32_t)i;
+            s.limit = std::min<i64>(vmax, n);
+            so::qsort_prefix(s.order, s.limit);
+            double mm = (double)n * max_miss + 1;
+            mm = std::max(mm, 100. / mm);
+            mm = std::min(std::max(mm, 10.), 120.);
+            s.mmiss = mm;
+            s.done = s.limit == 0;
+        });
+        c->stats.ms_host += th.ms();
+        // alignment rounds: the stop rule (fsearch.py:3103) is sequential per query, so each round
+        // aligns the next kRound candidates of every unfinished query and the host replays the rule
+        std::vector<so_pair> pairs;
+        std::vector<so_aln> alns;
+        struct Req {
+            int q;        // block-local query
+            int first;    // first pair of this candidate
+            int count;    // pairs (tiles) of this candidate
+            int cand;     // index into cands
+        };
+        std::vector<Req> reqs;
+        for (;;) {
+            pairs.clear();
+            reqs.clear();
+            for (i64 k = 0; k < nq; k++) {
+                QueryState &s = qs[(size_t)k];
+                if (s.done) continue;
+                const i64 qi_ord = b0 + k;
+                const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
+                const i64 hi = std::min<i64>(s.limit, s.next + kRound);
+                for (i64 h = s.next; h < hi; h++) {
+                    const int ci = (int)(uint32_t)s.order[(size_t)h];
+                    const so_cand &cd = s.cands[(size_t)ci];
+                    const i64 lj = (i64)(c->t_off[(size_t)cd.target + 1] - c->t_off[(size_t)cd.target]);
+                    Req r;
+                    r.q = (int)k, r.first = (int)pairs.size(), r.cand = ci, r.count = 0;
+                    if (li < 4096 && lj < 4096) {
+                        so_pair p;
+                        p.query = qi_ord, p.target = cd.target, p.q_off = 0, p.q_len = (int32_t)li, p.t_off = 0;
+                        p.t_len = (int32_t)lj, p.qst = (int32_t)cd.qi, p.sst = (int32_t)cd.qj;
+                        pairs.push_back(p);
+                        r.count = 1;
+                    } else {
+                        // kswat_st_long (fsearch.py:1480-1498): 4096-tiles down the diagonal; a tile
+                        // whose target slice is empty is skipped (undefined in the reference)
+                        i64 j = cd.qj;
+                        for (i64 i = cd.qi; i < li; i += 4096, j += 4096) {
+                            if (j >= lj) continue;
+                            so_pair p;
+                            p.query = qi_ord, p.target = cd.target, p.q_off = (int32_t)i;
+                            p.q_len = (int32_t)std::min<i64>(4096, li - i), p.t_off = (int32_t)j;
+                            p.t_len = (int32_t)std::min<i64>(4096, lj - j), p.qst = 0, p.sst = 0;
+                            pairs.push_back(p);
+                            r.count++;
+                        }
+                    }
+                    reqs.push_back(r);
+                }
+            }
+            if (reqs.empty()) break;
+            alns.resize(pairs.size());
+            int rc = so::align_pairs(c, pairs.data(), (i64)pairs.size(), alns.data());
+            if (rc != SO_OK) return rc;
+            Timer tr;
+            // replay (fsearch.py:3062-3106)
+            size_t r = 0;
+            while (r < reqs.size()) {
+                const int k = reqs[r].q;
+                QueryState &s = qs[(size_t)k];
+                const i64 qi_ord = b0 + k;
+                const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
+                for (; r < reqs.size() && reqs[r].q == k; r++) {
+                    if (s.done) continue;
+                    const Req &rq = reqs[r];
+                    const so_cand &cd = s.cands[(size_t)rq.cand];
+                    const i64 lj = (i64)(c->t_off[(size_t)cd.target + 1] - c->t_off[(size_t)cd.target]);
+                    const bool longpath = !(li < 4096 && lj < 4096);
+                    bool any = false;
+                    for (int t = 0; t < rq.count; t++) {
+                        const so_aln &a = alns[(size_t)(rq.first + t)];
+                        const so_pair &p = pairs[(size_t)(rq.first + t)];
+                        const i64 bit = so::score2bit(a.raw_score);
+                        const double e = so::bit2e(D, li, lj, bit);
+                        if (e <= P.expect) {
+                            so_hit hrow;
+                            memset(&hrow, 0, sizeof hrow);
+                            hrow.query = qi_ord, hrow.target = cd.target, hrow.qlen = (int32_t)li, hrow.tlen = (int32_t)lj;
+                            hrow.aln_len = a.aln_len, hrow.mismatch = a.mismatch, hrow.gaps = a.gaps;
+                            hrow.qst = a.qst + p.q_off + 1, hrow.qed = a.qed + p.q_off;
+                            hrow.sst = a.sst + p.t_off + 1, hrow.sed = a.sed + p.t_off;
+                            hrow.raw_score = a.raw_score, hrow.n_ident = a.n_ident, hrow.bit = bit;
+                            hrow.identity = a.aln_len ? (double)a.n_ident * (100. / (double)a.aln_len) : NAN;
+                            hrow.evalue = e;
+                            s.rows.push_back(hrow);
+                            any = true;
+                            s.bv++;
+                        }
+                    }
+                    (void)longpath;
+                    if (any)
+                        s.unmch = 0;
+                    else
+                        s.unmch++;
+                    s.next++;
+                    if ((double)s.unmch >= s.mmiss || (double)s.bv >= (double)P.v + s.mmiss) s.done = true;
+                }
+                if (s.next >= s.limit) s.done = true;
+            }
+            c->stats.ms_host += tr.ms();
+        }
+        // final per-query order: qsort_u by -bit, first v rows (fsearch.py:3108-3110)
+        Timer tf;
+        so::parallel_for(nq, [&](i64 k) {
+            QueryState &s = qs[(size_t)k];
+            const i64 n = (i64)s.rows.size();
+            if (n == 0) return;
+            std::vector<uint64_t> v((size_t)n);
+            for (i64 i = 0; i < n; i++)
+                v[(size_t)i] = ((uint64_t)(uint32_t)(0x7fffffff - (int32_t)s.rows[(size_t)i].bit) << 32) | (uint32_t)i;
+            so::qsort_prefix(v, n);
+            std::vector<so_hit> sorted;
+            const i64 lim = std::min<i64>(std::max<i64>(0, P.v), n);
+            sorted.reserve((size_t)lim);
+            for (i64 i = 0; i < lim; i++) sorted.push_back(s.rows[(size_t)(uint32_t)v[(size_t)i]]);
+            s.rows.swap(sorted);
+        });
+        for (i64 k = 0; k < nq; k++) {
+            all_rows.insert(all_rows.end(), qs[(size_t)k].rows.begin(), qs[(size_t)k].rows.end());
+            c->stats.queries++;
+        }
+        c->stats.ms_host += tf.ms();
+    }
+    c->stats.rows += (i64)all_rows.size();
+    *n_rows = (int64_t)all_rows.size();
+    *rows_out = (so_hit *)malloc(std::max<size_t>(1, all_rows.size()) * sizeof(so_hit));
+    if (!*rows_out) {
+        set_error("out of host memory");
+        return SO_ENOMEM;
+    }
+    if (!all_rows.empty()) memcpy(*rows_out, all_rows.data(), all_rows.size() * sizeof(so_hit));
+    c->stats.ms_total += total.ms();
+    return SO_OK;
+}
+
+int so_write_rows(const so_hit *rows, int64_t n, const so_fasta *queries, const so_fasta *targets, const char *path,
+                  int append) {
+    if (n < 0 || (n > 0 && !rows) || !queries || !targets || !path) {
+        set_error("so_write_rows: bad argument");
+        return SO_EINVAL;
+    }
+    FILE *f = fopen(path, append ? "ab" : "wb");
+    if (!f) {
+        set_error("cannot open %s for writing", path);
+        return SO_EIO;
+    }
+    std::string buf;
+    buf.reserve(1 << 20);
+    char num[256];
+    for (int64_t k = 0; k < n; k++) {
+        const so_hit &r = rows[k];
+        const char *hq, *ht;
+        int64_t lq, lt;
+        if (so_fasta_header(queries, r.query, &hq, &lq) != SO_OK || so_fasta_header(targets, r.target, &ht, &lt) != SO_OK) {
+            fclose(f);
+            return SO_EINVAL;
+        }
+        // ids = header up to the first space (fsearch.py:3066)
+        int64_t iq = 0, it = 0;
+        while (iq < lq && hq[iq] != ' ') iq++;
+        while (it < lt && ht[it] != ' ') it++;
+        buf.append(hq, (size_t)iq);
+        buf += '\t';
+        buf.append(ht, (size_t)it);
+        buf += '\t';
+        buf += so::fmt_identity(r.identity);
+        snprintf(num, sizeof num, "\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t", r.aln_len, r.mismatch, r.gaps, r.qst, r.qed, r.sst,
+                 r.sed);
+        buf += num;
+        buf += so::f2s(r.evalue);
+        snprintf(num, sizeof num, "\t%lld\t%d\t%d\t%lld\t", (long long)r.bit, r.qlen, r.tlen, (long long)r.query);
+        buf += num;
+        buf.append(ht, (size_t)lt);
+        buf += '\n';
+        if (buf.size() > (1 << 20) - 4096) {
+            if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
+                fclose(f);
+                set_error("short write on %s", path);
+                return SO_EIO;
+            }
+            buf.clear();
+        }
+    }
+    if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
+        fclose(f);
+        set_error("short write on %s", path);
+        return SO_EIO;
+    }
+    fclose(f);
+    return SO_OK;
+}
+}

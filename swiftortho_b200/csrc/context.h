@@ -1,0 +1,111 @@
+// Device-side state of one search context (one process / one B200).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <chrono>
+
+#include "common.h"
+
+namespace so {
+
+#define SO_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            so::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                          cudaGetErrorString(e_));                                             \
+            return SO_ENODEV;                                                                  \
+        }                                                                                      \
+    } while (0)
+
+// growable device buffer
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return SO_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e != cudaSuccess) {
+            cap = 0;
+            set_error("cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e));
+            return SO_ENOMEM;
+        }
+        cap = want;
+        return SO_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// One target chunk index resident in HBM (K3).
+struct ChunkIndex {
+    i64 c0 = 0, c1 = 0;          // target ordinals [c0, c1)
+    uint32_t total = 0;          // residues in the chunk
+    uint32_t n_seeds = 0;        // len(locus)
+    i64 n_used = 0;              // non-empty buckets
+    i64 threshold = 0;
+    uint32_t max_tlen = 0;
+    uint32_t *d_start = nullptr; // [NC + 1] start[b] = #entries with bucket < b
+    uint32_t *d_locus = nullptr; // [n_seeds] reverse insertion order inside a bucket
+    uint32_t *d_soas = nullptr;  // [M + 1] residue offsets inside the chunk
+    uint2 *d_hdsst = nullptr;    // [n_seeds] (sequence + 1, position) of every locus entry (bisect quirk applied)
+    double build_ms = 0;
+};
+
+struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double ms() const {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
+
+}  // namespace so
+
+struct so_ctx {
+    int device = 0;
+    so::Params P;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+
+    // targets (raw bytes) and queries (seg-masked bytes), packed, resident in HBM
+    so::i64 n_t = 0, n_q = 0;
+    std::vector<uint64_t> t_off, q_off;       // host copies of the offsets
+    std::vector<uint8_t> q_masked;            // host copy of the masked queries
+    const uint8_t *t_host = nullptr;          // caller-owned (valid during so_set_targets only)
+    uint8_t *d_tres = nullptr, *d_qres = nullptr;
+    uint64_t *d_toff = nullptr, *d_qoff = nullptr;
+    uint32_t *d_perm = nullptr;               // per query: positions in the reference quicksort order of -kscs (S3)
+    so::i64 sub_block = 0;                    // >0: fixed number of queries per seeding sub-block (tests)
+    uint32_t max_qlen = 0, max_tlen = 0;
+
+    std::vector<so::ChunkIndex> chunks;
+
+    // scratch (grown on demand, reused)
+    so::DBuf<uint8_t> scratch[32];
+    so::DBuf<uint64_t> trace;
+    void *h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+
+    so_stats stats = {};
+};
+
+namespace so {
+// implemented in the .cu files
+int upload_tables();
+int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out);
+int build_chunk_index(so_ctx *c, ChunkIndex &ix);
+void free_chunk_index(ChunkIndex &ix);
+struct BlockCands {                 // candidates of a query block against one chunk, reference order
+    std::vector<uint64_t> offsets;  // [nq + 1]
+    std::vector<so_cand> cands;
+};
+int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, BlockCands &out);
+int ensure_pinned(so_ctx *c, size_t bytes);
+}  // namespace so

@@ -1,0 +1,756 @@
+// K1-K6: index build, seed lookup, diagonal grouping and chained X-drop scoring on sm_100a.
+//
+// Index of one target chunk (replaces Fasta.build_msav, lib/fsearch.py:2208-2280)
+//   k_target_seeds   one thread per (residue offset, alphabet, pattern): whole-span x/X veto,
+//                    FNV-1a-32 over the care positions + the pattern ordinal, % NC, cross-pattern
+//                    dedup (spseeds_fnv, fsearch.py:519-556).  The key is written at the MIRRORED
+//                    insertion ordinal, so a STABLE radix sort on the bucket alone reproduces the
+//                    reference's reverse-insertion order inside a bucket (fsearch.py:2258-2266).
+//   radix sort       cub::DeviceRadixSort (library) on ceil(log2(NC+1)) bits
+//   k_bucket_starts  dense start[NC+1] table (start[b] = #entries with bucket < b) = the
+//                    reference's `start` list after the fill pass
+//   k_locus_decode   (sequence+1, position) of every locus entry with the reference's bisect quirk
+//                    (fsearch.py:2638-2642 + 134-153: largest idx with soas[idx] < x, so position 0
+//                    of sequence k is attributed to sequence k-1 at position len(k-1))
+// Search of a query block against one chunk (replaces Fasta.find_msav_m, fsearch.py:2645-2724)
+//   k_query_seeds    seeds of every query position -> bucket range [st, ed) with the reference's
+//                    clipping (get_bin_mem, fsearch.py:2530-2541: L = len(locus)-1; bucket NC-1 empty)
+//   k_filter         one warp per query: walk the positions in the reference's quicksort order of
+//                    -kscs (order computed once on the host), keep while the running bucket total
+//                    is <= threshold*len (fsearch.py:2667-2677)
+//   exclusive scan   cub::DeviceScan (library)
+//   k_expand         one warp per kept seed: emits (query, target, diagonal, qst) keys + the hit's
+//                    ordinal in the reference's scan order (its "first appearance" rank)
+//   radix sort       cub::DeviceRadixSort (library) on the packed key
+//   k_pair_ungap     one thread per (query, target) run of the sorted hits: per diagonal the
+//                    chained X-drop-30 extension (ungap / get_ungap_scores, fsearch.py:2454-2509),
+//                    threshold 25, best diagonal with first-appearance tie break, candidate order
+//                    key = rank of the first passing diagonal (fsearch.py:2696-2719)
+//   radix sort       candidates by (query, first-passing rank) -> reference candidate order
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+
+#include "context.h"
+
+namespace so {
+
+struct SeedCfg {
+    int S, A, step;
+    uint32_t nc;
+    int k[16];
+    uint32_t care[16];
+};
+__constant__ SeedCfg c_cfg;
+__constant__ uint16_t c_alpha[4 * 256];
+__constant__ int8_t c_score2[kClasses * kClasses];
+__constant__ uint8_t c_code2[256];
+
+static int upload_cfg(const Params &P) {
+    SeedCfg h;
+    memset(&h, 0, sizeof h);
+    h.S = (int)P.patterns.size();
+    h.A = (int)P.alphabets.size();
+    h.step = P.step;
+    h.nc = P.nc;
+    for (int s = 0; s < h.S; s++) {
+        h.k[s] = (int)P.patterns[(size_t)s].size();
+        uint32_t m = 0;
+        for (int j = 0; j < h.k[s]; j++)
+            if (P.patterns[(size_t)s][(size_t)j] != '0') m |= 1u << j;
+        h.care[s] = m;
+    }
+    uint16_t al[4 * 256];
+    memset(al, 0, sizeof al);
+    for (int a = 0; a < h.A; a++)
+        for (int i = 0; i < 256; i++) al[a * 256 + i] = P.alphabets[(size_t)a][(size_t)i];
+    int8_t tbl[kClasses * kClasses];
+    uint8_t code[256];
+    make_score_table(tbl);
+    make_code_table(code);
+    SO_CUDA(cudaMemcpyToSymbol(c_cfg, &h, sizeof h));
+    SO_CUDA(cudaMemcpyToSymbol(c_alpha, al, sizeof al));
+    SO_CUDA(cudaMemcpyToSymbol(c_score2, tbl, sizeof tbl));
+    SO_CUDA(cudaMemcpyToSymbol(c_code2, code, sizeof code));
+    return SO_OK;
+}
+
+// hash of the seed of pattern s / alphabet a starting at seq[i]; false if the span leaves the
+// sequence or holds x/X
+__device__ __forceinline__ bool seed_hash(const uint8_t *seq, int L, int i, int a, int s, const uint16_t *s_alpha,
+                                          uint32_t &bucket) {
+    const int k = c_cfg.k[s];
+    if (i + k > L) return false;
+    const uint32_t care = c_cfg.care[s];
+    uint32_t n = 0x811c9dc5u;
+    for (int j = 0; j < k; j++) {
+        const uint32_t ch = seq[i + j];
+        if (ch == 'x' || ch == 'X') return false;
+        if ((care >> j) & 1u) n = (n ^ (uint32_t)s_alpha[a * 256 + ch]) * 0x01000193u;
+    }
+    n = (n ^ (uint32_t)s) * 0x01000193u;
+    bucket = n % c_cfg.nc;
+    return true;
+}
+
+// emitted by spseeds_fnv? (valid and not a repeat of an earlier pattern's (bucket, i) in this alphabet)
+__device__ __forceinline__ bool seed_emitted(const uint8_t *seq, int L, int i, int a, int s,
+                                             const uint16_t *s_alpha, uint32_t &bucket) {
+    if (!seed_hash(seq, L, i, a, s, s_alpha, bucket)) return false;
+    for (int s2 = 0; s2 < s; s2++) {
+        uint32_t b2;
+        if (seed_hash(seq, L, i, a, s2, s_alpha, b2) && b2 == bucket) return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ void load_alpha(uint16_t *s_alpha) {
+    for (int k = threadIdx.x; k < c_cfg.A * 256; k += blockDim.x) s_alpha[k] = c_alpha[k];
+    __syncthreads();
+}
+
+// largest j with a[j] <= x  (a[0] = 0 <= x always)
+__device__ __forceinline__ int seq_of(const uint32_t *__restrict__ a, int n, uint32_t x) {
+    int lo = 0, hi = n;  // a has n+1 entries; answer in [0, n-1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] <= x)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------ index
+__global__ void __launch_bounds__(256) k_target_seeds(const uint8_t *__restrict__ res, const uint32_t *__restrict__ soas,
+                                                      int M, uint32_t total, uint32_t nslots,
+                                                      uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    __shared__ uint16_t s_alpha[4 * 256];
+    load_alpha(s_alpha);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nslots) return;
+    const int AS = c_cfg.A * c_cfg.S;
+    const uint32_t x = tid / AS;
+    const int as = (int)(tid % AS);
+    const int a = as / c_cfg.S, s = as % c_cfg.S;
+    const int j = seq_of(soas, M, x);
+    const uint32_t base = soas[j];
+    const int L = (int)(soas[j + 1] - base);
+    const int i = (int)(x - base);
+    const uint32_t ord = base * AS + (uint32_t)as * (uint32_t)L + (uint32_t)i;  // insertion ordinal
+    uint32_t bucket = c_cfg.nc;
+    if (i % c_cfg.step == 0) {
+        uint32_t b;
+        if (seed_emitted(res + base, L, i, a, s, s_alpha, b)) bucket = b;
+    }
+    const uint32_t pos = nslots - 1 - ord;
+    keys[pos] = bucket;
+    vals[pos] = x;
+    (void)total;
+}
+
+__global__ void __launch_bounds__(256) k_bucket_starts(const uint32_t *__restrict__ keys, uint32_t n, uint32_t nc,
+                                                       uint32_t *__restrict__ start) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n) return;
+    const long long prev = p == 0 ? -1 : (long long)min(keys[p - 1], nc);
+    const long long cur = p == n ? (long long)nc : (long long)min(keys[p], nc);
+    for (long long b = prev + 1; b <= cur; b++) start[b] = p;
+}
+
+__global__ void __launch_bounds__(256) k_locus_decode(const uint32_t *__restrict__ locus, uint32_t n,
+                                                      const uint32_t *__restrict__ soas, int M,
+                                                      uint2 *__restrict__ out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t x = locus[p];
+    // bisect(soas, x): largest idx with soas[idx] < x, -1 if none
+    int lo = -1, hi = M + 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (soas[mid] < x)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    uint2 r;
+    r.x = (uint32_t)(lo + 1);                 // 0 = the reference's idx -1 (never scores; dropped)
+    r.y = lo >= 0 ? x - soas[lo] : 0u;        // sst (may equal the sequence length)
+    out[p] = r;
+}
+
+void free_chunk_index(ChunkIndex &ix) {
+    if (ix.d_start) cudaFree(ix.d_start);
+    if (ix.d_locus) cudaFree(ix.d_locus);
+    if (ix.d_soas) cudaFree(ix.d_soas);
+    if (ix.d_hdsst) cudaFree(ix.d_hdsst);
+    ix.d_start = ix.d_locus = ix.d_soas = nullptr;
+    ix.d_hdsst = nullptr;
+}
+
+int build_chunk_index(so_ctx *c, ChunkIndex &ix) {
+    const Params &P = c->P;
+    int rc;
+    if ((rc = upload_cfg(P)) != SO_OK) return rc;
+    const i64 M = ix.c1 - ix.c0;
+    std::vector<uint32_t> soas((size_t)M + 1);
+    const uint64_t base = c->t_off[(size_t)ix.c0];
+    uint32_t maxlen = 0;
+    for (i64 j = 0; j <= M; j++) {
+        uint64_t v = c->t_off[(size_t)(ix.c0 + j)] - base;
+        if (v > 0xfffffff0ull) {
+            set_error("target chunk holds more than 4 Gi residues; lower -c");
+            return SO_ELIMIT;
+        }
+        soas[(size_t)j] = (uint32_t)v;
+        if (j > 0) maxlen = std::max<uint32_t>(maxlen, soas[(size_t)j] - soas[(size_t)j - 1]);
+    }
+    ix.total = soas[(size_t)M];
+    ix.max_tlen = maxlen;
+    const int AS = (int)(P.alphabets.size() * P.patterns.size());
+    const uint64_t nslots64 = (uint64_t)ix.total * (uint64_t)AS;
+    if (nslots64 > 0x7fffff00ull) {
+        set_error("target chunk has too many seed slots (%llu); lower -c", (unsigned long long)nslots64);
+        return SO_ELIMIT;
+    }
+    const uint32_t nslots = (uint32_t)nslots64;
+    SO_CUDA(cudaMalloc((void **)&ix.d_soas, ((size_t)M + 1) * sizeof(uint32_t)));
+    SO_CUDA(cudaMemcpyAsync(ix.d_soas, soas.data(), ((size_t)M + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                            c->stream));
+    SO_CUDA(cudaMalloc((void **)&ix.d_start, ((size_t)P.nc + 1) * sizeof(uint32_t)));
+    SO_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    std::vector<uint32_t> h_keys;
+    if (nslots > 0) {
+        if ((rc = c->scratch[4].reserve((size_t)nslots * 4)) != SO_OK) return rc;
+        if ((rc = c->scratch[5].reserve((size_t)nslots * 4)) != SO_OK) return rc;
+        if ((rc = c->scratch[6].reserve((size_t)nslots * 4)) != SO_OK) return rc;
+        if ((rc = c->scratch[7].reserve((size_t)nslots * 4)) != SO_OK) return rc;
+        uint32_t *k_in = (uint32_t *)c->scratch[4].p, *v_in = (uint32_t *)c->scratch[5].p;
+        uint32_t *k_out = (uint32_t *)c->scratch[6].p, *v_out = (uint32_t *)c->scratch[7].p;
+        k_target_seeds<<<(nslots + 255) / 256, 256, 0, c->stream>>>(c->d_tres + base, ix.d_soas, (int)M, ix.total,
+                                                                    nslots, k_in, v_in);
+        int bits = 1;
+        while (bits < 32 && (1ull << bits) <= (uint64_t)P.nc) bits++;
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)nslots, 0, bits, c->stream);
+        if ((rc = c->scratch[11].reserve(tmp)) != SO_OK) return rc;
+        SO_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch[11].p, tmp, k_in, k_out, v_in, v_out, (int)nslots, 0, bits,
+                                                c->stream));
+        k_bucket_starts<<<(nslots + 1 + 255) / 256, 256, 0, c->stream>>>(k_out, nslots, P.nc, ix.d_start);
+        c->stats.kernel_launches += 2;
+        c->stats.lib_launches += 1;
+        SO_CUDA(cudaGetLastError());
+        h_keys.resize(nslots);
+        SO_CUDA(cudaMemcpyAsync(h_keys.data(), k_out, (size_t)nslots * 4, cudaMemcpyDeviceToHost, c->stream));
+        SO_CUDA(cudaStreamSynchronize(c->stream));
+        c->stats.d2h_bytes += (i64)nslots * 4;
+        uint32_t nseeds = 0;
+        while (nseeds < nslots && h_keys[nseeds] < P.nc) nseeds++;  // invalid slots carry key NC and sort last
+        // (linear scan is fine: it also feeds the threshold below)
+        ix.n_seeds = nseeds;
+        if (nseeds > 0) {
+            SO_CUDA(cudaMalloc((void **)&ix.d_locus, (size_t)nseeds * sizeof(uint32_t)));
+            SO_CUDA(cudaMalloc((void **)&ix.d_hdsst, (size_t)nseeds * sizeof(uint2)));
+            SO_CUDA(cudaMemcpyAsync(ix.d_locus, v_out, (size_t)nseeds * 4, cudaMemcpyDeviceToDevice, c->stream));
+            k_locus_decode<<<(nseeds + 255) / 256, 256, 0, c->stream>>>(ix.d_locus, nseeds, ix.d_soas, (int)M,
+                                                                        ix.d_hdsst);
+            c->stats.kernel_launches += 1;
+        }
+    } else {
+        ix.n_seeds = 0;
+        SO_CUDA(cudaMemsetAsync(ix.d_start, 0, ((size_t)P.nc + 1) * sizeof(uint32_t), c->stream));
+    }
+    SO_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    SO_CUDA(cudaStreamSynchronize(c->stream));
+    SO_CUDA(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    ix.build_ms = ms;
+    // get_mu_sd (fsearch.py:746-761) over the non-empty bucket counts in bucket order: N starts
+    // at 1, sequential double accumulation; threshold = int(mu + 2 sd) (fsearch.py:2248-2250)
+    {
+        double N = 1, mu = 0.;
+        std::vector<uint32_t> counts;
+        for (uint32_t p = 0; p < ix.n_seeds;) {
+            uint32_t q = p + 1;
+            while (q < ix.n_seeds && h_keys[q] == h_keys[p]) q++;
+            counts.push_back(q - p);
+            p = q;
+        }
+        for (uint32_t v : counts) mu += (double)v, N += 1;
+        mu /= N;
+        double sd = 0.;
+        for (uint32_t v : counts) sd += std::pow((double)v - mu, 2);
+        sd = std::sqrt(sd / N);
+        ix.n_used = (i64)counts.size();
+        ix.threshold = (i64)(mu + 2 * sd);
+        // `thr < 1 and DB.threshold or thr` (fsearch.py:2992)
+        if (!(P.thr < 1 && ix.threshold != 0)) ix.threshold = P.thr;
+    }
+    return SO_OK;
+}
+
+// ------------------------------------------------------------------------------------------ search
+struct BlockGeom {
+    int nq;            // queries in the sub-block
+    int qb0;           // first query ordinal
+    int qst_bits, diag_bits, hd_bits;
+    int diag_bias;
+    uint32_t L;        // len(locus) - 1
+    uint32_t nc;
+    long long thr_mul; // threshold
+    int mink;
+    int c0;            // chunk start (global target ordinal)
+};
+
+// slot layout of query q: slot_off[q] + as * Lq + i
+__global__ void __launch_bounds__(256) k_query_seeds(const uint8_t *__restrict__ qres, const uint64_t *__restrict__ qoff,
+                                                     const uint32_t *__restrict__ slot_off, BlockGeom g,
+                                                     const uint32_t *__restrict__ start, uint32_t nslots,
+                                                     uint32_t *__restrict__ slot_st, uint32_t *__restrict__ slot_cnt) {
+    __shared__ uint16_t s_alpha[4 * 256];
+    load_alpha(s_alpha);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nslots) return;
+    const int ql = seq_of(slot_off, g.nq, tid);
+    const uint64_t qbase = qoff[g.qb0 + ql];
+    const int L = (int)(qoff[g.qb0 + ql + 1] - qbase);
+    const uint32_t rel = tid - slot_off[ql];
+    const int as = (int)(rel / (uint32_t)L);
+    const int i = (int)(rel % (uint32_t)L);
+    const int a = as / c_cfg.S, s = as % c_cfg.S;
+    uint32_t st = 0, cnt = 0, b;
+    if (seed_emitted(qres + qbase, L, i, a, s, s_alpha, b)) {
+        // get_bin_mem: the last bucket is empty; end clipped to len(locus)-1
+        if (b + 1 < g.nc) {
+            st = start[b];
+            uint32_t ed = min(start[b + 1], g.L);
+            cnt = ed > st ? ed - st : 0;
+        }
+    }
+    slot_st[tid] = st;
+    slot_cnt[tid] = cnt;
+}
+
+// one warp per query
+__global__ void __launch_bounds__(256) k_filter(const uint64_t *__restrict__ qoff, const uint32_t *__restrict__ slot_off,
+                                                const uint32_t *__restrict__ perm, BlockGeom g,
+                                                uint32_t *__restrict__ slot_cnt) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= g.nq) return;
+    const uint64_t qbase = qoff[g.qb0 + w];
+    const int L = (int)(qoff[g.qb0 + w + 1] - qbase);
+    const int P = L - g.mink + 1;
+    if (P <= 0) return;
+    const int AS = c_cfg.A * c_cfg.S;
+    const uint32_t so0 = slot_off[w];
+    const long long thr = g.thr_mul * (long long)L;
+    long long carry = 0;
+    for (int r0 = 0; r0 < P; r0 += 32) {
+        const int r = r0 + lane;
+        int pos = -1;
+        long long ct = 0;
+        if (r < P) {
+            pos = (int)perm[qbase + r];
+            for (int as = 0; as < AS; as++) ct += slot_cnt[so0 + (uint32_t)as * (uint32_t)L + (uint32_t)pos];
+        }
+        long long inc = ct;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const long long before = carry + inc - ct;  // running total before this position
+        if (r < P && before > thr)
+            for (int as = 0; as < AS; as++) slot_cnt[so0 + (uint32_t)as * (uint32_t)L + (uint32_t)pos] = 0;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+// one warp per slot
+__global__ void __launch_bounds__(256) k_expand(const uint32_t *__restrict__ slot_off, BlockGeom g, uint32_t nslots,
+                                                const uint64_t *__restrict__ qoff,
+                                                const uint32_t *__restrict__ slot_st, const uint32_t *__restrict__ slot_cnt,
+                                                const uint64_t *__restrict__ slot_out, const uint2 *__restrict__ hdsst,
+                                                uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < nslots; slot += nwarps) {
+        const uint32_t cnt = slot_cnt[slot];
+        if (cnt == 0) continue;
+        const int ql = seq_of(slot_off, g.nq, slot);
+        const int L = (int)(qoff[g.qb0 + ql + 1] - qoff[g.qb0 + ql]);
+        const uint32_t rel = slot - slot_off[ql];
+        const int qst = (int)(rel % (uint32_t)L);
+        const uint32_t st = slot_st[slot], out0 = (uint32_t)slot_out[slot];
+        const uint64_t hi = (uint64_t)ql << (g.hd_bits + g.diag_bits + g.qst_bits);
+        for (uint32_t k = lane; k < cnt; k += 32) {
+            const uint2 e = hdsst[st + k];
+            uint64_t key = ~0ull;  // hits attributed to "sequence -1" can never score: dropped
+            if (e.x != 0) {
+                const int diag = qst - (int)e.y + g.diag_bias;
+                key = hi | ((uint64_t)e.x << (g.diag_bits + g.qst_bits)) | ((uint64_t)diag << g.qst_bits) | (uint64_t)qst;
+            }
+            keys[out0 + k] = key;
+            vals[out0 + k] = out0 + k;
+        }
+    }
+}
+
+struct ChainState {
+    int total, x, qlo, slo;
+};
+
+__device__ __forceinline__ void chain_seed(ChainState &ch, int Q, int diag, const uint8_t *__restrict__ q, int ql,
+                                           const uint8_t *__restrict__ t, int tl, const int8_t *s_tbl,
+                                           const uint8_t *s_code) {
+    // ungap(qseq, sseq, Qst, Sst, qlo, slo) with dropX = 30 (fsearch.py:2454-2494); s = q - diag
+    int S = Q - diag;
+    const int off = max(max(ch.qlo - Q, ch.slo - S), 0);
+    Q += off;
+    int qq = Q, score = 0, mx = 0, mx_qed = Q;
+    while (qq > ch.qlo && qq < ql && (qq - diag) > ch.slo && (qq - diag) < tl) {
+        score += s_tbl[(int)s_code[q[qq]] * kClasses + s_code[t[qq - diag]]];
+        if (score > mx) {
+            mx = score;
+            mx_qed = qq;
+        } else if (score + 30 < mx)
+            break;
+        qq++;
+    }
+    qq = Q - 1;
+    score = mx;
+    while (qq < ql && qq > ch.qlo && (qq - diag) < tl && (qq - diag) > ch.slo) {
+        score += s_tbl[(int)s_code[q[qq]] * kClasses + s_code[t[qq - diag]]];
+        if (score > mx)
+            mx = score;
+        else if (score + 30 < mx)
+            break;
+        qq--;
+    }
+    ch.total += mx;
+    ch.qlo = mx_qed;            // next seed: qlo = max_qed, slo = max_sed (fsearch.py:2502-2506)
+    ch.slo = mx_qed - diag;
+}
+
+__global__ void __launch_bounds__(128) k_pair_ungap(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                    uint32_t n, BlockGeom g, const uint8_t *__restrict__ qres,
+                                                    const uint64_t *__restrict__ qoff, const uint8_t *__restrict__ tres,
+                                                    const uint64_t *__restrict__ toff, uint64_t *__restrict__ ckeys,
+                                                    uint64_t *__restrict__ cvals, unsigned long long *__restrict__ counter) {
+    __shared__ int8_t s_tbl[kClasses * kClasses];
+    __shared__ uint8_t s_code[256];
+    for (int k = threadIdx.x; k < kClasses * kClasses; k += blockDim.x) s_tbl[k] = c_score2[k];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_code[k] = c_code2[k];
+    __syncthreads();
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pair_shift = g.qst_bits + g.diag_bits;
+    bool head = false;
+    uint64_t key = 0;
+    if (p < n) {
+        key = keys[p];
+        head = key != ~0ull && (p == 0 || (keys[p - 1] >> pair_shift) != (key >> pair_shift));
+    }
+    int best_score = 0, best_diag = 0;
+    uint32_t best_rank = 0xffffffffu, first_rank = 0xffffffffu;
+    int ql_idx = 0, hd1 = 0;
+    if (head) {
+        const uint64_t pair = key >> pair_shift;
+        hd1 = (int)(pair & ((1ull << g.hd_bits) - 1));
+        ql_idx = (int)(pair >> g.hd_bits);
+        const uint64_t qb = qoff[g.qb0 + ql_idx];
+        const int ql = (int)(qoff[g.qb0 + ql_idx + 1] - qb);
+        const int tid = g.c0 + hd1 - 1;
+        const uint64_t tb = toff[tid];
+        const int tl = (int)(toff[tid + 1] - tb);
+        const uint8_t *q = qres + qb, *t = tres + tb;
+        const uint64_t qmask = (1ull << g.qst_bits) - 1, dmask = (1ull << g.diag_bits) - 1;
+        uint32_t e = p;
+        while (e < n) {
+            uint64_t ke = keys[e];
+            if ((ke >> pair_shift) != pair) break;
+            const uint64_t grp = ke >> g.qst_bits;
+            const int diag = (int)(grp & dmask) - g.diag_bias;
+            ChainState ch;
+            ch.total = 0, ch.x = 0, ch.qlo = 0, ch.slo = 0;
+            uint32_t rank_min = 0xffffffffu;
+            int prev_q = -1;
+            while (true) {
+                const int qst = (int)(ke & qmask);
+                rank_min = min(rank_min, vals[e]);
+                if (qst != prev_q) {
+                    chain_seed(ch, qst, diag, q, ql, t, tl, s_tbl, s_code);
+                    prev_q = qst;
+                }
+                e++;
+                if (e >= n) break;
+                ke = keys[e];
+                if ((ke >> g.qst_bits) != grp) break;
+            }
+            if (ch.total >= 25) {  // self.min (fsearch.py:2224, 2707)
+                first_rank = min(first_rank, rank_min);
+                if (ch.total > best_score || (ch.total == best_score && rank_min < best_rank)) {
+                    best_score = ch.total;
+                    best_rank = rank_min;
+                    best_diag = diag;
+                }
+            }
+        }
+    }
+    // warp-aggregated append of the candidates
+    const bool emit = head && best_score >= 25;
+    const unsigned m = __ballot_sync(0xffffffffu, emit);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (emit) {
+            const unsigned long long o = base + __popc(m & ((1u << lane) - 1));
+            ckeys[o] = ((uint64_t)ql_idx << 32) | first_rank;
+            // value: target ordinal (24 bits) | score (20 bits) | diagonal + bias (20 bits)
+            cvals[o] = ((uint64_t)(uint32_t)(g.c0 + hd1 - 1) << 40) | ((uint64_t)(uint32_t)best_score << 20) |
+                       (uint64_t)(uint32_t)(best_diag + g.diag_bias);
+        }
+    }
+}
+
+__global__ void k_query_bounds(const uint64_t *__restrict__ ckeys, uint32_t n, int nq, uint32_t *__restrict__ bounds) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > nq) return;
+    // first index whose query field is >= q
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((uint32_t)(ckeys[mid] >> 32) < (uint32_t)q)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    bounds[q] = lo;
+}
+
+struct Widen {
+    __host__ __device__ __forceinline__ uint64_t operator()(const uint32_t &v) const { return (uint64_t)v; }
+};
+
+static int bits_for(uint64_t maxval) {  // bits needed to hold values 0..maxval
+    int b = 1;
+    while (b < 63 && (1ull << b) <= maxval) b++;
+    return b;
+}
+
+enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TMP, SC_CKA, SC_CKB, SC_CVA, SC_CVB, SC_MISC };
+
+static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
+
+int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, BlockCands &out) {
+    const Params &P = c->P;
+    const i64 nq_total = q_end - q_begin;
+    out.offsets.assign((size_t)nq_total + 1, 0);
+    out.cands.clear();
+    if (nq_total <= 0) return SO_OK;
+    if (ix.n_seeds == 0) return SO_OK;
+    int rc;
+    if ((rc = upload_cfg(P)) != SO_OK) return rc;
+    const int AS = (int)(P.alphabets.size() * P.patterns.size());
+    const i64 M = ix.c1 - ix.c0;
+    i64 sub = c->sub_block > 0 ? c->sub_block : 256;
+    i64 b0 = q_begin;
+    cudaStream_t st = c->stream;
+    while (b0 < q_end) {
+        i64 b1 = std::min<i64>(q_end, b0 + sub);
+        const int nq = (int)(b1 - b0);
+        // slot offsets (queries shorter than the shortest seed span get no slots: the reference
+        // indexes out of bounds there (fsearch.py:2648-2652); defined as "no hits")
+        std::vector<uint32_t> slot_off((size_t)nq + 1, 0);
+        uint32_t maxql = 1;
+        uint64_t tot = 0;
+        for (int k = 0; k < nq; k++) {
+            uint64_t L = c->q_off[(size_t)(b0 + k + 1)] - c->q_off[(size_t)(b0 + k)];
+            uint64_t n = (L >= (uint64_t)P.mink) ? L * (uint64_t)AS : 0;
+            if (n) maxql = std::max<uint32_t>(maxql, (uint32_t)L);
+            tot += n;
+            if (tot > 0x7fffff00ull) break;
+            slot_off[(size_t)k + 1] = (uint32_t)tot;
+        }
+        if (tot > 0x7fffff00ull) {
+            if (nq == 1) {
+                set_error("query %lld alone exceeds the seed slot limit", (long long)b0);
+                return SO_ELIMIT;
+            }
+            sub = std::max<i64>(1, nq / 2);
+            continue;
+        }
+        const uint32_t nslots = (uint32_t)tot;
+        if (nslots == 0) {
+            b0 = b1;
+            continue;
+        }
+        BlockGeom g;
+        g.nq = nq;
+        g.qb0 = (int)b0;
+        g.qst_bits = bits_for(maxql);
+        g.diag_bias = (int)ix.max_tlen + 1;
+        g.diag_bits = bits_for((uint64_t)maxql + ix.max_tlen + 2);
+        g.hd_bits = bits_for((uint64_t)M + 1);
+        const int q_bits = bits_for((uint64_t)nq);
+        if (g.qst_bits + g.diag_bits + g.hd_bits + q_bits > 63) {
+            if (nq == 1) {
+                set_error("sequence too long for the seed key layout");
+                return SO_ELIMIT;
+            }
+            sub = std::max<i64>(1, nq / 2);
+            continue;
+        }
+        g.L = ix.n_seeds - 1;
+        g.nc = P.nc;
+        g.thr_mul = ix.threshold;
+        g.mink = P.mink;
+        g.c0 = (int)ix.c0;
+        if ((rc = c->scratch[SC_SLOTOFF].reserve(((size_t)nq + 1) * 4)) != SO_OK) return rc;
+        if ((rc = c->scratch[SC_ST].reserve((size_t)nslots * 4)) != SO_OK) return rc;
+        if ((rc = c->scratch[SC_CNT].reserve(((size_t)nslots + 1) * 4)) != SO_OK) return rc;
+        if ((rc = c->scratch[SC_OUT].reserve(((size_t)nslots + 1) * 8)) != SO_OK) return rc;
+        if ((rc = c->scratch[SC_MISC].reserve(((size_t)nq + 2) * 4 + 64)) != SO_OK) return rc;
+        uint32_t *d_slot_off = (uint32_t *)c->scratch[SC_SLOTOFF].p;
+        uint32_t *d_st = (uint32_t *)c->scratch[SC_ST].p, *d_cnt = (uint32_t *)c->scratch[SC_CNT].p;
+        uint64_t *d_out = (uint64_t *)c->scratch[SC_OUT].p;
+        SO_CUDA(cudaMemcpyAsync(d_slot_off, slot_off.data(), ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, st));
+        c->stats.h2d_bytes += ((i64)nq + 1) * 4;
+        SO_CUDA(cudaEventRecord(c->ev[0], st));
+        k_query_seeds<<<(nslots + 255) / 256, 256, 0, st>>>(c->d_qres, c->d_qoff, d_slot_off, g, ix.d_start, nslots, d_st,
+                                                            d_cnt);
+        k_filter<<<(nq * 32 + 255) / 256, 256, 0, st>>>(c->d_qoff, d_slot_off, c->d_perm, g, d_cnt);
+        SO_CUDA(cudaMemsetAsync(d_cnt + nslots, 0, 4, st));
+        size_t tmp = 0;
+        cub::TransformInputIterator<uint64_t, Widen, const uint32_t *> cnt64(d_cnt, Widen());
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt64, d_out, (int)nslots + 1, st);
+        if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+        SO_CUDA(cub::DeviceScan::ExclusiveSum(c->scratch[SC_TMP].p, tmp, cnt64, d_out, (int)nslots + 1, st));
+        c->stats.kernel_launches += 2;
+        c->stats.lib_launches += 1;
+        uint64_t H = 0;
+        SO_CUDA(cudaMemcpyAsync(&H, d_out + nslots, 8, cudaMemcpyDeviceToHost, st));
+        SO_CUDA(cudaStreamSynchronize(st));
+        SO_CUDA(cudaGetLastError());
+        if (H > kHitCap && nq > 1) {
+            sub = std::max<i64>(1, nq / 2);
+            continue;
+        }
+        if (H > 0xfffffff0ull) {
+            set_error("query %lld produces too many seed hits", (long long)b0);
+            return SO_ELIMIT;
+        }
+        c->stats.seed_hits += (i64)H;
+        if (H > 0) {
+            if ((rc = c->scratch[SC_KA].reserve((size_t)H * 8)) != SO_OK) return rc;
+            if ((rc = c->scratch[SC_KB].reserve((size_t)H * 8)) != SO_OK) return rc;
+            if ((rc = c->scratch[SC_VA].reserve((size_t)H * 4)) != SO_OK) return rc;
+            if ((rc = c->scratch[SC_VB].reserve((size_t)H * 4)) != SO_OK) return rc;
+            uint64_t *ka = (uint64_t *)c->scratch[SC_KA].p, *kb = (uint64_t *)c->scratch[SC_KB].p;
+            uint32_t *va = (uint32_t *)c->scratch[SC_VA].p, *vb = (uint32_t *)c->scratch[SC_VB].p;
+            const int ewarps = 148 * 64;
+            k_expand<<<ewarps * 32 / 256, 256, 0, st>>>(d_slot_off, g, nslots, c->d_qoff, d_st, d_cnt, d_out, ix.d_hdsst, ka,
+                                                        va);
+            SO_CUDA(cudaEventRecord(c->ev[1], st));
+            const int key_bits = g.qst_bits + g.diag_bits + g.hd_bits + q_bits;
+            // dropped hits carry ~0 and must sort last: include one extra bit above the fields
+            const int end_bit = std::min(64, key_bits + 1);
+            cub::DoubleBuffer<uint64_t> dk(ka, kb);
+            cub::DoubleBuffer<uint32_t> dv(va, vb);
+            tmp = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)H, 0, end_bit, st);
+            if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+            SO_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch[SC_TMP].p, tmp, dk, dv, (int)H, 0, end_bit, st));
+            SO_CUDA(cudaEventRecord(c->ev[2], st));
+            // candidates: at most one per (query, target) pair
+            const uint64_t ccap = std::min<uint64_t>(H, (uint64_t)nq * (uint64_t)(M + 1));
+            if ((rc = c->scratch[SC_CKA].reserve((size_t)ccap * 8)) != SO_OK) return rc;
+            if ((rc = c->scratch[SC_CKB].reserve((size_t)ccap * 8)) != SO_OK) return rc;
+            if ((rc = c->scratch[SC_CVA].reserve((size_t)ccap * 8)) != SO_OK) return rc;
+            if ((rc = c->scratch[SC_CVB].reserve((size_t)ccap * 8)) != SO_OK) return rc;
+            uint64_t *cka = (uint64_t *)c->scratch[SC_CKA].p, *ckb = (uint64_t *)c->scratch[SC_CKB].p;
+            uint64_t *cva = (uint64_t *)c->scratch[SC_CVA].p, *cvb = (uint64_t *)c->scratch[SC_CVB].p;
+            unsigned long long *d_counter = (unsigned long long *)(c->scratch[SC_MISC].p);
+            uint32_t *d_bounds = (uint32_t *)(c->scratch[SC_MISC].p + 16);
+            SO_CUDA(cudaMemsetAsync(d_counter, 0, 8, st));
+            k_pair_ungap<<<(uint32_t)((H + 127) / 128), 128, 0, st>>>(dk.Current(), dv.Current(), (uint32_t)H, g, c->d_qres,
+                                                                      c->d_qoff, c->d_tres, c->d_toff, cka, cva, d_counter);
+            SO_CUDA(cudaEventRecord(c->ev[3], st));
+            unsigned long long ncand = 0;
+            SO_CUDA(cudaMemcpyAsync(&ncand, d_counter, 8, cudaMemcpyDeviceToHost, st));
+            SO_CUDA(cudaStreamSynchronize(st));
+            SO_CUDA(cudaGetLastError());
+            c->stats.kernel_launches += 2;
+            c->stats.lib_launches += 1;
+            std::vector<uint32_t> bounds((size_t)nq + 1, 0);
+            std::vector<uint64_t> h_cv;
+            if (ncand > 0) {
+                cub::DoubleBuffer<uint64_t> ck(cka, ckb), cv(cva, cvb);
+                tmp = 0;
+                cub::DeviceRadixSort::SortPairs(nullptr, tmp, ck, cv, (int)ncand, 0, 32 + q_bits, st);
+                if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+                SO_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch[SC_TMP].p, tmp, ck, cv, (int)ncand, 0, 32 + q_bits, st));
+                k_query_bounds<<<(nq + 1 + 127) / 128, 128, 0, st>>>(ck.Current(), (uint32_t)ncand, nq, d_bounds);
+                SO_CUDA(cudaEventRecord(c->ev[4], st));
+                h_cv.resize((size_t)ncand);
+                SO_CUDA(cudaMemcpyAsync(h_cv.data(), cv.Current(), (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
+                SO_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds, ((size_t)nq + 1) * 4, cudaMemcpyDeviceToHost, st));
+                SO_CUDA(cudaStreamSynchronize(st));
+                SO_CUDA(cudaGetLastError());
+                c->stats.kernel_launches += 1;
+                c->stats.lib_launches += 1;
+                c->stats.d2h_bytes += (i64)ncand * 8 + ((i64)nq + 1) * 4;
+                float ms = 0;
+                cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
+                c->stats.ms_select += ms;
+            }
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+            c->stats.ms_seed += ms;
+            cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+            c->stats.ms_sort += ms;
+            cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+            c->stats.ms_ungap += ms;
+            const size_t base_c = out.cands.size();
+            out.cands.resize(base_c + (size_t)ncand);
+            for (size_t k = 0; k < (size_t)ncand; k++) {
+                const uint64_t v = h_cv[k];
+                const int diag = (int)(v & 0xfffffu) - g.diag_bias;
+                so_cand cd;
+                cd.target = (uint32_t)(v >> 40);
+                cd.score = (uint32_t)((v >> 20) & 0xfffffu);
+                // guess_start (fsearch.py:2544-2553): d = sst - qst = -diag
+                if (diag < 0)
+                    cd.qi = 0, cd.qj = (uint32_t)(-diag);
+                else
+                    cd.qi = (uint32_t)diag, cd.qj = 0;
+                out.cands[base_c + k] = cd;
+            }
+            for (int k = 0; k < nq; k++)
+                out.offsets[(size_t)(b0 - q_begin + k + 1)] = (uint64_t)base_c + bounds[(size_t)k + 1];
+        }
+        // offsets of queries without hits in this sub-block
+        for (int k = 0; k < nq; k++) {
+            size_t idx = (size_t)(b0 - q_begin + k + 1);
+            if (out.offsets[idx] < out.offsets[idx - 1]) out.offsets[idx] = out.offsets[idx - 1];
+        }
+        // adapt the sub-block size to the observed hit density
+        if (H > 0) {
+            double per_q = (double)H / (double)nq;
+            i64 want = (i64)((double)kHitCap * 0.5 / std::max(per_q, 1.0));
+            sub = std::min<i64>(std::max<i64>(want, 16), 2047);
+            if (c->sub_block > 0) sub = c->sub_block;
+        }
+        b0 = b1;
+    }
+    c->stats.candidates += (i64)out.cands.size();
+    return SO_OK;
+}
+
+}  // namespace so

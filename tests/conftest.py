@@ -88,6 +88,38 @@ class Oracle:
         n = self.L.orc_spseeds(a, len(a), step, nr.encode(), ssd.encode(), mod, b, p)
         return [[b[i], p[i]] for i in range(n)]
 
+    def candidates(self, qry, ref, c0, c1, q0, q1, flags, cap=4000000):
+        import numpy as np
+        f = {'-F': 'T', '-s': '111111', '-r': 'AST,CFILMVY,DN,EQ,G,H,KR,P,W', '-j': '1', '-M': '1000003', '-t': '-1'}
+        f.update(flags)
+        fn = self.L.orc_candidates
+        fn.restype = ctypes.c_longlong
+        fn.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_longlong] * 4 + [ctypes.c_char_p] * 3 + [
+            ctypes.c_longlong] * 3 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
+        off = np.zeros(q1 - q0 + 1, dtype=np.uint64)
+        out = np.zeros((cap, 4), dtype=np.uint32)
+        thr = ctypes.c_longlong()
+        n = fn(qry.encode(), ref.encode(), c0, c1, q0, q1, f['-F'].encode(), f['-s'].encode(), f['-r'].encode(),
+               int(f['-j']), int(f['-M']), int(f['-t']), off.ctypes.data, out.ctypes.data, cap, ctypes.byref(thr))
+        assert 0 <= n <= cap
+        return [out[int(off[i]):int(off[i + 1])] for i in range(q1 - q0)], thr.value
+
+    def index(self, ref, c0, c1, flags, cap=50000000):
+        import numpy as np
+        f = {'-s': '111111', '-r': 'AST,CFILMVY,DN,EQ,G,H,KR,P,W', '-j': '1', '-M': '1000003'}
+        f.update(flags)
+        fn = self.L.orc_index
+        fn.restype = ctypes.c_longlong
+        fn.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_char_p,
+                       ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong]
+        nc = int(f['-M'])
+        start = np.zeros(nc, dtype=np.uint32)
+        locus = np.zeros(cap, dtype=np.uint32)
+        n = fn(ref.encode(), c0, c1, f['-s'].encode(), f['-r'].encode(), int(f['-j']), nc, start.ctypes.data,
+               locus.ctypes.data, cap)
+        assert 0 <= n <= cap
+        return start, locus[:n]
+
     def blastp(self, qry, ref, out, flags):
         """flags: dict of fsearch-c flag letters (same as the golden cases)."""
         stats = (ctypes.c_longlong * 7)()
