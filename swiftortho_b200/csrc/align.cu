@@ -69,7 +69,14 @@ __device__ __forceinline__ void dp_row(int i, int len0, bool live, int c1base, c
         const int M = S[d] + sub;
         const int Dv = Dc[d + 1];
         int B = __vimax3_s32_relu(Ic, M, Dv);
-        int code = (B == M) ? 0 : ((B == Ic) ? 1 : ((B == Dv) ? 2 : 3));
+        // Trace priority M > I > D (fsearch.py:1404-1411) decided by ORDER comparisons of the three
+        // candidates.  Do NOT write `B == M` / `B == Dv`: ptxas 12.9 fuses an equality test against the
+        // result of max.s32.relu into the VIMNMX.RELU predicate output and gets it wrong on sm_100a
+        // (tools/test_vimax.cu reproduces it: 68 of 216 operand triples misclassified).
+        const bool pM = (M >= Ic) && (M >= Dv) && (M >= 0);
+        const bool pI = !pM && (Ic >= Dv) && (Ic >= 0);
+        const bool pD = !pM && !pI && (Dv >= 0);
+        int code = pM ? 0 : (pI ? 1 : (pD ? 2 : 3));
         int nI = B + (code == 1 ? -1 : -11);
         int nD = B + (code == 2 ? -1 : -11);
         if (EDGE) {
@@ -330,6 +337,14 @@ int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
     SO_CUDA(cudaMemcpyAsync(h_dp.data(), d_dp, (size_t)n * sizeof(DpOut), cudaMemcpyDeviceToHost, c->stream));
     SO_CUDA(cudaMemcpyAsync(h_tb.data(), d_tb, (size_t)n * sizeof(TbOut), cudaMemcpyDeviceToHost, c->stream));
     SO_CUDA(cudaStreamSynchronize(c->stream));
+    if (getenv("SO_DEBUG_TRACE") && n == 1) {
+        int rows = std::min(sorted[0].len1, sorted[0].len0 + 16);
+        std::vector<uint64_t> tr((size_t)rows * 32);
+        cudaMemcpy(tr.data(), c->trace.p, tr.size() * 8, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "DBG len0 %d len1 %d score %d imax %d jmax %d rows %d | tb i0 %d j0 %d al %d\n", sorted[0].len0,
+                sorted[0].len1, h_dp[0].score, h_dp[0].imax, h_dp[0].jmax, h_dp[0].rows, h_tb[0].i0, h_tb[0].j0, h_tb[0].al);
+        for (int i = 1; i <= rows && i <= 12; i++) fprintf(stderr, "DBG row %d %016llx\n", i, (unsigned long long)tr[(size_t)(i - 1) * 32]);
+    }
     float ms_dp = 0, ms_tb = 0;
     cudaEventElapsedTime(&ms_dp, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&ms_tb, c->ev[1], c->ev[2]);
