@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""Benchmark of the all-vs-all homology search hot path (BASELINE.json metric: proteins/s and gapped
+GCUPS) on 1..8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload = BASELINE config 2: synthetic 100 000 proteins (~350 aa, 20 taxa) all-vs-all,
+`-p blastp -e 1e-5 -s 111111 -r aa9 -M 120000000 -c 50000 -j 1`.
+A STEP is one pass of the whole hot path (seed lookup, diagonal grouping, chained X-drop scoring,
+candidate selection, banded gapped DP + traceback, e-value filter) for one block of `--block`
+queries per GPU against the complete 100 000-protein target index (2 chunks, resident in HBM).
+`value` = queries/s with the query block already in HBM; `e2e` = the same block pushed through the
+public host API from host buffers (so_set_queries H2D + so_search + 16-column text written to
+/dev/shm), every step.  Every step uses a different query block and touches GBs of seed-hit
+buffers, i.e. far more than the 126 MB L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+AA9 = 'AST,CFILMVY,DN,EQ,G,H,KR,P,W'
+FLAGS = dict(ssd='111111', nr=AA9, ht=120000000, step=1, expect=1e-5, v=500, max_miss=1e-3, thr=-1, flt='T', chk=50000)
+CACHE = os.environ.get('SWIFTORTHO_BENCH_CACHE', '/tmp/swiftortho_b200_bench')
+METRIC = 'all-vs-all proteins/sec (find_hit blastp, config 2: 100k synthetic proteins, seed 111111)'
+
+
+def dataset(n, taxa, rank=0, wait=True):
+    """config-2 FASTA (generated once per box, deterministic)."""
+    os.makedirs(CACHE, exist_ok=True)
+    path = os.path.join(CACHE, 'c2_%d_%d.fsa' % (n, taxa))
+    done = path + '.done'
+    if rank == 0 and not os.path.exists(done):
+        from swiftortho_b200 import synth
+        synth.write_config(path + '.tmp', 2, n=n, taxa=taxa)
+        os.replace(path + '.tmp', path)
+        open(done, 'w').close()
+    while wait and not os.path.exists(done):
+        time.sleep(0.2)
+    return path
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu):
+        self.rows, self.gpu, self.p = [], gpu, None
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q,
+                                       '--format=csv,noheader,nounits', '-lms', '200'],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if not self.p:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.p.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def _oracle_lib():
+    import ctypes as C
+    subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle')], stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(ROOT, 'oracle', '_build', 'liboracle.so'))
+    L.orc_session_open.restype = C.c_void_p
+    L.orc_session_open.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_longlong, C.c_double] + [C.c_longlong] * 3 + [
+        C.c_char_p] * 3 + [C.c_longlong] * 3
+    L.orc_session_search.restype = C.c_double
+    L.orc_session_search.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_char_p, C.POINTER(C.c_longlong)]
+    L.orc_session_build_seconds.restype = C.c_double
+    L.orc_session_build_seconds.argtypes = [C.c_void_p]
+    return L
+
+
+_SESSION = None
+
+
+def _cpu_worker(job):
+    import ctypes as C
+    L, h = _SESSION
+    q0, q1 = job
+    st = (C.c_longlong * 7)()
+    t = L.orc_session_search(h, q0, q1, b'', st)
+    return t, list(st)
+
+
+def cpu_arm(fasta, n_total, steps, warmup, per_worker, first_query=0):
+    """The oracle port (oracle/fsearch_oracle.cpp = CPU restatement of lib/fsearch.py) on all host
+    cores: the index is built once, then forked workers each search their own query window like the
+    reference's `find_hit.py -a <cores>` slices.  Returns per-step wall times and counters."""
+    global _SESSION
+    import multiprocessing as mp
+    L = _oracle_lib()
+    f = FLAGS
+    h = L.orc_session_open(fasta.encode(), fasta.encode(), f['expect'], f['v'], f['max_miss'], -1, -1, f['thr'],
+                           f['flt'].encode(), f['ssd'].encode(), f['nr'].encode(), f['step'], f['ht'], f['chk'])
+    assert h, 'oracle session failed'
+    build_s = L.orc_session_build_seconds(h)
+    _SESSION = (L, h)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    workers = max(1, min(cores, 64))
+    times, counters = [], [0] * 7
+    with mp.get_context('fork').Pool(workers) as pool:
+        q = first_query
+        for s in range(warmup + steps):
+            jobs = []
+            for w in range(workers):
+                a = q % max(1, n_total - per_worker)
+                jobs.append((a, a + per_worker))
+                q += per_worker
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                times.append(dt)
+                for _, st in res:
+                    counters = [a + b for a, b in zip(counters, st)]
+    return dict(times=times, workers=workers, per_step=workers * per_worker, build_s=build_s, counters=counters)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n, taxa = args.n, args.taxa
+    fasta = dataset(n, taxa)
+    r = cpu_arm(fasta, n, args.steps, args.warmup, args.cpu_queries)
+    tot = sum(r['times'])
+    value = r['per_step'] * len(r['times']) / tot
+    sample = '%d workers x %d queries per step against all %d targets (index built once: %.1f s, not timed)' % (
+        r['workers'], args.cpu_queries, n, r['build_s'])
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'proteins/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / len(r['times']),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic',
+            'config': workload_config(args, r['per_step']),
+            'cpu_baseline': {'value': value, 'unit': 'proteins/s', 'cores': r['workers'], 'kind': 'port',
+                             'sample': sample},
+            'e2e': {'value': value, 'unit': 'proteins/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gcups_cpu': r['counters'][5] / tot / 1e9}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, block):
+    return {'workload': 'BASELINE config 2: synthetic %d proteins (%d taxa, ~350 aa) all-vs-all, blastp -e 1e-5 '
+                        '-s 111111 -r aa9 -M 120000000 -c 50000 -j 1' % (args.n, args.taxa),
+            'step': 'one block of %d queries per GPU against the full target index (2 chunks resident in HBM)' % block,
+            'l2': 'every step uses a new query block; seed-hit buffers are GBs per step (>> 126 MB L2)'}
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local):
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    n, taxa, B = args.n, args.taxa, args.block
+    fasta = dataset(n, taxa, rank)
+    from swiftortho_b200 import search as so
+    F = so.Fasta(fasta)
+    S = so.Searcher(device=local, **FLAGS)
+    t0 = time.perf_counter()
+    S.set_targets(F)
+    info = S.build_index()
+    index_ms = 1e3 * (time.perf_counter() - t0)
+    S.set_queries(F)
+    nblocks = max(1, n // B)
+
+    def block_of(step):
+        b = (step * world + rank) % nblocks
+        return b * B, min(n, (b + 1) * B)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident arm (value)
+    for s in range(args.warmup):
+        S.search(*block_of(s))
+    S.stats(reset=True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    nq = 0
+    for s in range(args.steps):
+        a, b = block_of(args.warmup + s)
+        S.search(a, b)           # returns after the stream is synchronised
+        nq += b - a
+    barrier()
+    dt = time.perf_counter() - t0
+    st = S.stats(reset=True)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end-to-end arm: host buffers -> public API -> text rows, every step
+    import ctypes as C
+    import numpy as np
+    lib = S.lib
+    res_ptr = F._res.value
+    shm = '/dev/shm' if os.path.isdir('/dev/shm') else CACHE
+    outp = os.path.join(shm, 'swiftortho_b200_bench_%d.sc' % rank)
+
+    class Sub:  # a FASTA view restricted to one query block (headers come from the full container)
+        pass
+    e2e_q = 0
+    for s in range(args.warmup + args.steps):
+        a, b = block_of(1000 + s)
+        if s == args.warmup:
+            S.stats(reset=True)
+            barrier()
+            t1 = time.perf_counter()
+        off = np.ascontiguousarray(F.offsets[a:b + 1])
+        so.check(lib.so_set_queries(S.h, C.c_void_p(res_ptr), off.ctypes.data, b - a))
+        rows = S.search(0, b - a)
+        arr = rows.as_array()      # result records are host memory already (D2H happened inside so_search)
+        arr['query'] += a
+        hits = (so.so_hit * max(1, len(arr))).from_buffer_copy(arr.tobytes() if len(arr) else bytes(C.sizeof(so.so_hit)))
+        so.check(lib.so_write_rows(hits, len(arr), F.h, F.h, outp.encode(), 0))
+        if s >= args.warmup:
+            e2e_q += b - a
+    barrier()
+    dt2 = time.perf_counter() - t1
+    st2 = S.stats()
+    try:
+        os.remove(outp)
+    except OSError:
+        pass
+
+    # ---- reduce over ranks (max time, summed work)
+    vals = [dt, dt2, float(nq), float(e2e_q), float(st['dp_cells']), st['ms_dp'], st['ms_ungap'], st['ms_sort'],
+            st['ms_seed'], st['ms_select'], st['ms_traceback'], st['ms_host'], float(st['seed_hits']),
+            float(st['kernel_launches']), float(st['ungap_steps']), float(st['alignments']),
+            float(st2['h2d_bytes']), float(st2['d2h_bytes'])]
+    if dist is not None:
+        import torch
+        t = torch.tensor(vals, dtype=torch.float64, device='cuda')
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        vals = [mx[0].item(), mx[1].item()] + [sm[i].item() for i in range(2, 5)] + [mx[i].item() for i in range(5, 12)] + \
+               [sm[i].item() for i in range(12, 16)] + [mx[16].item(), mx[17].item()]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    (dt, dt2, nq, e2e_q, cells, ms_dp, ms_ungap, ms_sort, ms_seed, ms_select, ms_tb, ms_host, seed_hits, launches,
+     ungap_steps, alignments, h2d, d2h) = vals
+    value = nq / dt
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(
+        os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
+    int_peak = json.load(open(os.path.join(ROOT, 'profiles', 'int_peak.json')))
+    # dominant kernel of the step = chained X-drop scoring (k_pair_ungap): integer-pipe bound
+    # (6 INT ops per extension step); peak = measured INT32 op rate of this chip
+    ops = 6.0 * ungap_steps / max(world, 1)
+    ach = ops / (ms_ungap * 1e-3) / 1e9 if ms_ungap > 0 else 0.0
+    roof = {'kernel': 'k_pair_ungap', 'bound': 'int32', 'achieved': ach, 'peak': int_peak['gops_measured'],
+            'unit': 'Gop/s', 'frac': ach / int_peak['gops_measured'], 'traffic': None,
+            'peak_source': 'tools/int_peak.cu measured on this pool (profiles/int_peak.json)',
+            'share_of_step_device_time': ms_ungap / max(1e-9, ms_ungap + ms_sort + ms_seed + ms_select + ms_dp + ms_tb)}
+    # HBM view of the library radix sort (second largest): 8 passes x (12 B read + 12 B write) per hit
+    sort_bytes = seed_hits / max(world, 1) * 24.0 * 7
+    hbm = {'kernel': 'cub radix sort (library)', 'bound': 'hbm', 'achieved': sort_bytes / (ms_sort * 1e-3) / 1e9 if ms_sort else 0,
+           'peak': peaks.get('hbm_gbs', 6650.0), 'unit': 'GB/s',
+           'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback B200_PROFILING.md'}
+    hbm['frac'] = hbm['achieved'] / hbm['peak']
+    gcups = cells / max(world, 1) / (ms_dp * 1e-3) / 1e9 if ms_dp > 0 else 0.0
+    dp_roof = {'kernel': 'k_banded_dp', 'bound': 'int32', 'achieved': gcups, 'unit': 'GCUPS',
+               'peak': int_peak['gops_measured'] / 14.0, 'frac': gcups / (int_peak['gops_measured'] / 14.0),
+               'cells_per_step': cells / args.steps / max(world, 1), 'note': '14 INT ops per cell (SURVEY.md 8d)'}
+    line = {'metric': METRIC, 'value': value, 'unit': 'proteins/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic', 'config': workload_config(args, B),
+            'roofline': roof, 'roofline_sort': hbm, 'roofline_dp': dp_roof, 'gapped_gcups': gcups,
+            'e2e': {'value': e2e_q / dt2, 'unit': 'proteins/s', 'h2d_bytes_per_step': h2d / args.steps,
+                    'd2h_bytes_per_step': d2h / args.steps},
+            'gpu_launches': int(launches), 'clocks': clk,
+            'stage_ms_per_step': {k: v / args.steps for k, v in dict(seed=ms_seed, sort_lib=ms_sort, ungap=ms_ungap,
+                                                                      select=ms_select, dp=ms_dp, traceback=ms_tb,
+                                                                      host=ms_host).items()},
+            'index_build_ms': index_ms, 'index': info, 'alignments_per_query': alignments / max(1.0, nq),
+            'seed_hits_per_query': seed_hits / max(1.0, nq)}
+    if world == 1 and not args.no_cpu:
+        # CPU baseline (the oracle port) in a child process that never touches CUDA
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2',
+                              '--warmup', '1', '--n', str(n), '--taxa', str(taxa), '--cpu-queries', str(args.cpu_queries)],
+                             stdout=subprocess.PIPE, text=True, cwd=ROOT)
+        try:
+            ref = json.loads(out.stdout.strip().splitlines()[-1])
+            line['cpu_baseline'] = ref['cpu_baseline']
+            line['cpu_baseline']['gcups'] = ref.get('gcups_cpu')
+        except Exception as e:  # noqa: BLE001
+            line['cpu_baseline'] = {'error': repr(e)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--block', type=int, default=2048, help='queries per step per GPU')
+    ap.add_argument('--n', type=int, default=100000)
+    ap.add_argument('--taxa', type=int, default=20)
+    ap.add_argument('--cpu-queries', type=int, default=4, help='queries per CPU worker per step (bounded sample)')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local)
+
+
+if __name__ == '__main__':
+    main()

@@ -176,6 +176,7 @@ int so_write_rows(const so_hit *rows, int64_t n, const so_fasta *queries, const 
 /* counters of the last so_search / so_align_batch call (for bench.py) */
 typedef struct so_stats {
     int64_t queries, seed_hits, groups, candidates, alignments, dp_cells, rows;
+    int64_t ungap_steps;     /* residue pairs scored by the X-drop extensions (K6)   */
     int64_t kernel_launches; /* launches of this library's own kernels */
     int64_t lib_launches;    /* CUB (library) launches                 */
     double ms_seed, ms_sort, ms_ungap, ms_select, ms_align, ms_dp, ms_traceback, ms_host, ms_total;

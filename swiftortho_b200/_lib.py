@@ -50,7 +50,7 @@ class so_hit(C.Structure):
 
 class so_stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ('queries', 'seed_hits', 'groups', 'candidates', 'alignments', 'dp_cells',
-                                         'rows', 'kernel_launches', 'lib_launches')] + \
+                                         'rows', 'ungap_steps', 'kernel_launches', 'lib_launches')] + \
                [(n, C.c_double) for n in ('ms_seed', 'ms_sort', 'ms_ungap', 'ms_select', 'ms_align', 'ms_dp',
                                           'ms_traceback', 'ms_host', 'ms_total')] + \
                [('h2d_bytes', C.c_int64), ('d2h_bytes', C.c_int64)]

@@ -404,16 +404,17 @@ struct ChainState {
     int total, x, qlo, slo;
 };
 
-__device__ __forceinline__ void chain_seed(ChainState &ch, int Q, int diag, const uint8_t *__restrict__ q, int ql,
+__device__ __forceinline__ int chain_seed(ChainState &ch, int Q, int diag, const uint8_t *__restrict__ q, int ql,
                                            const uint8_t *__restrict__ t, int tl, const int8_t *s_tbl,
                                            const uint8_t *s_code) {
     // ungap(qseq, sseq, Qst, Sst, qlo, slo) with dropX = 30 (fsearch.py:2454-2494); s = q - diag
     int S = Q - diag;
     const int off = max(max(ch.qlo - Q, ch.slo - S), 0);
     Q += off;
-    int qq = Q, score = 0, mx = 0, mx_qed = Q;
+    int qq = Q, score = 0, mx = 0, mx_qed = Q, steps = 0;
     while (qq > ch.qlo && qq < ql && (qq - diag) > ch.slo && (qq - diag) < tl) {
         score += s_tbl[(int)s_code[q[qq]] * kClasses + s_code[t[qq - diag]]];
+        steps++;
         if (score > mx) {
             mx = score;
             mx_qed = qq;
@@ -425,6 +426,7 @@ __device__ __forceinline__ void chain_seed(ChainState &ch, int Q, int diag, cons
     score = mx;
     while (qq < ql && qq > ch.qlo && (qq - diag) < tl && (qq - diag) > ch.slo) {
         score += s_tbl[(int)s_code[q[qq]] * kClasses + s_code[t[qq - diag]]];
+        steps++;
         if (score > mx)
             mx = score;
         else if (score + 30 < mx)
@@ -434,6 +436,7 @@ __device__ __forceinline__ void chain_seed(ChainState &ch, int Q, int diag, cons
     ch.total += mx;
     ch.qlo = mx_qed;            // next seed: qlo = max_qed, slo = max_sed (fsearch.py:2502-2506)
     ch.slo = mx_qed - diag;
+    return steps;
 }
 
 __global__ void __launch_bounds__(128) k_pair_ungap(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
@@ -441,6 +444,7 @@ __global__ void __launch_bounds__(128) k_pair_ungap(const uint64_t *__restrict__
                                                     const uint64_t *__restrict__ qoff, const uint8_t *__restrict__ tres,
                                                     const uint64_t *__restrict__ toff, uint64_t *__restrict__ ckeys,
                                                     uint64_t *__restrict__ cvals, unsigned long long *__restrict__ counter) {
+    unsigned long long my_steps = 0;
     __shared__ int8_t s_tbl[kClasses * kClasses];
     __shared__ uint8_t s_code[256];
     for (int k = threadIdx.x; k < kClasses * kClasses; k += blockDim.x) s_tbl[k] = c_score2[k];
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(128) k_pair_ungap(const uint64_t *__restrict__
                 const int qst = (int)(ke & qmask);
                 rank_min = min(rank_min, vals[e]);
                 if (qst != prev_q) {
-                    chain_seed(ch, qst, diag, q, ql, t, tl, s_tbl, s_code);
+                    my_steps += (unsigned long long)chain_seed(ch, qst, diag, q, ql, t, tl, s_tbl, s_code);
                     prev_q = qst;
                 }
                 e++;
@@ -500,6 +504,9 @@ __global__ void __launch_bounds__(128) k_pair_ungap(const uint64_t *__restrict__
             }
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+    if ((threadIdx.x & 31) == 0 && my_steps) atomicAdd(counter + 1, my_steps);
     // warp-aggregated append of the candidates
     const bool emit = head && best_score >= 25;
     const unsigned m = __ballot_sync(0xffffffffu, emit);
@@ -677,14 +684,16 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Bl
             uint64_t *cka = (uint64_t *)c->scratch[SC_CKA].p, *ckb = (uint64_t *)c->scratch[SC_CKB].p;
             uint64_t *cva = (uint64_t *)c->scratch[SC_CVA].p, *cvb = (uint64_t *)c->scratch[SC_CVB].p;
             unsigned long long *d_counter = (unsigned long long *)(c->scratch[SC_MISC].p);
-            uint32_t *d_bounds = (uint32_t *)(c->scratch[SC_MISC].p + 16);
-            SO_CUDA(cudaMemsetAsync(d_counter, 0, 8, st));
+            uint32_t *d_bounds = (uint32_t *)(c->scratch[SC_MISC].p + 32);
+            SO_CUDA(cudaMemsetAsync(d_counter, 0, 16, st));
             k_pair_ungap<<<(uint32_t)((H + 127) / 128), 128, 0, st>>>(dk.Current(), dv.Current(), (uint32_t)H, g, c->d_qres,
                                                                       c->d_qoff, c->d_tres, c->d_toff, cka, cva, d_counter);
             SO_CUDA(cudaEventRecord(c->ev[3], st));
-            unsigned long long ncand = 0;
-            SO_CUDA(cudaMemcpyAsync(&ncand, d_counter, 8, cudaMemcpyDeviceToHost, st));
+            unsigned long long h_counter[2] = {0, 0};
+            SO_CUDA(cudaMemcpyAsync(h_counter, d_counter, 16, cudaMemcpyDeviceToHost, st));
             SO_CUDA(cudaStreamSynchronize(st));
+            const unsigned long long ncand = h_counter[0];
+            c->stats.ungap_steps += (i64)h_counter[1];
             SO_CUDA(cudaGetLastError());
             c->stats.kernel_launches += 2;
             c->stats.lib_launches += 1;
