@@ -233,6 +233,23 @@ __global__ void __launch_bounds__(128) k_traceback(const AlnTask *__restrict__ t
     out[t] = o;
 }
 
+// cells the reference fills for (len0, len1): rows i = 1..l1-1, columns [max(1,i-16), min(i+16,l0))
+static inline i64 band_cells(i64 len0, i64 len1) {
+    const i64 l0 = len0 + 1, rows = std::min<i64>(len1, len0 + 16);
+    i64 cl = 0;
+    // closed form per row: hi(i) - lo(i), hi = min(i+16, l0), lo = max(1, i-16)
+    // rows 1..16: lo = 1; rows >= 17: lo = i-16.   rows <= l0-16: hi = i+16; beyond: hi = l0.
+    for (i64 i = 1; i <= std::min<i64>(rows, 16); i++) cl += std::min<i64>(i + 16, l0) - 1;
+    if (rows > 16) {
+        const i64 a = 17, b = rows;                    // lo = i - 16
+        const i64 m = std::min<i64>(b, l0 - 16);       // rows a..m: hi = i + 16 -> 32 cells
+        if (m >= a) cl += 32 * (m - a + 1);
+        const i64 a2 = std::max<i64>(a, m + 1);        // rows a2..b: hi = l0 -> l0 - i + 16 cells
+        if (b >= a2) cl += (l0 + 16) * (b - a2 + 1) - (a2 + b) * (b - a2 + 1) / 2;
+    }
+    return cl;
+}
+
 // -----------------------------------------------------------------------------------------------
 // Host driver: resolves pairs to device tasks, sorts by length, launches, converts coordinates.
 // -----------------------------------------------------------------------------------------------
@@ -302,15 +319,6 @@ int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
         wbase[(size_t)w + 1] = wbase[(size_t)w] + (uint64_t)rows * 32;
     }
     (void)nwarps;
-    for (i64 k = 0; k < n; k++) {
-        const Prep &r = prep[(size_t)k];
-        // cells the reference fills: rows 1..l1-1, columns [max(1,i-16), min(i+16,l0))
-        i64 l0 = r.len0 + 1, l1 = r.len1 + 1;
-        for (i64 i = 1; i < l1 && i <= l0 + 15; i++) {
-            i64 a = std::max<i64>(1, i - 16), b = std::min<i64>(i + 16, l0);
-            if (b > a) cells += b - a;
-        }
-    }
     size_t need_trace = (size_t)wbase[(size_t)nwarps_pad] + 64;
     int rc;
     if ((rc = c->trace.reserve(need_trace)) != SO_OK) return rc;
@@ -353,7 +361,6 @@ int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
     c->stats.ms_traceback += ms_tb;
     c->stats.kernel_launches += 2;
     c->stats.alignments += n;
-    c->stats.dp_cells += cells;
     c->stats.h2d_bytes += (i64)(b_tasks + b_wb);
     c->stats.d2h_bytes += (i64)((size_t)n * (sizeof(DpOut) + sizeof(TbOut)));
     for (i64 s = 0; s < n; s++) {
@@ -377,13 +384,11 @@ int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
         } else {
             o.qst = b.j0 + r.qst, o.qed = d.jmax + r.qst, o.sst = b.i0 + r.sst, o.sed = d.imax + r.sst;
         }
-        i64 l0 = r.len0 + 1, l1 = r.len1 + 1, cl = 0;
-        for (i64 i = 1; i < l1 && i <= l0 + 15; i++) {
-            i64 a = std::max<i64>(1, i - 16), e = std::min<i64>(i + 16, l0);
-            if (e > a) cl += e - a;
-        }
+        const i64 cl = band_cells(r.len0, r.len1);
         o.cells = (int32_t)cl;
+        cells += cl;
     }
+    c->stats.dp_cells += cells;
     c->stats.ms_host += tm.ms() - (ms_dp + ms_tb);
     return SO_OK;
 }

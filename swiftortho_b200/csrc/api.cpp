@@ -67,13 +67,14 @@ static int check_offsets(const uint64_t *off, i64 n, uint32_t &maxlen, const cha
 // H3 + F: one query's candidate list -> alignment requests -> rows
 // ---------------------------------------------------------------------------------------------
 struct QueryState {
-    std::vector<uint64_t> order;  // candidates in the reference's sorted order (prefix of length `limit`)
-    std::vector<so_cand> cands;   // concatenated over chunks, reference order
+    std::vector<uint64_t> order;  // candidates in the reference's sorted order (prefix of length `limit`);
+                                  // low 32 bits = index into the chunk-major concatenation of the candidates
     i64 limit = 0;                // min(vmax, len(hits))
     i64 next = 0;                 // next candidate (in sorted order) to align
     double mmiss = 0;
     i64 unmch = 0, bv = 0;
     bool done = false;
+    std::vector<so_cand> sel;     // the first `limit` candidates in sorted order
     std::vector<so_hit> rows;
     // requests of the current round
     i64 req_first = 0, req_count = 0;  // candidates covered
@@ -170,7 +171,10 @@ void so_ctx_destroy(so_ctx *c) {
     if (c->d_toff) cudaFree(c->d_toff);
     if (c->d_qoff) cudaFree(c->d_qoff);
     if (c->d_perm) cudaFree(c->d_perm);
+    if (c->d_tcls) cudaFree(c->d_tcls);
+    if (c->d_qcls) cudaFree(c->d_qcls);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (auto &pc : c->cand_pool) pc.release();
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -193,7 +197,8 @@ int so_set_targets(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, 
     c->chunks.clear();
     if (c->d_tres) cudaFree(c->d_tres);
     if (c->d_toff) cudaFree(c->d_toff);
-    c->d_tres = nullptr, c->d_toff = nullptr;
+    if (c->d_tcls) cudaFree(c->d_tcls);
+    c->d_tres = nullptr, c->d_toff = nullptr, c->d_tcls = nullptr;
     c->n_t = n;
     c->t_off.assign(offsets, offsets + n + 1);
     const uint64_t base = offsets[0];
@@ -203,6 +208,8 @@ int so_set_targets(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, 
     SO_CUDA(cudaMalloc((void **)&c->d_toff, ((size_t)n + 1) * 8));
     SO_CUDA(cudaMemcpyAsync(c->d_tres, residues + base, bytes, cudaMemcpyHostToDevice, c->stream));
     SO_CUDA(cudaMemcpyAsync(c->d_toff, c->t_off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA(cudaMalloc((void **)&c->d_tcls, bytes + 64));
+    if ((rc = so::classify_residues(c, c->d_tres, c->d_tcls, bytes)) != SO_OK) return rc;
     SO_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.h2d_bytes += (i64)bytes + ((i64)n + 1) * 8;
     return SO_OK;
@@ -220,7 +227,8 @@ int so_set_queries(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, 
     if (c->d_qres) cudaFree(c->d_qres);
     if (c->d_qoff) cudaFree(c->d_qoff);
     if (c->d_perm) cudaFree(c->d_perm);
-    c->d_qres = nullptr, c->d_qoff = nullptr, c->d_perm = nullptr;
+    if (c->d_qcls) cudaFree(c->d_qcls);
+    c->d_qres = nullptr, c->d_qoff = nullptr, c->d_perm = nullptr, c->d_qcls = nullptr;
     c->n_q = n;
     c->q_off.assign(offsets, offsets + n + 1);
     const uint64_t base = offsets[0];
@@ -263,6 +271,8 @@ int so_set_queries(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, 
     SO_CUDA(cudaMemcpyAsync(c->d_qres, dst, bytes, cudaMemcpyHostToDevice, c->stream));
     SO_CUDA(cudaMemcpyAsync(c->d_qoff, qo, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     SO_CUDA(cudaMemcpyAsync(c->d_perm, perm.data(), bytes * 4, cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA(cudaMalloc((void **)&c->d_qcls, bytes + 64));
+    if ((rc = so::classify_residues(c, c->d_qres, c->d_qcls, bytes)) != SO_OK) return rc;
     SO_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.h2d_bytes += (i64)bytes * 5 + ((i64)n + 1) * 8;
     c->stats.ms_host += tm.ms();
@@ -327,17 +337,22 @@ int so_candidates(so_ctx *c, int64_t chunk, int64_t q_begin, int64_t q_end, uint
         return SO_EINVAL;
     }
     SO_CUDA(cudaSetDevice(c->device));
-    so::BlockCands bc;
+    so::PackedCands bc;
     int rc = so::chunk_candidates(c, c->chunks[(size_t)chunk], q_begin, q_end, bc);
-    if (rc != SO_OK) return rc;
+    if (rc != SO_OK) {
+        bc.release();
+        return rc;
+    }
     *cand_offsets = (uint64_t *)malloc(bc.offsets.size() * 8);
-    *cands = (so_cand *)malloc(std::max<size_t>(1, bc.cands.size()) * sizeof(so_cand));
+    *cands = (so_cand *)malloc(std::max<size_t>(1, bc.n) * sizeof(so_cand));
     if (!*cand_offsets || !*cands) {
+        bc.release();
         set_error("out of host memory");
         return SO_ENOMEM;
     }
     memcpy(*cand_offsets, bc.offsets.data(), bc.offsets.size() * 8);
-    if (!bc.cands.empty()) memcpy(*cands, bc.cands.data(), bc.cands.size() * sizeof(so_cand));
+    for (size_t k = 0; k < bc.n; k++) (*cands)[k] = so::unpack_cand(bc.vals[k]);
+    bc.release();
     return SO_OK;
 }
 
@@ -390,27 +405,40 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
         const i64 b1 = std::min<i64>(q_end, b0 + QB);
         const i64 nq = b1 - b0;
         std::vector<QueryState> qs((size_t)nq);
-        // PASS 1 (fsearch.py:2990-3016): candidates of every chunk, concatenated in chunk order
-        for (size_t ch = 0; ch < c->chunks.size(); ch++) {
-            so::BlockCands bc;
-            int rc = so::chunk_candidates(c, c->chunks[ch], b0, b1, bc);
+        // PASS 1 (fsearch.py:2990-3016): candidates of every chunk (packed, pinned, reference order)
+        Timer tc;
+        const size_t nch = c->chunks.size();
+        if (c->cand_pool.size() < nch) c->cand_pool.resize(nch);
+        for (size_t ch = 0; ch < nch; ch++) {
+            int rc = so::chunk_candidates(c, c->chunks[ch], b0, b1, c->cand_pool[ch]);
             if (rc != SO_OK) return rc;
-            Timer th;
-            so::parallel_for(nq, [&](i64 k) {
-                auto &dst = qs[(size_t)k].cands;
-                dst.insert(dst.end(), bc.cands.begin() + (i64)bc.offsets[(size_t)k],
-                           bc.cands.begin() + (i64)bc.offsets[(size_t)k + 1]);
-            });
-            c->stats.ms_host += th.ms();
         }
+        c->prof.cand_ms += tc.ms();
+        // candidate `idx` of query k in the chunk-major concatenation (fsearch.py:3043-3049)
+        auto cand_at = [&](i64 k, uint32_t idx) -> uint64_t {
+            for (size_t ch = 0; ch < nch; ch++) {
+                const so::PackedCands &pc = c->cand_pool[ch];
+                const uint64_t lo = pc.offsets[(size_t)k], hi = pc.offsets[(size_t)k + 1];
+                if (idx < hi - lo) return pc.vals[lo + idx];
+                idx -= (uint32_t)(hi - lo);
+            }
+            return 0;
+        };
         // PASS 2 (fsearch.py:3051-3059): qsort by -score, mmiss, vmax
         Timer th;
         so::parallel_for(nq, [&](i64 k) {
             QueryState &s = qs[(size_t)k];
-            const i64 n = (i64)s.cands.size();
+            i64 n = 0;
+            for (size_t ch = 0; ch < nch; ch++) n += (i64)(c->cand_pool[ch].offsets[(size_t)k + 1] - c->cand_pool[ch].offsets[(size_t)k]);
             s.order.resize((size_t)n);
-            for (i64 i = 0; i < n; i++)
-                s.order[(size_t)i] = ((uint64_t)(0xffffffffu - s.cands[(size_t)i].score) << 32) | (uint32_t)i;
+            i64 w = 0;
+            for (size_t ch = 0; ch < nch; ch++) {
+                const so::PackedCands &pc = c->cand_pool[ch];
+                for (uint64_t p = pc.offsets[(size_t)k]; p < pc.offsets[(size_t)k + 1]; p++, w++) {
+                    const uint32_t score = (uint32_t)((pc.vals[p] >> 20) & 0xfffffu);
+                    s.order[(size_t)w] = ((uint64_t)(0xffffffffu - score) << 32) | (uint32_t)w;
+                }
+            }
             s.limit = std::min<i64>(vmax, n);
             so::qsort_prefix(s.order, s.limit);
             double mm = (double)n * max_miss + 1;
@@ -418,10 +446,16 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             mm = std::min(std::max(mm, 10.), 120.);
             s.mmiss = mm;
             s.done = s.limit == 0;
+            // only the prefix is ever consumed: resolve it to candidates and drop the rest
+            s.sel.resize((size_t)s.limit);
+            for (i64 i = 0; i < s.limit; i++) s.sel[(size_t)i] = so::unpack_cand(cand_at(k, (uint32_t)s.order[(size_t)i]));
+            std::vector<uint64_t>().swap(s.order);
         });
         c->stats.ms_host += th.ms();
+        c->prof.order_ms += th.ms();
         // alignment rounds: the stop rule (fsearch.py:3103) is sequential per query, so each round
         // aligns the next kRound candidates of every unfinished query and the host replays the rule
+        Timer trd;
         std::vector<so_pair> pairs;
         std::vector<so_aln> alns;
         struct Req {
@@ -441,8 +475,8 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
                 const i64 hi = std::min<i64>(s.limit, s.next + kRound);
                 for (i64 h = s.next; h < hi; h++) {
-                    const int ci = (int)(uint32_t)s.order[(size_t)h];
-                    const so_cand &cd = s.cands[(size_t)ci];
+                    const int ci = (int)h;
+                    const so_cand &cd = s.sel[(size_t)ci];
                     const i64 lj = (i64)(c->t_off[(size_t)cd.target + 1] - c->t_off[(size_t)cd.target]);
                     Req r;
                     r.q = (int)k, r.first = (int)pairs.size(), r.cand = ci, r.count = 0;
@@ -471,8 +505,10 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             }
             if (reqs.empty()) break;
             alns.resize(pairs.size());
+            Timer ta;
             int rc = so::align_pairs(c, pairs.data(), (i64)pairs.size(), alns.data());
             if (rc != SO_OK) return rc;
+            c->prof.align_ms += ta.ms();
             Timer tr;
             // replay (fsearch.py:3062-3106)
             size_t r = 0;
@@ -484,7 +520,7 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 for (; r < reqs.size() && reqs[r].q == k; r++) {
                     if (s.done) continue;
                     const Req &rq = reqs[r];
-                    const so_cand &cd = s.cands[(size_t)rq.cand];
+                    const so_cand &cd = s.sel[(size_t)rq.cand];
                     const i64 lj = (i64)(c->t_off[(size_t)cd.target + 1] - c->t_off[(size_t)cd.target]);
                     const bool longpath = !(li < 4096 && lj < 4096);
                     bool any = false;
@@ -519,7 +555,9 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 if (s.next >= s.limit) s.done = true;
             }
             c->stats.ms_host += tr.ms();
+            c->prof.replay_ms += tr.ms();
         }
+        c->prof.rounds_ms += trd.ms();
         // final per-query order: qsort_u by -bit, first v rows (fsearch.py:3108-3110)
         Timer tf;
         so::parallel_for(nq, [&](i64 k) {
@@ -541,6 +579,7 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             c->stats.queries++;
         }
         c->stats.ms_host += tf.ms();
+        c->prof.final_ms += tf.ms();
     }
     c->stats.rows += (i64)all_rows.size();
     *n_rows = (int64_t)all_rows.size();
@@ -551,6 +590,12 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     }
     if (!all_rows.empty()) memcpy(*rows_out, all_rows.data(), all_rows.size() * sizeof(so_hit));
     c->stats.ms_total += total.ms();
+    c->prof.total_ms += total.ms();
+    if (getenv("SO_PROFILE")) {
+        const so::HostProfile &p = c->prof;
+        fprintf(stderr, "so_search profile (cumulative ms): total %.1f | candidates %.1f (d2h %.1f) | order %.1f | rounds %.1f (align %.1f replay %.1f) | final %.1f\n",
+                p.total_ms, p.cand_ms, p.d2h_ms, p.order_ms, p.rounds_ms, p.align_ms, p.replay_ms, p.final_ms);
+    }
     return SO_OK;
 }
 

@@ -59,6 +59,50 @@ struct ChunkIndex {
     double build_ms = 0;
 };
 
+// Candidates of a query block against one chunk, in the reference's order, as packed 64-bit values
+// (target ordinal << 40 | score << 20 | diagonal + kCandDiagBias) in a reusable PINNED host buffer.
+static const int kCandDiagBias = 1 << 19;
+struct PackedCands {
+    uint64_t *vals = nullptr;
+    size_t n = 0, cap = 0;
+    std::vector<uint64_t> offsets;  // [nq + 1]
+    int reserve(size_t want) {
+        if (want <= cap) return SO_OK;
+        size_t ncap = want + want / 2 + 4096;
+        uint64_t *nv = nullptr;
+        if (cudaMallocHost((void **)&nv, ncap * 8) != cudaSuccess) {
+            set_error("cudaMallocHost of %zu bytes failed", ncap * 8);
+            return SO_ENOMEM;
+        }
+        if (n) memcpy(nv, vals, n * 8);
+        if (vals) cudaFreeHost(vals);
+        vals = nv;
+        cap = ncap;
+        return SO_OK;
+    }
+    void release() {
+        if (vals) cudaFreeHost(vals);
+        vals = nullptr;
+        n = cap = 0;
+    }
+};
+static inline so_cand unpack_cand(uint64_t v) {
+    so_cand cd;
+    const int diag = (int)(v & 0xfffffu) - kCandDiagBias;
+    cd.target = (uint32_t)(v >> 40);
+    cd.score = (uint32_t)((v >> 20) & 0xfffffu);
+    // guess_start (fsearch.py:2544-2553): d = sst - qst = -diag -> head of the diagonal
+    if (diag < 0)
+        cd.qi = 0, cd.qj = (uint32_t)(-diag);
+    else
+        cd.qi = (uint32_t)diag, cd.qj = 0;
+    return cd;
+}
+
+struct HostProfile {  // wall-clock breakdown of the host side (SO_PROFILE=1 prints it)
+    double cand_ms = 0, d2h_ms = 0, order_ms = 0, rounds_ms = 0, align_ms = 0, replay_ms = 0, final_ms = 0, total_ms = 0;
+};
+
 struct Timer {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     double ms() const {
@@ -80,6 +124,7 @@ struct so_ctx {
     std::vector<uint8_t> q_masked;            // host copy of the masked queries
     const uint8_t *t_host = nullptr;          // caller-owned (valid during so_set_targets only)
     uint8_t *d_tres = nullptr, *d_qres = nullptr;
+    uint8_t *d_tcls = nullptr, *d_qcls = nullptr;  // 5-bit BLOSUM62 residue classes of the same buffers
     uint64_t *d_toff = nullptr, *d_qoff = nullptr;
     uint32_t *d_perm = nullptr;               // per query: positions in the reference quicksort order of -kscs (S3)
     so::i64 sub_block = 0;                    // >0: fixed number of queries per seeding sub-block (tests)
@@ -94,6 +139,8 @@ struct so_ctx {
     size_t h_pinned_cap = 0;
 
     so_stats stats = {};
+    so::HostProfile prof;
+    std::vector<so::PackedCands> cand_pool;   // one pinned buffer per chunk, reused across query blocks
 };
 
 namespace so {
@@ -102,10 +149,7 @@ int upload_tables();
 int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out);
 int build_chunk_index(so_ctx *c, ChunkIndex &ix);
 void free_chunk_index(ChunkIndex &ix);
-struct BlockCands {                 // candidates of a query block against one chunk, reference order
-    std::vector<uint64_t> offsets;  // [nq + 1]
-    std::vector<so_cand> cands;
-};
-int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, BlockCands &out);
+int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out);
 int ensure_pinned(so_ctx *c, size_t bytes);
+int classify_residues(so_ctx *c, const uint8_t *d_in, uint8_t *d_out, size_t n);
 }  // namespace so

@@ -400,130 +400,236 @@ __global__ void __launch_bounds__(256) k_expand(const uint32_t *__restrict__ slo
     }
 }
 
-struct ChainState {
-    int total, x, qlo, slo;
+// ---------------------------------------------------------------------------------------------
+// Chained X-drop scoring, lane-persistent.
+//
+// The sorted hit array is cut into diagonal groups (query, target, diagonal).  A group costs anything
+// from one to thousands of extension steps, so a thread-per-group mapping leaves ~3 of 32 lanes busy
+// (ncu, round 1: 2.65 active threads per instruction).  Here every LANE runs a small state machine
+// (NEED -> SEED -> RIGHT -> LEFT -> NEXT ...) and all 32 lanes execute the same "one extension step"
+// body each iteration, whatever group / seed / direction they are in; a lane that finishes its group
+// pulls the next group index from a global counter (warp-aggregated atomicAdd).
+// Semantics: ungap / get_ungap_scores (fsearch.py:2454-2509): per seed (ascending unique qst) a right
+// extension from (Q, S) and a left extension from (Q-1, S-1) continuing the right maximum, both
+// X-drop 30, both confined to lo < q < hi where lo = max(0, diag) for the first seed (index 0 of either
+// sequence is never scored) and the previous segment's max_qed afterwards; hi = min(ql, tl + diag).
+// ---------------------------------------------------------------------------------------------
+struct HeadFlag {
+    const uint64_t *keys;
+    int shift;
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t &p) const {
+        const uint64_t k = keys[p];
+        if (k == ~0ull) return 0u;
+        return (p == 0 || (keys[p - 1] >> shift) != (k >> shift)) ? 1u : 0u;
+    }
 };
 
-__device__ __forceinline__ int chain_seed(ChainState &ch, int Q, int diag, const uint8_t *__restrict__ q, int ql,
-                                           const uint8_t *__restrict__ t, int tl, const int8_t *s_tbl,
-                                           const uint8_t *s_code) {
-    // ungap(qseq, sseq, Qst, Sst, qlo, slo) with dropX = 30 (fsearch.py:2454-2494); s = q - diag
-    int S = Q - diag;
-    const int off = max(max(ch.qlo - Q, ch.slo - S), 0);
-    Q += off;
-    int qq = Q, score = 0, mx = 0, mx_qed = Q, steps = 0;
-    while (qq > ch.qlo && qq < ql && (qq - diag) > ch.slo && (qq - diag) < tl) {
-        score += s_tbl[(int)s_code[q[qq]] * kClasses + s_code[t[qq - diag]]];
-        steps++;
-        if (score > mx) {
-            mx = score;
-            mx_qed = qq;
-        } else if (score + 30 < mx)
-            break;
-        qq++;
-    }
-    qq = Q - 1;
-    score = mx;
-    while (qq < ql && qq > ch.qlo && (qq - diag) < tl && (qq - diag) > ch.slo) {
-        score += s_tbl[(int)s_code[q[qq]] * kClasses + s_code[t[qq - diag]]];
-        steps++;
-        if (score > mx)
-            mx = score;
-        else if (score + 30 < mx)
-            break;
-        qq--;
-    }
-    ch.total += mx;
-    ch.qlo = mx_qed;            // next seed: qlo = max_qed, slo = max_sed (fsearch.py:2502-2506)
-    ch.slo = mx_qed - diag;
-    return steps;
+__global__ void __launch_bounds__(256) k_scatter_heads(const uint64_t *__restrict__ keys, uint32_t n, int shift,
+                                                       const uint32_t *__restrict__ gidx, uint32_t *__restrict__ gheads) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint64_t k = keys[p];
+    if (k == ~0ull) return;
+    if (p == 0 || (keys[p - 1] >> shift) != (k >> shift)) gheads[gidx[p]] = p;
 }
 
-__global__ void __launch_bounds__(128) k_pair_ungap(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                                    uint32_t n, BlockGeom g, const uint8_t *__restrict__ qres,
-                                                    const uint64_t *__restrict__ qoff, const uint8_t *__restrict__ tres,
-                                                    const uint64_t *__restrict__ toff, uint64_t *__restrict__ ckeys,
-                                                    uint64_t *__restrict__ cvals, unsigned long long *__restrict__ counter) {
-    unsigned long long my_steps = 0;
+__global__ void __launch_bounds__(256) k_group_ungap(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                     uint32_t n, const uint32_t *__restrict__ gheads, uint32_t G, BlockGeom g,
+                                                     const uint8_t *__restrict__ qcls, const uint64_t *__restrict__ qoff,
+                                                     const uint8_t *__restrict__ tcls, const uint64_t *__restrict__ toff,
+                                                     uint32_t *__restrict__ gscore, uint32_t *__restrict__ grank,
+                                                     unsigned long long *__restrict__ counters) {
     __shared__ int8_t s_tbl[kClasses * kClasses];
-    __shared__ uint8_t s_code[256];
     for (int k = threadIdx.x; k < kClasses * kClasses; k += blockDim.x) s_tbl[k] = c_score2[k];
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_code[k] = c_code2[k];
     __syncthreads();
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint64_t qmask = (1ull << g.qst_bits) - 1, dmask = (1ull << g.diag_bits) - 1;
     const int pair_shift = g.qst_bits + g.diag_bits;
-    bool head = false;
-    uint64_t key = 0;
-    if (p < n) {
-        key = keys[p];
-        head = key != ~0ull && (p == 0 || (keys[p - 1] >> pair_shift) != (key >> pair_shift));
-    }
-    int best_score = 0, best_diag = 0;
-    uint32_t best_rank = 0xffffffffu, first_rank = 0xffffffffu;
-    int ql_idx = 0, hd1 = 0;
-    if (head) {
-        const uint64_t pair = key >> pair_shift;
-        hd1 = (int)(pair & ((1ull << g.hd_bits) - 1));
-        ql_idx = (int)(pair >> g.hd_bits);
-        const uint64_t qb = qoff[g.qb0 + ql_idx];
-        const int ql = (int)(qoff[g.qb0 + ql_idx + 1] - qb);
-        const int tid = g.c0 + hd1 - 1;
-        const uint64_t tb = toff[tid];
-        const int tl = (int)(toff[tid + 1] - tb);
-        const uint8_t *q = qres + qb, *t = tres + tb;
-        const uint64_t qmask = (1ull << g.qst_bits) - 1, dmask = (1ull << g.diag_bits) - 1;
-        uint32_t e = p;
-        while (e < n) {
-            uint64_t ke = keys[e];
-            if ((ke >> pair_shift) != pair) break;
-            const uint64_t grp = ke >> g.qst_bits;
-            const int diag = (int)(grp & dmask) - g.diag_bias;
-            ChainState ch;
-            ch.total = 0, ch.x = 0, ch.qlo = 0, ch.slo = 0;
-            uint32_t rank_min = 0xffffffffu;
-            int prev_q = -1;
-            while (true) {
-                const int qst = (int)(ke & qmask);
-                rank_min = min(rank_min, vals[e]);
-                if (qst != prev_q) {
-                    my_steps += (unsigned long long)chain_seed(ch, qst, diag, q, ql, t, tl, s_tbl, s_code);
-                    prev_q = qst;
+    constexpr int U = 8;                      // extension steps per loop iteration
+    const unsigned long long kBatch = 256;    // group indices taken per atomic
+    // per-lane state
+    bool has = false, fin = false, stopped = false;
+    uint32_t gi = 0, e = 0, rank_min = 0;
+    uint64_t grp = 0;
+    const uint8_t *q = nullptr, *t = nullptr;  // t is pre-shifted by -diag: t[qq] faces q[qq]
+    int lo = 0, hi = 0, total = 0, prev_q = -1;
+    int Q = 0, qq = 0, score = 0, mx = 0, mx_qed = 0, dir = 1;
+    unsigned long long steps = 0;
+    uint32_t pool_next = 0, pool_end = 0;  // warp-uniform
+    bool exhausted = false;                // warp-uniform
+    for (;;) {
+        // ---- (1) lanes without a group take the next one (a warp draws kBatch indices per atomic)
+        const unsigned need = __ballot_sync(0xffffffffu, !has && !fin);
+        if (need) {
+            if (pool_next == pool_end && !exhausted) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(counters + 2, kBatch);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= G)
+                    exhausted = true;
+                else {
+                    pool_next = (uint32_t)base;
+                    pool_end = (uint32_t)min((unsigned long long)G, base + kBatch);
                 }
-                e++;
-                if (e >= n) break;
-                ke = keys[e];
-                if ((ke >> g.qst_bits) != grp) break;
             }
-            if (ch.total >= 25) {  // self.min (fsearch.py:2224, 2707)
-                first_rank = min(first_rank, rank_min);
-                if (ch.total > best_score || (ch.total == best_score && rank_min < best_rank)) {
-                    best_score = ch.total;
-                    best_rank = rank_min;
-                    best_diag = diag;
+            if (!has && !fin) {
+                const uint32_t mine = pool_next + __popc(need & ((1u << lane) - 1));
+                if (mine < pool_end) {
+                    gi = mine;
+                    e = gheads[gi];
+                    const uint64_t key = keys[e];
+                    grp = key >> g.qst_bits;
+                    const int diag = (int)(grp & dmask) - g.diag_bias;
+                    const uint64_t pair = key >> pair_shift;
+                    const int hd1 = (int)(pair & ((1ull << g.hd_bits) - 1));
+                    const int qi = (int)(pair >> g.hd_bits);
+                    const uint64_t qb = qoff[g.qb0 + qi];
+                    const int ql = (int)(qoff[g.qb0 + qi + 1] - qb);
+                    const int tid = g.c0 + hd1 - 1;
+                    const uint64_t tb = toff[tid];
+                    const int tl = (int)(toff[tid + 1] - tb);
+                    q = qcls + qb;
+                    t = tcls + tb - diag;
+                    lo = max(0, diag);            // first seed: 0 < q and 0 < s
+                    hi = min(ql, tl + diag);      // q < ql and s < tl
+                    total = 0;
+                    rank_min = vals[e];
+                    prev_q = (int)(key & qmask);
+                    Q = max(prev_q, lo);          // off = max(qlo - Q, slo - S, 0)
+                    qq = Q, score = 0, mx = 0, mx_qed = Q, dir = 1;
+                    stopped = false;
+                    has = true;
+                } else if (exhausted)
+                    fin = true;  // otherwise the pool is refilled in the next iteration
+            }
+            pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
+        }
+        if (__all_sync(0xffffffffu, fin)) break;
+        // ---- (2) U extension steps; right (dir = +1) and left (dir = -1) extensions share the body
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool act = has && !stopped;
+            const bool in = act && qq > lo && qq < hi;
+            int sc = 0;
+            if (in) sc = s_tbl[(int)q[qq] * kClasses + t[qq]];
+            if (in) {
+                score += sc;
+                steps++;
+                if (score > mx) {
+                    mx = score;
+                    if (dir > 0) mx_qed = qq;
+                } else if (score + 30 < mx)
+                    stopped = true;
+                qq += dir;
+            } else if (act)
+                stopped = true;
+        }
+        // ---- (3) transitions of the lanes whose extension ended
+        if (has && stopped) {
+            if (dir > 0) {  // right done -> left from (Q-1, S-1), continuing the right maximum
+                dir = -1;
+                qq = Q - 1;
+                score = mx;
+                stopped = false;
+            } else {        // seed done
+                total += mx;
+                lo = mx_qed;  // next seed: qlo = max_qed, slo = max_sed (same diagonal)
+                bool more = false;
+                for (;;) {
+                    e++;
+                    if (e >= n) break;
+                    const uint64_t k2 = keys[e];
+                    if ((k2 >> g.qst_bits) != grp) break;
+                    rank_min = min(rank_min, vals[e]);
+                    const int qst = (int)(k2 & qmask);
+                    if (qst == prev_q) continue;  // same point again (other pattern / alphabet): lis() drops it
+                    prev_q = qst;
+                    more = true;
+                    break;
+                }
+                if (more) {
+                    Q = max(prev_q, lo);
+                    qq = Q, score = 0, mx = 0, mx_qed = Q, dir = 1;
+                    stopped = false;
+                } else {
+                    gscore[gi] = (uint32_t)total;
+                    grank[gi] = rank_min;
+                    has = false;
                 }
             }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
-    if ((threadIdx.x & 31) == 0 && my_steps) atomicAdd(counter + 1, my_steps);
-    // warp-aggregated append of the candidates
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
+    if (lane == 0 && steps) atomicAdd(counters + 1, steps);
+}
+
+// one thread per diagonal group; the first group of a (query, target) pair folds the pair:
+// threshold 25, best diagonal (first appearance wins ties), candidate order = first passing rank
+__global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gheads,
+                                                     uint32_t G, BlockGeom g, const uint32_t *__restrict__ gscore,
+                                                     const uint32_t *__restrict__ grank, uint64_t *__restrict__ ckeys,
+                                                     uint64_t *__restrict__ cvals, unsigned long long *__restrict__ counters) {
+    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pair_shift = g.qst_bits + g.diag_bits;
+    const uint64_t dmask = (1ull << g.diag_bits) - 1;
+    bool head = false;
+    uint64_t pair = 0;
+    if (gi < G) {
+        pair = keys[gheads[gi]] >> pair_shift;
+        head = gi == 0 || (keys[gheads[gi - 1]] >> pair_shift) != pair;
+    }
+    int best_score = 0, best_diag = 0;
+    uint32_t best_rank = 0xffffffffu, first_rank = 0xffffffffu;
+    if (head) {
+        for (uint32_t k = gi; k < G; k++) {
+            const uint64_t kk = keys[gheads[k]];
+            if ((kk >> pair_shift) != pair) break;
+            const int sc = (int)gscore[k];
+            if (sc >= 25) {  // self.min (fsearch.py:2224, 2707)
+                const uint32_t rk = grank[k];
+                first_rank = min(first_rank, rk);
+                if (sc > best_score || (sc == best_score && rk < best_rank)) {
+                    best_score = sc;
+                    best_rank = rk;
+                    best_diag = (int)((kk >> g.qst_bits) & dmask) - g.diag_bias;
+                }
+            }
+        }
+    }
     const bool emit = head && best_score >= 25;
     const unsigned m = __ballot_sync(0xffffffffu, emit);
     if (m) {
         const int lane = threadIdx.x & 31;
         const int leader = __ffs(m) - 1;
         unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+        if (lane == leader) base = atomicAdd(counters, (unsigned long long)__popc(m));
         base = __shfl_sync(0xffffffffu, base, leader);
         if (emit) {
             const unsigned long long o = base + __popc(m & ((1u << lane) - 1));
-            ckeys[o] = ((uint64_t)ql_idx << 32) | first_rank;
+            const int hd1 = (int)(pair & ((1ull << g.hd_bits) - 1));
+            const int qi = (int)(pair >> g.hd_bits);
+            ckeys[o] = ((uint64_t)qi << 32) | first_rank;
             // value: target ordinal (24 bits) | score (20 bits) | diagonal + bias (20 bits)
             cvals[o] = ((uint64_t)(uint32_t)(g.c0 + hd1 - 1) << 40) | ((uint64_t)(uint32_t)best_score << 20) |
-                       (uint64_t)(uint32_t)(best_diag + g.diag_bias);
+                       (uint64_t)(uint32_t)(best_diag + kCandDiagBias);
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_classify(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = c_code2[in[i]];
+}
+
+int classify_residues(so_ctx *c, const uint8_t *d_in, uint8_t *d_out, size_t n) {
+    int rc = upload_cfg(c->P);
+    if (rc != SO_OK) return rc;
+    if (n == 0) return SO_OK;
+    k_classify<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_in, d_out, n);
+    SO_CUDA(cudaGetLastError());
+    c->stats.kernel_launches += 1;
+    return SO_OK;
 }
 
 __global__ void k_query_bounds(const uint64_t *__restrict__ ckeys, uint32_t n, int nq, uint32_t *__restrict__ bounds) {
@@ -551,15 +657,16 @@ static int bits_for(uint64_t maxval) {  // bits needed to hold values 0..maxval
     return b;
 }
 
-enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TMP, SC_CKA, SC_CKB, SC_CVA, SC_CVB, SC_MISC };
+enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TMP, SC_CKA, SC_CKB, SC_CVA, SC_CVB, SC_MISC,
+       SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK };
 
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
 
-int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, BlockCands &out) {
+int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out) {
     const Params &P = c->P;
     const i64 nq_total = q_end - q_begin;
     out.offsets.assign((size_t)nq_total + 1, 0);
-    out.cands.clear();
+    out.n = 0;
     if (nq_total <= 0) return SO_OK;
     if (ix.n_seeds == 0) return SO_OK;
     int rc;
@@ -685,9 +792,49 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Bl
             uint64_t *cva = (uint64_t *)c->scratch[SC_CVA].p, *cvb = (uint64_t *)c->scratch[SC_CVB].p;
             unsigned long long *d_counter = (unsigned long long *)(c->scratch[SC_MISC].p);
             uint32_t *d_bounds = (uint32_t *)(c->scratch[SC_MISC].p + 32);
-            SO_CUDA(cudaMemsetAsync(d_counter, 0, 16, st));
-            k_pair_ungap<<<(uint32_t)((H + 127) / 128), 128, 0, st>>>(dk.Current(), dv.Current(), (uint32_t)H, g, c->d_qres,
-                                                                      c->d_qoff, c->d_tres, c->d_toff, cka, cva, d_counter);
+            SO_CUDA(cudaMemsetAsync(d_counter, 0, 32, st));
+            // diagonal groups: head flags -> exclusive scan -> compact head positions
+            const int grp_shift = g.qst_bits;
+            if ((rc = c->scratch[SC_GIDX].reserve(((size_t)H + 1) * 4)) != SO_OK) return rc;
+            uint32_t *d_gidx = (uint32_t *)c->scratch[SC_GIDX].p;
+            {
+                HeadFlag hf{dk.Current(), grp_shift};
+                cub::CountingInputIterator<uint32_t> cnt(0);
+                cub::TransformInputIterator<uint32_t, HeadFlag, cub::CountingInputIterator<uint32_t>> flags(cnt, hf);
+                tmp = 0;
+                cub::DeviceScan::ExclusiveSum(nullptr, tmp, flags, d_gidx, (int)H, st);
+                if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+                SO_CUDA(cub::DeviceScan::ExclusiveSum(c->scratch[SC_TMP].p, tmp, flags, d_gidx, (int)H, st));
+            }
+            // number of groups = gidx[H-1] + flag(H-1); read it back to size the group arrays
+            uint32_t last_idx = 0;
+            uint64_t last_keys[2] = {0, 0};
+            SO_CUDA(cudaMemcpyAsync(&last_idx, d_gidx + (H - 1), 4, cudaMemcpyDeviceToHost, st));
+            SO_CUDA(cudaMemcpyAsync(last_keys, dk.Current() + (H >= 2 ? H - 2 : 0), H >= 2 ? 16 : 8, cudaMemcpyDeviceToHost, st));
+            SO_CUDA(cudaStreamSynchronize(st));
+            uint32_t G;
+            {
+                const uint64_t kl = H >= 2 ? last_keys[1] : last_keys[0];
+                bool flag = kl != ~0ull && (H < 2 || (last_keys[0] >> grp_shift) != (kl >> grp_shift));
+                G = last_idx + (flag ? 1u : 0u);
+            }
+            c->stats.groups += (i64)G;
+            if ((rc = c->scratch[SC_GHEAD].reserve(((size_t)G + 1) * 4)) != SO_OK) return rc;
+            if ((rc = c->scratch[SC_GSCORE].reserve(((size_t)G + 1) * 4)) != SO_OK) return rc;
+            if ((rc = c->scratch[SC_GRANK].reserve(((size_t)G + 1) * 4)) != SO_OK) return rc;
+            uint32_t *d_gheads = (uint32_t *)c->scratch[SC_GHEAD].p, *d_gscore = (uint32_t *)c->scratch[SC_GSCORE].p;
+            uint32_t *d_grank = (uint32_t *)c->scratch[SC_GRANK].p;
+            if (G > 0) {
+                k_scatter_heads<<<(uint32_t)((H + 255) / 256), 256, 0, st>>>(dk.Current(), (uint32_t)H, grp_shift, d_gidx, d_gheads);
+                int per_sm = 4;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_group_ungap, 256, 0);
+                const int ublocks = 148 * std::max(1, per_sm);
+                k_group_ungap<<<ublocks, 256, 0, st>>>(dk.Current(), dv.Current(), (uint32_t)H, d_gheads, G, g, c->d_qcls, c->d_qoff,
+                                                       c->d_tcls, c->d_toff, d_gscore, d_grank, d_counter);
+                k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, G, g, d_gscore, d_grank, cka, cva, d_counter);
+                c->stats.kernel_launches += 3;
+                c->stats.lib_launches += 1;
+            }
             SO_CUDA(cudaEventRecord(c->ev[3], st));
             unsigned long long h_counter[2] = {0, 0};
             SO_CUDA(cudaMemcpyAsync(h_counter, d_counter, 16, cudaMemcpyDeviceToHost, st));
@@ -695,10 +842,10 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Bl
             const unsigned long long ncand = h_counter[0];
             c->stats.ungap_steps += (i64)h_counter[1];
             SO_CUDA(cudaGetLastError());
-            c->stats.kernel_launches += 2;
+            c->stats.kernel_launches += 1;
             c->stats.lib_launches += 1;
             std::vector<uint32_t> bounds((size_t)nq + 1, 0);
-            std::vector<uint64_t> h_cv;
+            const size_t base_c = out.n;
             if (ncand > 0) {
                 cub::DoubleBuffer<uint64_t> ck(cka, ckb), cv(cva, cvb);
                 tmp = 0;
@@ -707,17 +854,20 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Bl
                 SO_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch[SC_TMP].p, tmp, ck, cv, (int)ncand, 0, 32 + q_bits, st));
                 k_query_bounds<<<(nq + 1 + 127) / 128, 128, 0, st>>>(ck.Current(), (uint32_t)ncand, nq, d_bounds);
                 SO_CUDA(cudaEventRecord(c->ev[4], st));
-                h_cv.resize((size_t)ncand);
-                SO_CUDA(cudaMemcpyAsync(h_cv.data(), cv.Current(), (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
+                Timer td;
+                if ((rc = out.reserve(base_c + (size_t)ncand)) != SO_OK) return rc;
+                SO_CUDA(cudaMemcpyAsync(out.vals + base_c, cv.Current(), (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
                 SO_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds, ((size_t)nq + 1) * 4, cudaMemcpyDeviceToHost, st));
                 SO_CUDA(cudaStreamSynchronize(st));
                 SO_CUDA(cudaGetLastError());
+                out.n = base_c + (size_t)ncand;
                 c->stats.kernel_launches += 1;
                 c->stats.lib_launches += 1;
                 c->stats.d2h_bytes += (i64)ncand * 8 + ((i64)nq + 1) * 4;
                 float ms = 0;
                 cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
                 c->stats.ms_select += ms;
+                c->prof.d2h_ms += td.ms();
             }
             float ms = 0;
             cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
@@ -726,21 +876,6 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Bl
             c->stats.ms_sort += ms;
             cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
             c->stats.ms_ungap += ms;
-            const size_t base_c = out.cands.size();
-            out.cands.resize(base_c + (size_t)ncand);
-            for (size_t k = 0; k < (size_t)ncand; k++) {
-                const uint64_t v = h_cv[k];
-                const int diag = (int)(v & 0xfffffu) - g.diag_bias;
-                so_cand cd;
-                cd.target = (uint32_t)(v >> 40);
-                cd.score = (uint32_t)((v >> 20) & 0xfffffu);
-                // guess_start (fsearch.py:2544-2553): d = sst - qst = -diag
-                if (diag < 0)
-                    cd.qi = 0, cd.qj = (uint32_t)(-diag);
-                else
-                    cd.qi = (uint32_t)diag, cd.qj = 0;
-                out.cands[base_c + k] = cd;
-            }
             for (int k = 0; k < nq; k++)
                 out.offsets[(size_t)(b0 - q_begin + k + 1)] = (uint64_t)base_c + bounds[(size_t)k + 1];
         }
@@ -758,7 +893,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Bl
         }
         b0 = b1;
     }
-    c->stats.candidates += (i64)out.cands.size();
+    c->stats.candidates += (i64)out.n;
     return SO_OK;
 }
 
