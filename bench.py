@@ -178,6 +178,23 @@ def workload_config(args, block):
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
+# positions in the per-rank value vector that are combined with MAX (times); the rest are summed (work)
+MAX_IDX = (0, 1, 5, 6, 7, 8, 9, 10, 11, 16, 17)
+
+
+def reduce_over_ranks(vals, dist, device):
+    """max over ranks for times, sum over ranks for work counters (multi-GPU numbers are never wall
+    clock of one rank)."""
+    if dist is None:
+        return list(vals)
+    import torch
+    t = torch.tensor(vals, dtype=torch.float64, device=device)
+    mx, sm = t.clone(), t.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    return [(mx[i] if i in MAX_IDX else sm[i]).item() for i in range(len(vals))]
+
+
 def run_ours(args, rank, world, local):
     dist = None
     if world > 1:
@@ -263,15 +280,7 @@ def run_ours(args, rank, world, local):
             st['ms_seed'], st['ms_select'], st['ms_traceback'], st['ms_host'], float(st['seed_hits']),
             float(st['kernel_launches']), float(st['ungap_steps']), float(st['alignments']),
             float(st2['h2d_bytes']), float(st2['d2h_bytes'])]
-    if dist is not None:
-        import torch
-        t = torch.tensor(vals, dtype=torch.float64, device='cuda')
-        mx = t.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = t.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        vals = [mx[0].item(), mx[1].item()] + [sm[i].item() for i in range(2, 5)] + [mx[i].item() for i in range(5, 12)] + \
-               [sm[i].item() for i in range(12, 16)] + [mx[16].item(), mx[17].item()]
+    vals = reduce_over_ranks(vals, dist, 'cuda' if dist is not None else None)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -124,24 +124,11 @@ def main(argv=None):
     local = int(os.environ.get('LOCAL_RANK', str(rank)))
     os.makedirs(tmpdir, exist_ok=True)
     tmp_name = outfile.split(os.sep)[-1]
-    common = (exp, bv)
     if world > 1:
-        sl = slices_by_residues(Q, Start, End, world)
-        mine = sl[rank] if rank < len(sl) else None
-        if mine:
-            part = '%s/%s.%012d' % (tmpdir, tmp_name, mine[0])
-            _worker((local % ndev, qry, ref, part, exp, bv, mine[0], mine[1], rstart, rend, miss, thr, step, flt, ht,
-                     chk, ssd, nr))
-            open(part + '.done', 'w').close()
-        if rank == 0:
-            import time
-            for s in sl:
-                while not os.path.exists('%s/%s.%012d.done' % (tmpdir, tmp_name, s[0])):
-                    time.sleep(0.05)
-            _concat(outfile, ['%s/%s.%012d' % (tmpdir, tmp_name, s[0]) for s in sl], wrt)
-            shutil.rmtree(tmpdir, ignore_errors=True)
+        run_sharded(Q, Start, End, rank, world, outfile, tmpdir, wrt,
+                    lambda s, e, part: _worker((local % ndev, qry, ref, part, exp, bv, s, e, rstart, rend, miss, thr,
+                                                step, flt, ht, chk, ssd, nr)))
         return 0
-    del common
     ngpu = max(1, min(ngpu, ndev))
     sl = slices_by_residues(Q, Start, End, ngpu) if End > Start else []
     jobs = []
@@ -156,6 +143,28 @@ def main(argv=None):
     _concat(outfile, parts, wrt)
     shutil.rmtree(tmpdir, ignore_errors=True)                          # bin/find_hit.py:354-355
     return 0
+
+
+def run_sharded(Q, Start, End, rank, world, outfile, tmpdir, wrt, worker):
+    """One rank of a multi-process run: search this rank's query slice into a part file; rank 0 waits for
+    every part and concatenates them in ascending query order (bin/find_hit.py:135-146).  No collective
+    is needed on this path: the exchange is the part files, exactly like the reference."""
+    import time
+    os.makedirs(tmpdir, exist_ok=True)
+    tmp_name = outfile.split(os.sep)[-1]
+    sl = slices_by_residues(Q, Start, End, world) if End > Start else []
+    mine = sl[rank] if rank < len(sl) else None
+    if mine:
+        part = '%s/%s.%012d' % (tmpdir, tmp_name, mine[0])
+        worker(mine[0], mine[1], part)
+        open(part + '.done', 'w').close()
+    if rank == 0:
+        for s in sl:
+            while not os.path.exists('%s/%s.%012d.done' % (tmpdir, tmp_name, s[0])):
+                time.sleep(0.05)
+        _concat(outfile, ['%s/%s.%012d' % (tmpdir, tmp_name, s[0]) for s in sl], wrt)
+        shutil.rmtree(tmpdir, ignore_errors=True)
+    return sl
 
 
 def _concat(outfile, parts, wrt):

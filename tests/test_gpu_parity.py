@@ -250,3 +250,18 @@ def test_search_config4_seed_against_oracle(so, oracle, tmp_path):
     out = str(tmp_path / 'gpu.sc')
     so.blastp(p, p, out, expect=1e-3, step=1, ht=120000000, chk=50000, ssd='1110100111')
     assert open(out, 'rb').read() == open(ref, 'rb').read()
+
+
+def test_find_hit_cli_drop_in(so, golden_cases, tmp_path):
+    """The find_hit.py-compatible command line (bin/find_hit.py flags) writes the reference's file."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    fsa = os.path.join(GOLDEN, 'synth60.fsa')
+    out = str(tmp_path / 'cli.sc')
+    r = subprocess.run([sys.executable, '-m', 'swiftortho_b200.find_hit', '-p', 'blastp', '-i', fsa, '-d', fsa, '-o', out,
+                        '-e', '1e-5', '-s', '111111', '-M', '1000003', '-a', '1'], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert 'chk size 50000' in r.stdout
+    assert open(out, 'rb').read() == open(os.path.join(GOLDEN, 'synth60.sc'), 'rb').read()
+    assert not os.path.exists(out + '_sc_tmpdir')
