@@ -291,11 +291,11 @@ def run_ours(args, rank, world, local):
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(
         os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     int_peak = json.load(open(os.path.join(ROOT, 'profiles', 'int_peak.json')))
-    # dominant kernel of the step = chained X-drop scoring (k_pair_ungap): integer-pipe bound
+    # dominant kernel of the step = chained X-drop scoring (k_group_ungap): integer-pipe bound
     # (6 INT ops per extension step); peak = measured INT32 op rate of this chip
     ops = 6.0 * ungap_steps / max(world, 1)
     ach = ops / (ms_ungap * 1e-3) / 1e9 if ms_ungap > 0 else 0.0
-    roof = {'kernel': 'k_pair_ungap', 'bound': 'int32', 'achieved': ach, 'peak': int_peak['gops_measured'],
+    roof = {'kernel': 'k_group_ungap', 'bound': 'int32', 'achieved': ach, 'peak': int_peak['gops_measured'],
             'unit': 'Gop/s', 'frac': ach / int_peak['gops_measured'], 'traffic': None,
             'peak_source': 'tools/int_peak.cu measured on this pool (profiles/int_peak.json)',
             'share_of_step_device_time': ms_ungap / max(1e-9, ms_ungap + ms_sort + ms_seed + ms_select + ms_dp + ms_tb)}

@@ -250,6 +250,14 @@ static inline i64 band_cells(i64 len0, i64 len1) {
     return cl;
 }
 
+void merge_align_stats(so_ctx *c) {
+    so_stats &a = c->stats_aln, &d = c->stats;
+    d.alignments += a.alignments, d.dp_cells += a.dp_cells, d.kernel_launches += a.kernel_launches;
+    d.ms_align += a.ms_align, d.ms_dp += a.ms_dp, d.ms_traceback += a.ms_traceback, d.ms_host += a.ms_host;
+    d.h2d_bytes += a.h2d_bytes, d.d2h_bytes += a.d2h_bytes;
+    memset(&a, 0, sizeof a);
+}
+
 // -----------------------------------------------------------------------------------------------
 // Host driver: resolves pairs to device tasks, sorts by length, launches, converts coordinates.
 // -----------------------------------------------------------------------------------------------
@@ -331,20 +339,20 @@ int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
     uint64_t *d_wb = (uint64_t *)c->scratch[1].p;
     DpOut *d_dp = (DpOut *)c->scratch[2].p;
     TbOut *d_tb = (TbOut *)c->scratch[3].p;
-    SO_CUDA(cudaMemcpyAsync(d_tasks, sorted.data(), b_tasks, cudaMemcpyHostToDevice, c->stream));
-    SO_CUDA(cudaMemcpyAsync(d_wb, wbase.data(), b_wb, cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA(cudaMemcpyAsync(d_tasks, sorted.data(), b_tasks, cudaMemcpyHostToDevice, c->stream_aln));
+    SO_CUDA(cudaMemcpyAsync(d_wb, wbase.data(), b_wb, cudaMemcpyHostToDevice, c->stream_aln));
     const int grid = (int)((n + 127) / 128);
-    SO_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    k_banded_dp<<<grid, 128, 0, c->stream>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp);
-    SO_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    k_traceback<<<grid, 128, 0, c->stream>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp, d_tb);
-    SO_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    SO_CUDA(cudaEventRecord(c->ev_aln[0], c->stream_aln));
+    k_banded_dp<<<grid, 128, 0, c->stream_aln>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp);
+    SO_CUDA(cudaEventRecord(c->ev_aln[1], c->stream_aln));
+    k_traceback<<<grid, 128, 0, c->stream_aln>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp, d_tb);
+    SO_CUDA(cudaEventRecord(c->ev_aln[2], c->stream_aln));
     SO_CUDA(cudaGetLastError());
     std::vector<DpOut> h_dp((size_t)n);
     std::vector<TbOut> h_tb((size_t)n);
-    SO_CUDA(cudaMemcpyAsync(h_dp.data(), d_dp, (size_t)n * sizeof(DpOut), cudaMemcpyDeviceToHost, c->stream));
-    SO_CUDA(cudaMemcpyAsync(h_tb.data(), d_tb, (size_t)n * sizeof(TbOut), cudaMemcpyDeviceToHost, c->stream));
-    SO_CUDA(cudaStreamSynchronize(c->stream));
+    SO_CUDA(cudaMemcpyAsync(h_dp.data(), d_dp, (size_t)n * sizeof(DpOut), cudaMemcpyDeviceToHost, c->stream_aln));
+    SO_CUDA(cudaMemcpyAsync(h_tb.data(), d_tb, (size_t)n * sizeof(TbOut), cudaMemcpyDeviceToHost, c->stream_aln));
+    SO_CUDA(cudaStreamSynchronize(c->stream_aln));
     if (getenv("SO_DEBUG_TRACE") && n == 1) {
         int rows = std::min(sorted[0].len1, sorted[0].len0 + 16);
         std::vector<uint64_t> tr((size_t)rows * 32);
@@ -354,15 +362,15 @@ int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
         for (int i = 1; i <= rows && i <= 12; i++) fprintf(stderr, "DBG row %d %016llx\n", i, (unsigned long long)tr[(size_t)(i - 1) * 32]);
     }
     float ms_dp = 0, ms_tb = 0;
-    cudaEventElapsedTime(&ms_dp, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&ms_tb, c->ev[1], c->ev[2]);
-    c->stats.ms_align += ms_dp + ms_tb;
-    c->stats.ms_dp += ms_dp;
-    c->stats.ms_traceback += ms_tb;
-    c->stats.kernel_launches += 2;
-    c->stats.alignments += n;
-    c->stats.h2d_bytes += (i64)(b_tasks + b_wb);
-    c->stats.d2h_bytes += (i64)((size_t)n * (sizeof(DpOut) + sizeof(TbOut)));
+    cudaEventElapsedTime(&ms_dp, c->ev_aln[0], c->ev_aln[1]);
+    cudaEventElapsedTime(&ms_tb, c->ev_aln[1], c->ev_aln[2]);
+    c->stats_aln.ms_align += ms_dp + ms_tb;
+    c->stats_aln.ms_dp += ms_dp;
+    c->stats_aln.ms_traceback += ms_tb;
+    c->stats_aln.kernel_launches += 2;
+    c->stats_aln.alignments += n;
+    c->stats_aln.h2d_bytes += (i64)(b_tasks + b_wb);
+    c->stats_aln.d2h_bytes += (i64)((size_t)n * (sizeof(DpOut) + sizeof(TbOut)));
     for (i64 s = 0; s < n; s++) {
         const int k = order[(size_t)s];
         const Prep &r = prep[(size_t)k];
@@ -388,8 +396,8 @@ int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
         o.cells = (int32_t)cl;
         cells += cl;
     }
-    c->stats.dp_cells += cells;
-    c->stats.ms_host += tm.ms() - (ms_dp + ms_tb);
+    c->stats_aln.dp_cells += cells;
+    c->stats_aln.ms_host += tm.ms() - (ms_dp + ms_tb);
     return SO_OK;
 }
 

@@ -5,6 +5,10 @@
 // 16-column text writer (lib/fsearch.py:3233-3243).
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <thread>
 
@@ -151,7 +155,9 @@ int so_ctx_create(int device, const so_params *p, so_ctx **out) {
     c->device = device;
     c->P = P;
     SO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SO_CUDA(cudaStreamCreateWithFlags(&c->stream_aln, cudaStreamNonBlocking));
     for (auto &e : c->ev) SO_CUDA(cudaEventCreate(&e));
+    for (auto &e : c->ev_aln) SO_CUDA(cudaEventCreate(&e));
     if ((rc = so::upload_tables()) != SO_OK) {
         delete c;
         return rc;
@@ -177,6 +183,9 @@ void so_ctx_destroy(so_ctx *c) {
     for (auto &pc : c->cand_pool) pc.release();
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : c->ev_aln)
+        if (e) cudaEventDestroy(e);
+    if (c->stream_aln) cudaStreamDestroy(c->stream_aln);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -362,7 +371,9 @@ int so_align_batch(so_ctx *c, const so_pair *pairs, int64_t n, so_aln *out) {
         return SO_EINVAL;
     }
     SO_CUDA(cudaSetDevice(c->device));
-    return so::align_pairs(c, pairs, n, out);
+    int rc = so::align_pairs(c, pairs, n, out);
+    so::merge_align_stats(c);
+    return rc;
 }
 
 int so_stats_get(const so_ctx *c, so_stats *s) {
@@ -400,24 +411,32 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     const double max_miss = std::max(P.max_miss, 1e-3);                      // fsearch.py:2970
     const i64 vmax = (i64)std::max(100., std::max((double)(P.v + 100), (double)P.v * 1.1));  // fsearch.py:3059
     std::vector<so_hit> all_rows;
-    const i64 QB = 512;
-    for (i64 b0 = q_begin; b0 < q_end; b0 += QB) {
-        const i64 b1 = std::min<i64>(q_end, b0 + QB);
+    const size_t nch = c->chunks.size();
+    // query block size: candidates of a block are held packed in pinned memory, one buffer per chunk
+    const i64 QB = std::max<i64>(64, std::min<i64>(512, 4096 / (i64)std::max<size_t>(1, nch)));
+    if (c->cand_pool.size() < 2 * nch) c->cand_pool.resize(2 * nch);
+    // Two-stage pipeline: this thread produces the candidates of block b+1 on the GPU while a worker
+    // thread sorts / selects / aligns (own stream) / filters block b.  Rows are appended in block order.
+    struct Job {
+        i64 b0, b1;
+        int slot;
+    };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Job> jobs;
+    bool producer_done = false, slot_busy[2] = {false, false};
+    int worker_rc = SO_OK;
+    std::string worker_err;
+    so_stats wstats;
+    memset(&wstats, 0, sizeof wstats);
+
+    auto post_block = [&](i64 b0, i64 b1, int slot, const std::function<void()> &release_slot) -> int {
         const i64 nq = b1 - b0;
         std::vector<QueryState> qs((size_t)nq);
-        // PASS 1 (fsearch.py:2990-3016): candidates of every chunk (packed, pinned, reference order)
-        Timer tc;
-        const size_t nch = c->chunks.size();
-        if (c->cand_pool.size() < nch) c->cand_pool.resize(nch);
-        for (size_t ch = 0; ch < nch; ch++) {
-            int rc = so::chunk_candidates(c, c->chunks[ch], b0, b1, c->cand_pool[ch]);
-            if (rc != SO_OK) return rc;
-        }
-        c->prof.cand_ms += tc.ms();
         // candidate `idx` of query k in the chunk-major concatenation (fsearch.py:3043-3049)
         auto cand_at = [&](i64 k, uint32_t idx) -> uint64_t {
             for (size_t ch = 0; ch < nch; ch++) {
-                const so::PackedCands &pc = c->cand_pool[ch];
+                const so::PackedCands &pc = c->cand_pool[(size_t)slot * nch + ch];
                 const uint64_t lo = pc.offsets[(size_t)k], hi = pc.offsets[(size_t)k + 1];
                 if (idx < hi - lo) return pc.vals[lo + idx];
                 idx -= (uint32_t)(hi - lo);
@@ -429,11 +448,11 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
         so::parallel_for(nq, [&](i64 k) {
             QueryState &s = qs[(size_t)k];
             i64 n = 0;
-            for (size_t ch = 0; ch < nch; ch++) n += (i64)(c->cand_pool[ch].offsets[(size_t)k + 1] - c->cand_pool[ch].offsets[(size_t)k]);
+            for (size_t ch = 0; ch < nch; ch++) n += (i64)(c->cand_pool[(size_t)slot * nch + ch].offsets[(size_t)k + 1] - c->cand_pool[(size_t)slot * nch + ch].offsets[(size_t)k]);
             s.order.resize((size_t)n);
             i64 w = 0;
             for (size_t ch = 0; ch < nch; ch++) {
-                const so::PackedCands &pc = c->cand_pool[ch];
+                const so::PackedCands &pc = c->cand_pool[(size_t)slot * nch + ch];
                 for (uint64_t p = pc.offsets[(size_t)k]; p < pc.offsets[(size_t)k + 1]; p++, w++) {
                     const uint32_t score = (uint32_t)((pc.vals[p] >> 20) & 0xfffffu);
                     s.order[(size_t)w] = ((uint64_t)(0xffffffffu - score) << 32) | (uint32_t)w;
@@ -451,8 +470,9 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             for (i64 i = 0; i < s.limit; i++) s.sel[(size_t)i] = so::unpack_cand(cand_at(k, (uint32_t)s.order[(size_t)i]));
             std::vector<uint64_t>().swap(s.order);
         });
-        c->stats.ms_host += th.ms();
+        wstats.ms_host += th.ms();
         c->prof.order_ms += th.ms();
+        release_slot();  // the packed candidates of this block are no longer needed
         // alignment rounds: the stop rule (fsearch.py:3103) is sequential per query, so each round
         // aligns the next kRound candidates of every unfinished query and the host replays the rule
         Timer trd;
@@ -554,7 +574,7 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 }
                 if (s.next >= s.limit) s.done = true;
             }
-            c->stats.ms_host += tr.ms();
+            wstats.ms_host += tr.ms();
             c->prof.replay_ms += tr.ms();
         }
         c->prof.rounds_ms += trd.ms();
@@ -576,10 +596,81 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
         });
         for (i64 k = 0; k < nq; k++) {
             all_rows.insert(all_rows.end(), qs[(size_t)k].rows.begin(), qs[(size_t)k].rows.end());
-            c->stats.queries++;
+            wstats.queries++;
         }
-        c->stats.ms_host += tf.ms();
+        wstats.ms_host += tf.ms();
         c->prof.final_ms += tf.ms();
+        return SO_OK;
+    };
+
+    std::thread worker([&]() {
+        cudaSetDevice(c->device);
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !jobs.empty() || producer_done; });
+                if (jobs.empty()) return;
+                j = jobs.front();
+                jobs.pop_front();
+            }
+            bool released = false;
+            auto release = [&]() {
+                if (released) return;
+                released = true;
+                std::lock_guard<std::mutex> lk(mu);
+                slot_busy[j.slot] = false;
+                cv.notify_all();
+            };
+            int rc = worker_rc == SO_OK ? post_block(j.b0, j.b1, j.slot, release) : SO_OK;
+            if (rc != SO_OK && worker_rc == SO_OK) {
+                std::lock_guard<std::mutex> lk(mu);
+                worker_rc = rc;
+                worker_err = so::get_error();
+            }
+            release();
+        }
+    });
+    int prod_rc = SO_OK;
+    int blk = 0;
+    for (i64 b0 = q_begin; b0 < q_end && prod_rc == SO_OK; b0 += QB, blk++) {
+        const i64 b1 = std::min<i64>(q_end, b0 + QB);
+        const int slot = blk & 1;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !slot_busy[slot]; });
+            if (worker_rc != SO_OK) break;
+            slot_busy[slot] = true;
+        }
+        // PASS 1 (fsearch.py:2990-3016): candidates of every chunk (packed, pinned, reference order)
+        Timer tc;
+        for (size_t ch = 0; ch < nch && prod_rc == SO_OK; ch++)
+            prod_rc = so::chunk_candidates(c, c->chunks[ch], b0, b1, c->cand_pool[(size_t)slot * nch + ch]);
+        c->prof.cand_ms += tc.ms();
+        std::lock_guard<std::mutex> lk(mu);
+        if (prod_rc == SO_OK)
+            jobs.push_back(Job{b0, b1, slot});
+        else
+            slot_busy[slot] = false;
+        cv.notify_all();
+    }
+    std::string prod_err = prod_rc != SO_OK ? std::string(so::get_error()) : std::string();
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        producer_done = true;
+        cv.notify_all();
+    }
+    worker.join();
+    c->stats.ms_host += wstats.ms_host;
+    c->stats.queries += wstats.queries;
+    so::merge_align_stats(c);
+    if (prod_rc != SO_OK) {
+        set_error("%s", prod_err.c_str());
+        return prod_rc;
+    }
+    if (worker_rc != SO_OK) {
+        set_error("%s", worker_err.c_str());
+        return worker_rc;
     }
     c->stats.rows += (i64)all_rows.size();
     *n_rows = (int64_t)all_rows.size();

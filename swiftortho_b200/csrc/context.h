@@ -117,6 +117,8 @@ struct so_ctx {
     so::Params P;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaStream_t stream_aln = nullptr;        // alignment rounds run on their own stream (pipeline worker thread)
+    cudaEvent_t ev_aln[4] = {};
 
     // targets (raw bytes) and queries (seg-masked bytes), packed, resident in HBM
     so::i64 n_t = 0, n_q = 0;
@@ -139,6 +141,7 @@ struct so_ctx {
     size_t h_pinned_cap = 0;
 
     so_stats stats = {};
+    so_stats stats_aln = {};                  // written by the alignment side only; merged by merge_align_stats
     so::HostProfile prof;
     std::vector<so::PackedCands> cand_pool;   // one pinned buffer per chunk, reused across query blocks
 };
@@ -151,5 +154,6 @@ int build_chunk_index(so_ctx *c, ChunkIndex &ix);
 void free_chunk_index(ChunkIndex &ix);
 int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out);
 int ensure_pinned(so_ctx *c, size_t bytes);
+void merge_align_stats(so_ctx *c);
 int classify_residues(so_ctx *c, const uint8_t *d_in, uint8_t *d_out, size_t n);
 }  // namespace so
