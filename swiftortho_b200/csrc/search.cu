@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256) k_expand(const uint32_t *__restrict__ slo
                 key = hi | ((uint64_t)e.x << (g.diag_bits + g.qst_bits)) | ((uint64_t)diag << g.qst_bits) | (uint64_t)qst;
             }
             keys[out0 + k] = key;
-            vals[out0 + k] = out0 + k;
+            if (vals) vals[out0 + k] = out0 + k;
         }
     }
 }
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(256) k_group_ungap(const uint64_t *__restrict_
                     lo = max(0, diag);            // first seed: 0 < q and 0 < s
                     hi = min(ql, tl + diag);      // q < ql and s < tl
                     total = 0;
-                    rank_min = vals[e];
+                    rank_min = vals ? vals[e] : 0u;
                     prev_q = (int)(key & qmask);
                     Q = max(prev_q, lo);          // off = max(qlo - Q, slo - S, 0)
                     qq = Q, score = 0, mx = 0, mx_qed = Q, dir = 1;
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(256) k_group_ungap(const uint64_t *__restrict_
                     if (e >= n) break;
                     const uint64_t k2 = keys[e];
                     if ((k2 >> g.qst_bits) != grp) break;
-                    rank_min = min(rank_min, vals[e]);
+                    if (vals) rank_min = min(rank_min, vals[e]);
                     const int qst = (int)(k2 & qmask);
                     if (qst == prev_q) continue;  // same point again (other pattern / alphabet): lis() drops it
                     prev_q = qst;
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(256) k_group_ungap(const uint64_t *__restrict_
                     stopped = false;
                 } else {
                     gscore[gi] = (uint32_t)total;
-                    grank[gi] = rank_min;
+                    if (vals) grank[gi] = rank_min;
                     has = false;
                 }
             }
@@ -566,10 +566,38 @@ __global__ void __launch_bounds__(256) k_group_ungap(const uint64_t *__restrict_
 
 // one thread per diagonal group; the first group of a (query, target) pair folds the pair:
 // threshold 25, best diagonal (first appearance wins ties), candidate order = first passing rank
+// Keys-only path (one pattern, one alphabet): the hit ordinal is not carried through the sort.  The
+// sort is stable and hits are generated in ordinal order, so the first hit of a group has the group's
+// smallest ordinal; it is recomputed here, only for groups that pass the threshold, as
+// slot_out[slot(query, qst)] + position of the locus entry (target, sst) inside the seed's bucket range
+// (bucket entries are in descending locus order = descending (sequence, position)).
+struct RankCtx {
+    const uint32_t *slot_off, *slot_st, *slot_cnt;
+    const uint64_t *slot_out;
+    const uint2 *hdsst;
+};
+
+__device__ __forceinline__ uint32_t recompute_rank(const RankCtx &rc, int qi, int qst, uint32_t hd1, uint32_t sst) {
+    const uint32_t slot = rc.slot_off[qi] + (uint32_t)qst;
+    const uint32_t st = rc.slot_st[slot];
+    uint32_t lo = 0, hi = rc.slot_cnt[slot];  // first entry <= (hd1, sst) in a descending list
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint2 e = rc.hdsst[st + mid];
+        const bool greater = e.x > hd1 || (e.x == hd1 && e.y > sst);
+        if (greater)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return (uint32_t)rc.slot_out[slot] + lo;
+}
+
 __global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gheads,
                                                      uint32_t G, BlockGeom g, const uint32_t *__restrict__ gscore,
-                                                     const uint32_t *__restrict__ grank, uint64_t *__restrict__ ckeys,
-                                                     uint64_t *__restrict__ cvals, unsigned long long *__restrict__ counters) {
+                                                     const uint32_t *__restrict__ grank, RankCtx rctx,
+                                                     uint64_t *__restrict__ ckeys, uint64_t *__restrict__ cvals,
+                                                     unsigned long long *__restrict__ counters) {
     const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
     const int pair_shift = g.qst_bits + g.diag_bits;
     const uint64_t dmask = (1ull << g.diag_bits) - 1;
@@ -587,7 +615,15 @@ __global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict_
             if ((kk >> pair_shift) != pair) break;
             const int sc = (int)gscore[k];
             if (sc >= 25) {  // self.min (fsearch.py:2224, 2707)
-                const uint32_t rk = grank[k];
+                uint32_t rk;
+                if (grank)
+                    rk = grank[k];
+                else {
+                    const int dg = (int)((kk >> g.qst_bits) & dmask) - g.diag_bias;
+                    const int qst = (int)(kk & ((1ull << g.qst_bits) - 1));
+                    rk = recompute_rank(rctx, (int)(pair >> g.hd_bits), qst, (uint32_t)(pair & ((1ull << g.hd_bits) - 1)),
+                                        (uint32_t)(qst - dg));
+                }
                 first_rank = min(first_rank, rk);
                 if (sc > best_score || (sc == best_score && rk < best_rank)) {
                     best_score = sc;
@@ -764,10 +800,15 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
         if (H > 0) {
             if ((rc = c->scratch[SC_KA].reserve((size_t)H * 8)) != SO_OK) return rc;
             if ((rc = c->scratch[SC_KB].reserve((size_t)H * 8)) != SO_OK) return rc;
-            if ((rc = c->scratch[SC_VA].reserve((size_t)H * 4)) != SO_OK) return rc;
-            if ((rc = c->scratch[SC_VB].reserve((size_t)H * 4)) != SO_OK) return rc;
+            // one pattern + one alphabet: keys-only sort that skips the qst bits (see RankCtx)
+            const bool keys_only = AS == 1 && !getenv("SO_FORCE_PAIRS");
+            if (!keys_only) {
+                if ((rc = c->scratch[SC_VA].reserve((size_t)H * 4)) != SO_OK) return rc;
+                if ((rc = c->scratch[SC_VB].reserve((size_t)H * 4)) != SO_OK) return rc;
+            }
             uint64_t *ka = (uint64_t *)c->scratch[SC_KA].p, *kb = (uint64_t *)c->scratch[SC_KB].p;
-            uint32_t *va = (uint32_t *)c->scratch[SC_VA].p, *vb = (uint32_t *)c->scratch[SC_VB].p;
+            uint32_t *va = keys_only ? nullptr : (uint32_t *)c->scratch[SC_VA].p;
+            uint32_t *vb = keys_only ? nullptr : (uint32_t *)c->scratch[SC_VB].p;
             const int ewarps = 148 * 64;
             k_expand<<<ewarps * 32 / 256, 256, 0, st>>>(d_slot_off, g, nslots, c->d_qoff, d_st, d_cnt, d_out, ix.d_hdsst, ka,
                                                         va);
@@ -778,9 +819,15 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             cub::DoubleBuffer<uint64_t> dk(ka, kb);
             cub::DoubleBuffer<uint32_t> dv(va, vb);
             tmp = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)H, 0, end_bit, st);
-            if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
-            SO_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch[SC_TMP].p, tmp, dk, dv, (int)H, 0, end_bit, st));
+            if (keys_only) {
+                cub::DeviceRadixSort::SortKeys(nullptr, tmp, dk, (int)H, g.qst_bits, end_bit, st);
+                if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+                SO_CUDA(cub::DeviceRadixSort::SortKeys(c->scratch[SC_TMP].p, tmp, dk, (int)H, g.qst_bits, end_bit, st));
+            } else {
+                cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)H, 0, end_bit, st);
+                if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+                SO_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch[SC_TMP].p, tmp, dk, dv, (int)H, 0, end_bit, st));
+            }
             SO_CUDA(cudaEventRecord(c->ev[2], st));
             // candidates: at most one per (query, target) pair
             const uint64_t ccap = std::min<uint64_t>(H, (uint64_t)nq * (uint64_t)(M + 1));
@@ -829,9 +876,12 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                 int per_sm = 4;
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_group_ungap, 256, 0);
                 const int ublocks = 148 * std::max(1, per_sm);
-                k_group_ungap<<<ublocks, 256, 0, st>>>(dk.Current(), dv.Current(), (uint32_t)H, d_gheads, G, g, c->d_qcls, c->d_qoff,
+                const uint32_t *d_vals = keys_only ? nullptr : dv.Current();
+                k_group_ungap<<<ublocks, 256, 0, st>>>(dk.Current(), d_vals, (uint32_t)H, d_gheads, G, g, c->d_qcls, c->d_qoff,
                                                        c->d_tcls, c->d_toff, d_gscore, d_grank, d_counter);
-                k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, G, g, d_gscore, d_grank, cka, cva, d_counter);
+                RankCtx rctx{d_slot_off, d_st, d_cnt, d_out, ix.d_hdsst};
+                k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, G, g, d_gscore, keys_only ? nullptr : d_grank,
+                                                               rctx, cka, cva, d_counter);
                 c->stats.kernel_launches += 3;
                 c->stats.lib_launches += 1;
             }
