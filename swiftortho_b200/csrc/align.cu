@@ -10,7 +10,7 @@
 //                 reference's row-major order, so "first strict maximum" (fsearch.py:1401) needs
 //                 no reduction.  max(0, I, M, D) is one DPX instruction (__vimax3_s32_relu).
 //                 BLOSUM62 lives in shared memory as a 32x32 int8 table over 5-bit residue classes.
-//                 The 2-bit trace (0 '\', 1 '-', 2 '|', 3 '*'; priority M > I > D as in
+//                 The 2-bit trace (3 '\', 2 '-', 1 '|', 0 '*'; priority M > I > D as in
 //                 fsearch.py:1404-1411) is written as one 64-bit word per row, laid out
 //                 [warp][row][lane] so a warp's store is one coalesced 256-byte line.
 //   k_traceback   one thread per alignment walks the trace from (i_max, j_max) with the reference's
@@ -55,59 +55,53 @@ struct TbOut {
     int i0, j0, al, nid, mis, gap, bad, pad;
 };
 
+// One band row.  Cell values are PACKED: P = score * 4 + code with code 3 '\' (came from M), 2 '-' (from I),
+// 1 '|' (from D), 0 '*' (none).  Taking max(0, I', M', D') over packed candidates yields the score AND the
+// reference's trace priority M > I > D (fsearch.py:1404-1411) in one DPX max3.relu: equal scores differ in
+// the low bits, a zero-score M gives 3 ('\'), all-negative gives 0 ('*').  No equality test against the max
+// result is needed (ptxas 12.9 miscompiles `B == operand` after max.s32.relu on sm_100a, tools/test_vimax.cu).
+//   S3[d]  = P | 3 of lane d in the previous row      -> M' = S3[d] + 4*sub
+//   Dc[d]  = vertical candidate of that cell: P - 4 if its code is '|' (extend, -1) else (P|3) - 46 (open, -11)
+//   Ip     = horizontal candidate of the cell to the left: P - 4 if its code is '-' else (P|3) - 45
+// Row maximum with "first column wins" = max over (P|3)*32 + (31 - d).
 template <bool EDGE>
-__device__ __forceinline__ void dp_row(int i, int len0, bool live, int c1base, const int8_t *s_tbl, int (&S)[32],
+__device__ __forceinline__ void dp_row(int i, int len0, bool live, int c1base, const int8_t *s_tbl4, int (&S3)[32],
                                        int (&Dc)[33], const uint32_t (&W)[8], uint32_t &tlo, uint32_t &thi,
-                                       int &best, int &bpos) {
-    int Ic = -11;  // left of lane 0: guard cell / column 0 -> score 0 + go
+                                       int &rowkey) {
+    int Ip = -42;  // left of lane 0: guard cell / column 0 -> score 0, not '-' -> (0 - 11) * 4 + 2
     tlo = 0;
     thi = 0;
+    rowkey = 0;
 #pragma unroll
     for (int d = 0; d < 32; d++) {
         const int c0 = (W[d >> 2] >> ((d & 3) * 8)) & 0xff;
-        const int sub = s_tbl[c1base + c0];
-        const int M = S[d] + sub;
-        const int Dv = Dc[d + 1];
-        int B = __vimax3_s32_relu(Ic, M, Dv);
-        // Trace priority M > I > D (fsearch.py:1404-1411) decided by ORDER comparisons of the three
-        // candidates.  Do NOT write `B == M` / `B == Dv`: ptxas 12.9 fuses an equality test against the
-        // result of max.s32.relu into the VIMNMX.RELU predicate output and gets it wrong on sm_100a
-        // (tools/test_vimax.cu reproduces it: 68 of 216 operand triples misclassified).
-        const bool pM = (M >= Ic) && (M >= Dv) && (M >= 0);
-        const bool pI = !pM && (Ic >= Dv) && (Ic >= 0);
-        const bool pD = !pM && !pI && (Dv >= 0);
-        int code = pM ? 0 : (pI ? 1 : (pD ? 2 : 3));
-        int nI = B + (code == 1 ? -1 : -11);
-        int nD = B + (code == 2 ? -1 : -11);
+        const int sub4 = s_tbl4[c1base + c0];
+        const int Mp = S3[d] + sub4;
+        int P = __vimax3_s32_relu(Ip, Mp, Dc[d + 1]);
         if (EDGE) {
             const bool valid = live && (unsigned)(i + d - 17) < (unsigned)len0;  // 1 <= j < l0
-            if (!valid) {
-                B = 0;
-                nI = -11;
-                nD = -11;
-                code = 3;
-            }
+            if (!valid) P = 0;  // score 0, code '*': contributes I = D = open from 0, M from 0
         }
-        if (B > best) {
-            best = B;
-            bpos = (i << 5) | d;
-        }
-        S[d] = B;
-        Dc[d] = nD;
-        Ic = nI;
+        const int t = P & 3;
+        const int P3 = P | 3;
+        const int Pm4 = P - 4;
+        Ip = (t == 2) ? Pm4 : P3 - 45;
+        Dc[d] = (t == 1) ? Pm4 : P3 - 46;
+        S3[d] = P3;
+        rowkey = max(rowkey, P3 * 32 + (31 - d));
         if (d < 16)
-            tlo |= (uint32_t)code << (2 * d);
+            tlo |= (uint32_t)t << (2 * d);
         else
-            thi |= (uint32_t)code << (2 * (d - 16));
+            thi |= (uint32_t)t << (2 * (d - 16));
     }
 }
 
 __global__ void __launch_bounds__(128) k_banded_dp(const AlnTask *__restrict__ tasks, int n,
                                                    const uint64_t *__restrict__ warp_base,
                                                    uint64_t *__restrict__ trace, DpOut *__restrict__ out) {
-    __shared__ int8_t s_tbl[kClasses * kClasses];
+    __shared__ int8_t s_tbl4[kClasses * kClasses];  // 4 * BLOSUM62 (fits int8: -16 .. 44)
     __shared__ uint8_t s_code[256];
-    for (int k = threadIdx.x; k < kClasses * kClasses; k += blockDim.x) s_tbl[k] = c_score[k];
+    for (int k = threadIdx.x; k < kClasses * kClasses; k += blockDim.x) s_tbl4[k] = (int8_t)(4 * c_score[k]);
     for (int k = threadIdx.x; k < 256; k += blockDim.x) s_code[k] = c_code[k];
     __syncthreads();
 
@@ -128,10 +122,10 @@ __global__ void __launch_bounds__(128) k_banded_dp(const AlnTask *__restrict__ t
     for (int o = 16; o > 0; o >>= 1) wrows = max(wrows, __shfl_xor_sync(0xffffffffu, wrows, o));
     uint64_t *tr = trace + warp_base[t >> 5] + lane;
 
-    int S[32], Dc[33];
+    int S3[32], Dc[33];
 #pragma unroll
-    for (int d = 0; d < 32; d++) S[d] = 0, Dc[d] = -11;  // row 0: score 0, trace '-' (never '|')
-    Dc[32] = -11;
+    for (int d = 0; d < 32; d++) S3[d] = 3, Dc[d] = -43;  // row 0: score 0, trace '-' (never '|')
+    Dc[32] = -43;  // the cell right of the band in the previous row: score 0, never '|'
     // window of s0 classes: byte d holds class(s0[i + d - 17]) for the current row i
     uint32_t W[8];
 #pragma unroll
@@ -142,17 +136,25 @@ __global__ void __launch_bounds__(128) k_banded_dp(const AlnTask *__restrict__ t
         const uint32_t cls = (idx < len0) ? s_code[tk.s0[idx]] : 0;
         W[d >> 2] |= cls << ((d & 3) * 8);
     }
-    int best = 0, bpos = 0;
+    int best3 = 3, besti = 0, bestd = 0;  // best3 = (best score) * 4 + 3
     for (int i = 1; i <= wrows; i++) {
         const bool live = i <= nrows;
         const int c1base = live ? (int)s_code[tk.s1[i - 1]] * kClasses : 0;
         uint32_t tlo, thi;
+        int rowkey;
         const bool interior = live && i >= 17 && i + 15 <= len0;
         if (__all_sync(0xffffffffu, interior))
-            dp_row<false>(i, len0, live, c1base, s_tbl, S, Dc, W, tlo, thi, best, bpos);
+            dp_row<false>(i, len0, live, c1base, s_tbl4, S3, Dc, W, tlo, thi, rowkey);
         else
-            dp_row<true>(i, len0, live, c1base, s_tbl, S, Dc, W, tlo, thi, best, bpos);
+            dp_row<true>(i, len0, live, c1base, s_tbl4, S3, Dc, W, tlo, thi, rowkey);
         if (live) tr[(size_t)(i - 1) * 32] = ((uint64_t)thi << 32) | tlo;
+        // first strict maximum in row-major order (fsearch.py:1401)
+        const int rs = rowkey >> 5;
+        if (rs > best3) {
+            best3 = rs;
+            besti = i;
+            bestd = 31 - (rowkey & 31);
+        }
         // slide the window: drop byte 0, append class(s0[i + 15]) for row i + 1
         const int nidx = i + 15;
         const uint32_t ncls = (nidx < len0) ? s_code[tk.s0[nidx]] : 0;
@@ -162,9 +164,9 @@ __global__ void __launch_bounds__(128) k_banded_dp(const AlnTask *__restrict__ t
     }
     if (active) {
         DpOut o;
-        o.score = best;
-        o.imax = best > 0 ? (bpos >> 5) : 0;
-        o.jmax = best > 0 ? ((bpos >> 5) + (bpos & 31) - 16) : 0;
+        o.score = best3 >> 2;
+        o.imax = o.score > 0 ? besti : 0;
+        o.jmax = o.score > 0 ? (besti + bestd - 16) : 0;
         o.rows = nrows;
         out[t] = o;
     }
@@ -180,15 +182,15 @@ __global__ void __launch_bounds__(128) k_traceback(const AlnTask *__restrict__ t
     const uint64_t *tr = trace + warp_base[t >> 5] + (threadIdx.x & 31);
     int i = dp[t].imax, j = dp[t].jmax;
     int al = 0, nid = 0, mis = 0, gap = 0, bad = 0;
-    int run_type = 0, run_len = 0;  // 1: trace '-', 2: trace '|'
+    int run_type = 0, run_len = 0;  // 2: trace '-', 1: trace '|'
     int cached_row = -1;
     uint64_t word = 0;
     while (i > 0 || j > 0) {
         int code;
         if (i == 0)
-            code = 1;  // row 0 holds '-' (fsearch.py:1379-1382)
+            code = 2;  // row 0 holds '-' (fsearch.py:1379-1382)
         else if (j == 0)
-            code = 2;  // column 0 holds '|' (fsearch.py:1383-1386)
+            code = 1;  // column 0 holds '|' (fsearch.py:1383-1386)
         else {
             const int d = j - i + 16;
             if (d < 0 || d > 31) {
@@ -201,9 +203,9 @@ __global__ void __launch_bounds__(128) k_traceback(const AlnTask *__restrict__ t
             }
             code = (int)((word >> (2 * d)) & 3);
         }
-        if (code == 3) break;
+        if (code == 0) break;
         al++;
-        if (code == 0) {
+        if (code == 3) {
             if (tk.s0[j - 1] == tk.s1[i - 1])
                 nid++;
             else
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(128) k_traceback(const AlnTask *__restrict__ t
                 run_type = code;
             }
             run_len++;
-            if (code == 1)
+            if (code == 2)
                 j--;
             else
                 i--;
