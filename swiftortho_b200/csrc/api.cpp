@@ -73,6 +73,7 @@ static int check_offsets(const uint64_t *off, i64 n, uint32_t &maxlen, const cha
 struct QueryState {
     std::vector<uint64_t> order;  // candidates in the reference's sorted order (prefix of length `limit`);
                                   // low 32 bits = index into the chunk-major concatenation of the candidates
+    i64 qord = 0;                 // global query ordinal
     i64 limit = 0;                // min(vmax, len(hits))
     i64 next = 0;                 // next candidate (in sorted order) to align
     double mmiss = 0;
@@ -430,7 +431,12 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     so_stats wstats;
     memset(&wstats, 0, sizeof wstats);
 
-    auto post_block = [&](i64 b0, i64 b1, int slot, const std::function<void()> &release_slot) -> int {
+    // queries whose candidates are selected but not aligned yet: alignment rounds run over several blocks
+    // at once so one launch carries enough alignments to fill the GPU
+    std::vector<QueryState> pending;
+    const size_t kAlignBatch = 2048;
+
+    auto order_block = [&](i64 b0, i64 b1, int slot, const std::function<void()> &release_slot) -> int {
         const i64 nq = b1 - b0;
         std::vector<QueryState> qs((size_t)nq);
         // candidate `idx` of query k in the chunk-major concatenation (fsearch.py:3043-3049)
@@ -447,6 +453,7 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
         Timer th;
         so::parallel_for(nq, [&](i64 k) {
             QueryState &s = qs[(size_t)k];
+            s.qord = b0 + k;
             i64 n = 0;
             for (size_t ch = 0; ch < nch; ch++) n += (i64)(c->cand_pool[(size_t)slot * nch + ch].offsets[(size_t)k + 1] - c->cand_pool[(size_t)slot * nch + ch].offsets[(size_t)k]);
             s.order.resize((size_t)n);
@@ -473,6 +480,15 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
         wstats.ms_host += th.ms();
         c->prof.order_ms += th.ms();
         release_slot();  // the packed candidates of this block are no longer needed
+        for (auto &q : qs) pending.push_back(std::move(q));
+        return SO_OK;
+    };
+
+    auto align_pending = [&]() -> int {
+        std::vector<QueryState> qs;
+        qs.swap(pending);
+        const i64 nq = (i64)qs.size();
+        if (nq == 0) return SO_OK;
         // alignment rounds: the stop rule (fsearch.py:3103) is sequential per query, so each round
         // aligns the next kRound candidates of every unfinished query and the host replays the rule
         Timer trd;
@@ -491,7 +507,7 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             for (i64 k = 0; k < nq; k++) {
                 QueryState &s = qs[(size_t)k];
                 if (s.done) continue;
-                const i64 qi_ord = b0 + k;
+                const i64 qi_ord = s.qord;
                 const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
                 const i64 hi = std::min<i64>(s.limit, s.next + kRound);
                 for (i64 h = s.next; h < hi; h++) {
@@ -535,7 +551,7 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             while (r < reqs.size()) {
                 const int k = reqs[r].q;
                 QueryState &s = qs[(size_t)k];
-                const i64 qi_ord = b0 + k;
+                const i64 qi_ord = s.qord;
                 const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
                 for (; r < reqs.size() && reqs[r].q == k; r++) {
                     if (s.done) continue;
@@ -610,7 +626,7 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return !jobs.empty() || producer_done; });
-                if (jobs.empty()) return;
+                if (jobs.empty()) break;
                 j = jobs.front();
                 jobs.pop_front();
             }
@@ -622,13 +638,26 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 slot_busy[j.slot] = false;
                 cv.notify_all();
             };
-            int rc = worker_rc == SO_OK ? post_block(j.b0, j.b1, j.slot, release) : SO_OK;
+            int rc = worker_rc == SO_OK ? order_block(j.b0, j.b1, j.slot, release) : SO_OK;
+            bool last;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                last = jobs.empty() && producer_done;
+            }
+            if (rc == SO_OK && worker_rc == SO_OK && (pending.size() >= kAlignBatch || last)) rc = align_pending();
             if (rc != SO_OK && worker_rc == SO_OK) {
                 std::lock_guard<std::mutex> lk(mu);
                 worker_rc = rc;
                 worker_err = so::get_error();
             }
             release();
+        }
+        if (worker_rc == SO_OK && !pending.empty()) {
+            int rc = align_pending();
+            if (rc != SO_OK) {
+                worker_rc = rc;
+                worker_err = so::get_error();
+            }
         }
     });
     int prod_rc = SO_OK;
