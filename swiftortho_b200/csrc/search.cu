@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(256) k_scatter_heads(const uint64_t *__restric
     if (p == 0 || (keys[p - 1] >> shift) != (k >> shift)) gheads[gidx[p]] = p;
 }
 
-__global__ void __launch_bounds__(256) k_group_ungap(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+__global__ void __launch_bounds__(256) k_group_ungap_generic(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                      uint32_t n, const uint32_t *__restrict__ gheads, uint32_t G, BlockGeom g,
                                                      const uint8_t *__restrict__ qcls, const uint64_t *__restrict__ qoff,
                                                      const uint8_t *__restrict__ tcls, const uint64_t *__restrict__ toff,
@@ -566,6 +566,162 @@ __global__ void __launch_bounds__(256) k_group_ungap(const uint64_t *__restrict_
 
 // one thread per diagonal group; the first group of a (query, target) pair folds the pair:
 // threshold 25, best diagonal (first appearance wins ties), candidate order = first passing rank
+// Fast variant for sequences shorter than 8192 residues.  The running score and the step counter are
+// one packed register v = (score << 13) + p, p = 8191 - (steps taken); the score table holds
+// (sub << 13) - 1, so one add advances both.  max(mxk, v) keeps the maximum AND the first step that
+// reached it (equal scores: the earlier step has the larger p), the X-drop test
+// score + 30 < max is ((v | 8191) + (30 << 13)) < mxk, and the number of scored residue pairs of a
+// phase is 8191 - (v & 8191).  Positions are 32-bit indices into the packed class buffers.
+__global__ void __launch_bounds__(256) k_group_ungap(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                     uint32_t n, const uint32_t *__restrict__ gheads, uint32_t G, BlockGeom g,
+                                                     const uint8_t *__restrict__ qcls, const uint64_t *__restrict__ qoff,
+                                                     const uint8_t *__restrict__ tcls, const uint64_t *__restrict__ toff,
+                                                     uint32_t *__restrict__ gscore, uint32_t *__restrict__ grank,
+                                                     unsigned long long *__restrict__ counters) {
+    __shared__ int s_tblv[kClasses * kClasses];
+    for (int k = threadIdx.x; k < kClasses * kClasses; k += blockDim.x) s_tblv[k] = ((int)c_score2[k] << 13) - 1;
+    __syncthreads();
+    // Bases kept in registers as opaque values: otherwise ptxas re-loads the kernel parameters and
+    // re-derives the shared window address inside every extension step (8 of 25 instructions).
+    uint64_t qcls64 = (uint64_t)qcls, tcls64 = (uint64_t)tcls;
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_tblv);
+    asm volatile("" : "+l"(qcls64), "+l"(tcls64), "+r"(sbase));
+    const int lane = threadIdx.x & 31;
+    const uint64_t qmask = (1ull << g.qst_bits) - 1, dmask = (1ull << g.diag_bits) - 1;
+    const int pair_shift = g.qst_bits + g.diag_bits;
+    constexpr int U = 8;                      // extension steps per loop iteration
+    constexpr int PMAX = 8191, DROP = 30 << 13;
+    const unsigned long long kBatch = 256;    // group indices taken per atomic
+    bool has = false, fin = false;
+    bool alive = false;                       // the current extension is still running
+    uint32_t gi = 0, e = 0, rank_min = 0;
+    uint64_t grp = 0;
+    uint32_t qbase = 0, dlt = 0;              // target residue facing qcls[iq] is tcls[iq + dlt]
+    int lo = 0, hi = 0, total = 0, prev_q = -1, Q = 0, dir = 1;
+    uint32_t iq = 0, lo1 = 0, span = 0;       // in range  <=>  (iq - lo1) < span  (lo1 = qbase+lo+1, span = hi-lo-1)
+    int v = 0, mxk = 0;
+    uint32_t mx_qed = 0;                      // iq of the right extension's maximum
+    unsigned int steps = 0;
+    uint32_t pool_next = 0, pool_end = 0;     // warp-uniform
+    bool exhausted = false;                   // warp-uniform
+    for (;;) {
+        // ---- (1) lanes without a group take the next one (a warp draws kBatch indices per atomic)
+        const unsigned need = __ballot_sync(0xffffffffu, !has && !fin);
+        if (need) {
+            if (pool_next == pool_end && !exhausted) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(counters + 2, kBatch);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= G)
+                    exhausted = true;
+                else {
+                    pool_next = (uint32_t)base;
+                    pool_end = (uint32_t)min((unsigned long long)G, base + kBatch);
+                }
+            }
+            if (!has && !fin) {
+                const uint32_t mine = pool_next + __popc(need & ((1u << lane) - 1));
+                if (mine < pool_end) {
+                    gi = mine;
+                    e = gheads[gi];
+                    const uint64_t key = keys[e];
+                    grp = key >> g.qst_bits;
+                    const int diag = (int)(grp & dmask) - g.diag_bias;
+                    const uint64_t pair = key >> pair_shift;
+                    const int hd1 = (int)(pair & ((1ull << g.hd_bits) - 1));
+                    const int qi = (int)(pair >> g.hd_bits);
+                    const uint64_t qb = qoff[g.qb0 + qi];
+                    const int ql = (int)(qoff[g.qb0 + qi + 1] - qb);
+                    const int tid = g.c0 + hd1 - 1;
+                    const uint64_t tb = toff[tid];
+                    const int tl = (int)(toff[tid + 1] - tb);
+                    qbase = (uint32_t)qb;
+                    dlt = (uint32_t)tb - (uint32_t)diag - qbase;
+                    lo = max(0, diag);            // first seed: 0 < q and 0 < s
+                    hi = min(ql, tl + diag);      // q < ql and s < tl
+                    total = 0;
+                    rank_min = vals ? vals[e] : 0u;
+                    prev_q = (int)(key & qmask);
+                    Q = max(prev_q, lo);          // off = max(qlo - Q, slo - S, 0)
+                    iq = qbase + (uint32_t)Q;
+                    lo1 = qbase + (uint32_t)lo + 1u;
+                    span = hi > lo + 1 ? (uint32_t)(hi - lo - 1) : 0u;
+                    v = PMAX, mxk = PMAX, dir = 1;  // score 0, no step taken
+                    alive = true;
+                    has = true;
+                } else if (exhausted)
+                    fin = true;  // otherwise the pool is refilled in the next iteration
+            }
+            pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
+        }
+        if (__all_sync(0xffffffffu, fin)) break;
+        // ---- (2) U extension steps; right (dir = +1) and left (dir = -1) extensions share the body
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool in = alive && (iq - lo1) < span;
+            int tv = 0;
+            if (in) {
+                uint64_t aq, at;
+                uint32_t cq, ct;
+                asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(aq) : "r"(iq), "l"(qcls64));
+                asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(at) : "r"(iq + dlt), "l"(tcls64));
+                asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(cq) : "l"(aq));
+                asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(ct) : "l"(at));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tv) : "r"(sbase + ((cq << 5 | ct) << 2)));
+            }
+            v += tv;
+            mxk = max(mxk, v);
+            alive = in && ((v | PMAX) + DROP >= mxk);
+            iq += (uint32_t)dir;
+        }
+        // ---- (3) transitions of the lanes whose extension ended
+        if (has && !alive) {
+            steps += (unsigned)(PMAX - (v & PMAX));
+            if (dir > 0) {  // right done -> left from (Q-1, S-1), continuing the right maximum
+                const int k = PMAX - (mxk & PMAX);           // 1-based step that reached the maximum (0: none)
+                mx_qed = qbase + (uint32_t)Q + (uint32_t)max(k, 1) - 1u;
+                v = (mxk | PMAX);                            // score = right maximum, fresh step counter
+                mxk = v;
+                dir = -1;
+                iq = qbase + (uint32_t)Q - 1u;
+                alive = true;
+            } else {        // seed done
+                total += mxk >> 13;
+                lo = (int)(mx_qed - qbase);  // next seed: qlo = max_qed, slo = max_sed (same diagonal)
+                bool more = false;
+                for (;;) {
+                    e++;
+                    if (e >= n) break;
+                    const uint64_t k2 = keys[e];
+                    if ((k2 >> g.qst_bits) != grp) break;
+                    if (vals) rank_min = min(rank_min, vals[e]);
+                    const int qst = (int)(k2 & qmask);
+                    if (qst == prev_q) continue;  // same point again (other pattern / alphabet): lis() drops it
+                    prev_q = qst;
+                    more = true;
+                    break;
+                }
+                if (more) {
+                    Q = max(prev_q, lo);
+                    iq = qbase + (uint32_t)Q;
+                    lo1 = qbase + (uint32_t)lo + 1u;
+                    span = hi > lo + 1 ? (uint32_t)(hi - lo - 1) : 0u;
+                    v = PMAX, mxk = PMAX, dir = 1;
+                    alive = true;
+                } else {
+                    gscore[gi] = (uint32_t)total;
+                    if (vals) grank[gi] = rank_min;
+                    has = false;
+                }
+            }
+        }
+    }
+    unsigned long long st64 = steps;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) st64 += __shfl_xor_sync(0xffffffffu, st64, o);
+    if (lane == 0 && st64) atomicAdd(counters + 1, st64);
+}
+
 // Keys-only path (one pattern, one alphabet): the hit ordinal is not carried through the sort.  The
 // sort is stable and hits are generated in ordinal order, so the first hit of a group has the group's
 // smallest ordinal; it is recomputed here, only for groups that pass the threshold, as
@@ -873,12 +1029,22 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             uint32_t *d_grank = (uint32_t *)c->scratch[SC_GRANK].p;
             if (G > 0) {
                 k_scatter_heads<<<(uint32_t)((H + 255) / 256), 256, 0, st>>>(dk.Current(), (uint32_t)H, grp_shift, d_gidx, d_gheads);
+                // packed fast variant needs < 8192 steps per extension and 32-bit residue indices
+                const bool fast_ungap = maxql < 8192 && ix.max_tlen < 8192 && c->q_off[(size_t)c->n_q] < 0xfff00000ull &&
+                                        c->t_off[(size_t)c->n_t] < 0xfff00000ull && !getenv("SO_GENERIC_UNGAP");
                 int per_sm = 4;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_group_ungap, 256, 0);
+                if (fast_ungap)
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_group_ungap, 256, 0);
+                else
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_group_ungap_generic, 256, 0);
                 const int ublocks = 148 * std::max(1, per_sm);
                 const uint32_t *d_vals = keys_only ? nullptr : dv.Current();
-                k_group_ungap<<<ublocks, 256, 0, st>>>(dk.Current(), d_vals, (uint32_t)H, d_gheads, G, g, c->d_qcls, c->d_qoff,
-                                                       c->d_tcls, c->d_toff, d_gscore, d_grank, d_counter);
+                if (fast_ungap)
+                    k_group_ungap<<<ublocks, 256, 0, st>>>(dk.Current(), d_vals, (uint32_t)H, d_gheads, G, g, c->d_qcls, c->d_qoff,
+                                                           c->d_tcls, c->d_toff, d_gscore, d_grank, d_counter);
+                else
+                    k_group_ungap_generic<<<ublocks, 256, 0, st>>>(dk.Current(), d_vals, (uint32_t)H, d_gheads, G, g, c->d_qcls,
+                                                                   c->d_qoff, c->d_tcls, c->d_toff, d_gscore, d_grank, d_counter);
                 RankCtx rctx{d_slot_off, d_st, d_cnt, d_out, ix.d_hdsst};
                 k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, G, g, d_gscore, keys_only ? nullptr : d_grank,
                                                                rctx, cka, cva, d_counter);
