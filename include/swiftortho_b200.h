@@ -181,6 +181,8 @@ typedef struct so_stats {
     int64_t lib_launches;    /* CUB (library) launches                 */
     double ms_seed, ms_sort, ms_ungap, ms_select, ms_align, ms_dp, ms_traceback, ms_host, ms_total;
     int64_t h2d_bytes, d2h_bytes;
+    double ms_ungap_kernel;  /* X-drop kernels alone (k_single_ungap + k_group_ungap), inside ms_ungap */
+    int64_t multi_groups;    /* diagonal groups holding more than one seed (chained path)            */
 } so_stats;
 int so_stats_get(const so_ctx *c, so_stats *s);
 int so_stats_reset(so_ctx *c);

@@ -53,7 +53,8 @@ class so_stats(C.Structure):
                                          'rows', 'ungap_steps', 'kernel_launches', 'lib_launches')] + \
                [(n, C.c_double) for n in ('ms_seed', 'ms_sort', 'ms_ungap', 'ms_select', 'ms_align', 'ms_dp',
                                           'ms_traceback', 'ms_host', 'ms_total')] + \
-               [('h2d_bytes', C.c_int64), ('d2h_bytes', C.c_int64)]
+               [('h2d_bytes', C.c_int64), ('d2h_bytes', C.c_int64), ('ms_ungap_kernel', C.c_double),
+                ('multi_groups', C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

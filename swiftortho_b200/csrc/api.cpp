@@ -180,6 +180,7 @@ void so_ctx_destroy(so_ctx *c) {
     if (c->d_perm) cudaFree(c->d_perm);
     if (c->d_tcls) cudaFree(c->d_tcls);
     if (c->d_qcls) cudaFree(c->d_qcls);
+    if (c->d_tung) cudaFree(c->d_tung);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &pc : c->cand_pool) pc.release();
     for (auto &e : c->ev)
@@ -220,6 +221,7 @@ int so_set_targets(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, 
     SO_CUDA(cudaMemcpyAsync(c->d_toff, c->t_off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     SO_CUDA(cudaMalloc((void **)&c->d_tcls, bytes + 64));
     if ((rc = so::classify_residues(c, c->d_tres, c->d_tcls, bytes)) != SO_OK) return rc;
+    if ((rc = so::build_ungap_targets(c)) != SO_OK) return rc;
     SO_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.h2d_bytes += (i64)bytes + ((i64)n + 1) * 8;
     return SO_OK;

@@ -127,6 +127,10 @@ struct so_ctx {
     const uint8_t *t_host = nullptr;          // caller-owned (valid during so_set_targets only)
     uint8_t *d_tres = nullptr, *d_qres = nullptr;
     uint8_t *d_tcls = nullptr, *d_qcls = nullptr;  // 5-bit BLOSUM62 residue classes of the same buffers
+    // X-drop view of the targets (search.cu, k_single_ungap): classes with position 0 of every
+    // sequence replaced by a terminator, forward copy at tung_off[0] and reversed copy at tung_off[1]
+    uint8_t *d_tung = nullptr;
+    uint32_t tung_off[2] = {0, 0};
     uint64_t *d_toff = nullptr, *d_qoff = nullptr;
     uint32_t *d_perm = nullptr;               // per query: positions in the reference quicksort order of -kscs (S3)
     so::i64 sub_block = 0;                    // >0: fixed number of queries per seeding sub-block (tests)
@@ -135,7 +139,7 @@ struct so_ctx {
     std::vector<so::ChunkIndex> chunks;
 
     // scratch (grown on demand, reused)
-    so::DBuf<uint8_t> scratch[32];
+    so::DBuf<uint8_t> scratch[40];
     so::DBuf<uint64_t> trace;
     void *h_pinned = nullptr;
     size_t h_pinned_cap = 0;
@@ -156,4 +160,5 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
 int ensure_pinned(so_ctx *c, size_t bytes);
 void merge_align_stats(so_ctx *c);
 int classify_residues(so_ctx *c, const uint8_t *d_in, uint8_t *d_out, size_t n);
+int build_ungap_targets(so_ctx *c);
 }  // namespace so

@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) k_group_ungap_generic(const uint64_t *__r
         if (need) {
             if (pool_next == pool_end && !exhausted) {
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(counters + 2, kBatch);
+                if (lane == 0) base = atomicAdd(counters + 4, kBatch);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (base >= G)
                     exhausted = true;
@@ -564,157 +564,350 @@ __global__ void __launch_bounds__(256) k_group_ungap_generic(const uint64_t *__r
     if (lane == 0 && steps) atomicAdd(counters + 1, steps);
 }
 
-// one thread per diagonal group; the first group of a (query, target) pair folds the pair:
-// threshold 25, best diagonal (first appearance wins ties), candidate order = first passing rank
-// Fast variant for sequences shorter than 8192 residues.  The running score and the step counter are
-// one packed register v = (score << 13) + p, p = 8191 - (steps taken); the score table holds
-// (sub << 13) - 1, so one add advances both.  max(mxk, v) keeps the maximum AND the first step that
-// reached it (equal scores: the earlier step has the larger p), the X-drop test
-// score + 30 < max is ((v | 8191) + (30 << 13)) < mxk, and the number of scored residue pairs of a
-// phase is 8191 - (v & 8191).  Positions are 32-bit indices into the packed class buffers.
-__global__ void __launch_bounds__(256) k_group_ungap(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                                     uint32_t n, const uint32_t *__restrict__ gheads, uint32_t G, BlockGeom g,
-                                                     const uint8_t *__restrict__ qcls, const uint64_t *__restrict__ qoff,
-                                                     const uint8_t *__restrict__ tcls, const uint64_t *__restrict__ toff,
-                                                     uint32_t *__restrict__ gscore, uint32_t *__restrict__ grank,
-                                                     unsigned long long *__restrict__ counters) {
-    __shared__ int s_tblv[kClasses * kClasses];
-    for (int k = threadIdx.x; k < kClasses * kClasses; k += blockDim.x) s_tblv[k] = ((int)c_score2[k] << 13) - 1;
-    __syncthreads();
-    // Bases kept in registers as opaque values: otherwise ptxas re-loads the kernel parameters and
-    // re-derives the shared window address inside every extension step (8 of 25 instructions).
-    uint64_t qcls64 = (uint64_t)qcls, tcls64 = (uint64_t)tcls;
-    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_tblv);
-    asm volatile("" : "+l"(qcls64), "+l"(tcls64), "+r"(sbase));
-    const int lane = threadIdx.x & 31;
-    const uint64_t qmask = (1ull << g.qst_bits) - 1, dmask = (1ull << g.diag_bits) - 1;
-    const int pair_shift = g.qst_bits + g.diag_bits;
-    constexpr int U = 8;                      // extension steps per loop iteration
-    constexpr int PMAX = 8191, DROP = 30 << 13;
-    const unsigned long long kBatch = 256;    // group indices taken per atomic
-    bool has = false, fin = false;
-    bool alive = false;                       // the current extension is still running
-    uint32_t gi = 0, e = 0, rank_min = 0;
-    uint64_t grp = 0;
-    uint32_t qbase = 0, dlt = 0;              // target residue facing qcls[iq] is tcls[iq + dlt]
-    int lo = 0, hi = 0, total = 0, prev_q = -1, Q = 0, dir = 1;
-    uint32_t iq = 0, lo1 = 0, span = 0;       // in range  <=>  (iq - lo1) < span  (lo1 = qbase+lo+1, span = hi-lo-1)
-    int v = 0, mxk = 0;
-    uint32_t mx_qed = 0;                      // iq of the right extension's maximum
-    unsigned int steps = 0;
-    uint32_t pool_next = 0, pool_end = 0;     // warp-uniform
-    bool exhausted = false;                   // warp-uniform
-    for (;;) {
-        // ---- (1) lanes without a group take the next one (a warp draws kBatch indices per atomic)
-        const unsigned need = __ballot_sync(0xffffffffu, !has && !fin);
-        if (need) {
-            if (pool_next == pool_end && !exhausted) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(counters + 2, kBatch);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= G)
-                    exhausted = true;
-                else {
-                    pool_next = (uint32_t)base;
-                    pool_end = (uint32_t)min((unsigned long long)G, base + kBatch);
-                }
-            }
-            if (!has && !fin) {
-                const uint32_t mine = pool_next + __popc(need & ((1u << lane) - 1));
-                if (mine < pool_end) {
-                    gi = mine;
-                    e = gheads[gi];
-                    const uint64_t key = keys[e];
-                    grp = key >> g.qst_bits;
-                    const int diag = (int)(grp & dmask) - g.diag_bias;
-                    const uint64_t pair = key >> pair_shift;
-                    const int hd1 = (int)(pair & ((1ull << g.hd_bits) - 1));
-                    const int qi = (int)(pair >> g.hd_bits);
-                    const uint64_t qb = qoff[g.qb0 + qi];
-                    const int ql = (int)(qoff[g.qb0 + qi + 1] - qb);
-                    const int tid = g.c0 + hd1 - 1;
-                    const uint64_t tb = toff[tid];
-                    const int tl = (int)(toff[tid + 1] - tb);
-                    qbase = (uint32_t)qb;
-                    dlt = (uint32_t)tb - (uint32_t)diag - qbase;
-                    lo = max(0, diag);            // first seed: 0 < q and 0 < s
-                    hi = min(ql, tl + diag);      // q < ql and s < tl
-                    total = 0;
-                    rank_min = vals ? vals[e] : 0u;
-                    prev_q = (int)(key & qmask);
-                    Q = max(prev_q, lo);          // off = max(qlo - Q, slo - S, 0)
-                    iq = qbase + (uint32_t)Q;
-                    lo1 = qbase + (uint32_t)lo + 1u;
-                    span = hi > lo + 1 ? (uint32_t)(hi - lo - 1) : 0u;
-                    v = PMAX, mxk = PMAX, dir = 1;  // score 0, no step taken
-                    alive = true;
-                    has = true;
-                } else if (exhausted)
-                    fin = true;  // otherwise the pool is refilled in the next iteration
-            }
-            pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
+// ---------------------------------------------------------------------------------------------
+// Single-seed diagonal groups (the bulk: ~95 % of the groups are one random seed hit).
+//
+// A single seed needs one right extension from (Q, S) and one left extension from (Q-1, S-1) that
+// continues the right maximum (fsearch.py:2454-2494); the group score is the sum of the two gains,
+// so the two phases are independent.  k_single_ungap runs them lane-serially:
+//   * X-drop views of the sequences: residue classes with position 0 of every sequence replaced by
+//     a terminator class (the reference never scores index 0 of either sequence and stops at
+//     either end: `0 < q < ql and 0 < s < tl`), stored forward and reversed, so a left extension is
+//     a forward walk over the reversed copies and no range arithmetic is left in the loop.
+//   * 16 residues per lane per load (LDG.128, 16-byte aligned target chunk; leading bytes before the
+//     start are rewritten to a "skip" class that scores 0 and is not counted); the matching 16 query
+//     bytes are muxed out of two aligned chunks (the query side is shared by the lanes of a warp, so
+//     its lines stay in L1).
+//   * score table in shared memory, one private copy per LANE ([26 x 32 entries][32 lanes] int32):
+//     random lookups are bank-conflict free.
+//   * state per phase is two registers: v = S*8192 - n (S running score, n steps) and
+//     d = (max - S)*8192 + (steps since the max).  Table entries are 1 - s*8192, so a step is
+//     v -= e; d = max(d + e, 0); alive = d < 31*8192   (X-drop: S + 30 < max),
+//     and the phase gain is (v + d + 8191) >> 13, the step count (-v) & 8191.  The terminator entry
+//     is 2^29 (drops at once, leaves v + d and the count unchanged).
+// Lanes are refilled in batches: the service block (result write, next group, phase switch, first
+// loads) runs only when kRefill or more lanes are idle.  Requires sequences < 8192 residues.
+// ---------------------------------------------------------------------------------------------
+enum { kUngPad = 64, kUngStop = 24, kUngSkip = 25, kUngRows = 26, kUngTabBytes = kUngRows * 32 * 32 * 4 };
+static const uint32_t kDescSingle = 1u << 24, kDescNoLeft = 1u << 25;
+
+__global__ void __launch_bounds__(256) k_ung_fill(const uint8_t *__restrict__ cls, uint32_t n, uint8_t *__restrict__ dst,
+                                                  uint32_t offF, uint32_t offR, uint32_t total, int shift) {
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= total) return;
+    uint32_t v = kUngStop;
+    if (pos >= offF && pos - offF < n)
+        v = cls[pos - offF];
+    else if (pos >= offR && pos - offR < n)
+        v = cls[n - 1 - (pos - offR)];
+    dst[pos] = (uint8_t)(v << shift);
+}
+
+__global__ void __launch_bounds__(256) k_ung_marks(const uint64_t *__restrict__ off, uint32_t nseq, uint64_t base,
+                                                   uint32_t n, uint8_t *__restrict__ dst, uint32_t offF, uint32_t offR,
+                                                   int shift) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseq) return;
+    const uint64_t x = off[i] - base;
+    if (x >= n) return;
+    dst[offF + (uint32_t)x] = (uint8_t)(kUngStop << shift);
+    dst[offR + (n - 1 - (uint32_t)x)] = (uint8_t)(kUngStop << shift);
+}
+
+static void ung_layout(uint32_t n, uint32_t off[2], uint32_t &total) {
+    const uint32_t r = (n + 15u) & ~15u;
+    off[0] = kUngPad;
+    off[1] = kUngPad + r + kUngPad;
+    total = off[1] + r + kUngPad;
+}
+
+static int ung_build(so_ctx *c, const uint8_t *d_cls, const uint64_t *d_off, uint32_t nseq, uint64_t base, uint32_t n,
+                     uint8_t *dst, const uint32_t off[2], uint32_t total, int shift) {
+    k_ung_fill<<<(total + 255) / 256, 256, 0, c->stream>>>(d_cls, n, dst, off[0], off[1], total, shift);
+    if (nseq) k_ung_marks<<<(nseq + 255) / 256, 256, 0, c->stream>>>(d_off, nseq, base, n, dst, off[0], off[1], shift);
+    SO_CUDA(cudaGetLastError());
+    c->stats.kernel_launches += 2;
+    return SO_OK;
+}
+
+int build_ungap_targets(so_ctx *c) {
+    if (c->d_tung) cudaFree(c->d_tung);
+    c->d_tung = nullptr;
+    const uint64_t R = c->t_off[(size_t)c->n_t];
+    if (R == 0 || R >= 0x7fffff00ull) return SO_OK;  // chained kernels handle everything
+    uint32_t total;
+    ung_layout((uint32_t)R, c->tung_off, total);
+    SO_CUDA(cudaMalloc((void **)&c->d_tung, total));
+    return ung_build(c, c->d_tcls, c->d_toff, (uint32_t)c->n_t, 0, (uint32_t)R, c->d_tung, c->tung_off, total, 0);
+}
+
+// one thread per sorted hit: group heads, the X-drop descriptor of the group (global target residue
+// index of the seed, query residue index inside the sub-block's query view, flags) and the list of
+// chained (multi-seed) flag
+__global__ void __launch_bounds__(256) k_group_desc(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                    uint32_t n, BlockGeom g, const uint32_t *__restrict__ gidx,
+                                                    const uint64_t *__restrict__ qoff, const uint64_t *__restrict__ toff,
+                                                    uint64_t qa, uint32_t *__restrict__ gheads, uint2 *__restrict__ desc,
+                                                    uint64_t *__restrict__ gkey,
+                                                    uint32_t *__restrict__ grank,
+                                                    unsigned long long *__restrict__ counters) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int shift = g.qst_bits;
+    bool multi = false;
+    uint32_t gi = 0;
+    if (p < n) {
+        const uint64_t k = keys[p];
+        if (k != ~0ull && (p == 0 || (keys[p - 1] >> shift) != (k >> shift))) {
+            gi = gidx[p];
+            gheads[gi] = p;
+            gkey[gi] = k;
+            multi = p + 1 < n && (keys[p + 1] >> shift) == (k >> shift);
+            const int qst = (int)(k & ((1ull << g.qst_bits) - 1));
+            const int diag = (int)((k >> g.qst_bits) & ((1ull << g.diag_bits) - 1)) - g.diag_bias;
+            const uint64_t pair = k >> (g.qst_bits + g.diag_bits);
+            const int hd1 = (int)(pair & ((1ull << g.hd_bits) - 1));
+            const int qi = (int)(pair >> g.hd_bits);
+            const int sst = qst - diag;
+            const uint32_t xt = (uint32_t)toff[g.c0 + hd1 - 1] + (uint32_t)sst;
+            const uint32_t uq = (uint32_t)(qoff[g.qb0 + qi] - qa) + (uint32_t)qst;
+            desc[gi] = make_uint2(xt, uq | (multi ? 0u : kDescSingle) | ((qst == 0 || sst == 0) ? kDescNoLeft : 0u));
+            if (vals) grank[gi] = vals[p];  // k_xdrop folds the other hits of a chained group in
         }
-        if (__all_sync(0xffffffffu, fin)) break;
-        // ---- (2) U extension steps; right (dir = +1) and left (dir = -1) extensions share the body
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, multi);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(counters + 3, (unsigned long long)__popc(m));  // statistic only
+}
+
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int v;
+    asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// 16 query bytes starting at byte 4*ws + bs of the aligned chunk pair (a, b); w1 / w2 = bits of ws
+__device__ __forceinline__ void ung_qwindow(const uint4 &a, const uint4 &b, bool w1, bool w2, uint32_t bs8, uint32_t W[4]) {
+    const uint32_t X[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t Y[7], Z[5];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const bool in = alive && (iq - lo1) < span;
-            int tv = 0;
-            if (in) {
-                uint64_t aq, at;
-                uint32_t cq, ct;
-                asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(aq) : "r"(iq), "l"(qcls64));
-                asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(at) : "r"(iq + dlt), "l"(tcls64));
-                asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(cq) : "l"(aq));
-                asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(ct) : "l"(at));
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tv) : "r"(sbase + ((cq << 5 | ct) << 2)));
-            }
-            v += tv;
-            mxk = max(mxk, v);
-            alive = in && ((v | PMAX) + DROP >= mxk);
-            iq += (uint32_t)dir;
-        }
-        // ---- (3) transitions of the lanes whose extension ended
-        if (has && !alive) {
-            steps += (unsigned)(PMAX - (v & PMAX));
-            if (dir > 0) {  // right done -> left from (Q-1, S-1), continuing the right maximum
-                const int k = PMAX - (mxk & PMAX);           // 1-based step that reached the maximum (0: none)
-                mx_qed = qbase + (uint32_t)Q + (uint32_t)max(k, 1) - 1u;
-                v = (mxk | PMAX);                            // score = right maximum, fresh step counter
-                mxk = v;
-                dir = -1;
-                iq = qbase + (uint32_t)Q - 1u;
-                alive = true;
-            } else {        // seed done
-                total += mxk >> 13;
-                lo = (int)(mx_qed - qbase);  // next seed: qlo = max_qed, slo = max_sed (same diagonal)
-                bool more = false;
-                for (;;) {
-                    e++;
-                    if (e >= n) break;
-                    const uint64_t k2 = keys[e];
-                    if ((k2 >> g.qst_bits) != grp) break;
-                    if (vals) rank_min = min(rank_min, vals[e]);
-                    const int qst = (int)(k2 & qmask);
-                    if (qst == prev_q) continue;  // same point again (other pattern / alphabet): lis() drops it
-                    prev_q = qst;
-                    more = true;
-                    break;
+    for (int j = 0; j < 7; j++) Y[j] = w1 ? X[j + 1] : X[j];
+#pragma unroll
+    for (int j = 0; j < 5; j++) Z[j] = w2 ? Y[j + 2] : Y[j];
+#pragma unroll
+    for (int j = 0; j < 4; j++) W[j] = __funnelshift_r(Z[j], Z[j + 1], bs8);
+}
+// bytes [0, lo) of the chunk -> class `below`, bytes [hi, 16) -> class `above` (lo <= hi)
+__device__ __forceinline__ uint32_t ung_low_mask(int nbytes) {  // low `nbytes` bytes set (clamped to 0..4)
+    const int sh = min(max(nbytes, 0), 4) * 8;
+    return sh >= 32 ? 0xffffffffu : ((1u << sh) - 1u);
+}
+__device__ __forceinline__ void ung_mask_below(uint4 &t, int lo, uint32_t cls) {
+    uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t m = ung_low_mask(lo - 4 * k);
+        w[k] = (w[k] & ~m) | ((cls * 0x01010101u) & m);
+    }
+    t = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void ung_mask_from(uint4 &t, int hi, uint32_t cls) {
+    uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t m = ung_low_mask(hi - 4 * k);
+        w[k] = (w[k] & m) | ((cls * 0x01010101u) & ~m);
+    }
+    t = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// 16 chained X-drop steps on table entries e0..e15 (see the header comment):
+//   dd = max(dd + e, 0)   unpredicated (one VIADDMNMX, alu pipe)
+//   if alive: v -= e; d = dd   (d: value at the last live step; the copy is written as dd * one so that
+//                               ptxas keeps it a predicated IMAD on the fma pipe instead of an alu SEL)
+//   alive &= dd < 31 * 8192
+// Per step: alu PRMT + VIADDMNMX + ISETP, fma IMAD (table address) + IMAD.IADD + IMAD, one LDS.
+#define SO_XS(n)                                                                                         \
+    "add.s32 t, dd, %" #n ";\n\tmax.s32 dd, t, 0;\n\t@p mad.lo.s32 %1, dd, %3, 0;\n\t@p sub.s32 %0, %0, %" #n \
+    ";\n\tsetp.lt.and.s32 p, dd, 253952, p;\n\t"
+__device__ __forceinline__ void ung_steps16(int &v, int &d, int &alive, int one, const int (&e)[16]) {
+    asm("{\n\t.reg .pred p;\n\t.reg .s32 t, dd;\n\tsetp.ne.s32 p, %2, 0;\n\tmov.s32 dd, %1;\n\t"
+        SO_XS(4) SO_XS(5) SO_XS(6) SO_XS(7) SO_XS(8) SO_XS(9) SO_XS(10) SO_XS(11)
+        SO_XS(12) SO_XS(13) SO_XS(14) SO_XS(15) SO_XS(16) SO_XS(17) SO_XS(18) SO_XS(19)
+        "selp.s32 %2, 1, 0, p;\n\t}"
+        : "+r"(v), "+r"(d), "+r"(alive)
+        : "r"(one), "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]),
+          "r"(e[9]), "r"(e[10]), "r"(e[11]), "r"(e[12]), "r"(e[13]), "r"(e[14]), "r"(e[15]));
+}
+#undef SO_XS
+
+template <int kRefill>
+__global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc, uint32_t G,
+                                                  const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                  uint32_t nhits, const uint32_t *__restrict__ gheads, int qst_bits,
+                                                  const uint4 *__restrict__ T4, uint32_t toffF, uint32_t toffR, uint32_t R,
+                                                  const uint4 *__restrict__ Q4, uint32_t qoffF, uint32_t qoffR, uint32_t Lq,
+                                                  uint32_t *__restrict__ gscore, uint32_t *__restrict__ grank,
+                                                  unsigned long long *__restrict__ counters, int one) {
+    extern __shared__ int s_tab[];  // [(ct << 5 | cq)][lane]
+    for (int k = threadIdx.x; k < kUngRows * 32 * 32; k += blockDim.x) {
+        const int e = k >> 5, ct = e >> 5, cq = e & 31;
+        int val = 1 << 29;
+        if (ct == kUngSkip)
+            val = 0;
+        else if (ct < 24 && cq < 24)
+            val = 1 - (int)c_score2[cq * kClasses + ct] * 8192;
+        s_tab[k] = val;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t lanebase = (uint32_t)__cvta_generic_to_shared(s_tab) + (uint32_t)lane * 4u;
+    const uint32_t qmask = (1u << qst_bits) - 1u;
+    constexpr int kNoLimit = 1 << 30;
+    const unsigned long long kBatch = 512;  // group indices taken per atomic
+    int alive = 0;
+    bool has = false, fin = false, noleft = false, multi = false, chained = false;
+    bool w1 = false, w2 = false;
+    int phase = 0, acc = 0, v = 0, d = 0, lim = kNoLimit;
+    int qcur = 0, lo = 0;                  // chains: qst of the seed being extended, max_qed of the last segment
+    uint32_t gi = 0, xt = 0, uq = 0, tci = 0, qci = 0, bs8 = 0, e = 0;
+    uint4 tc = make_uint4(0, 0, 0, 0), carry = make_uint4(0, 0, 0, 0);
+    uint32_t W[4] = {0, 0, 0, 0};
+    unsigned int steps = 0;
+    uint32_t pool_next = 0, pool_end = 0;  // warp-uniform
+    bool exhausted = false;                // warp-uniform
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !alive);
+        if (__popc(idle) >= kRefill) {
+            // ---- service: finished phases, next seeds / groups, first loads of the next phase
+            bool setup = false;
+            if (!alive && has) {
+                const int nst = (-v) & 8191;
+                acc += (v + d + 8191) >> 13;
+                steps += (unsigned)nst;
+                bool seed_done = true;
+                if (phase == 0) {
+                    // later seeds: the left extension stops above the previous segment's max_qed
+                    lim = chained ? qcur - 1 - lo : kNoLimit;
+                    // max_qed: query index of the first step that reached the right maximum (fsearch.py:2470-2474)
+                    lo = qcur + max(nst - (d & 8191), 1) - 1;
+                    if (!noleft && lim > 0) {
+                        phase = 1;
+                        setup = true;
+                        seed_done = false;
+                    }
                 }
-                if (more) {
-                    Q = max(prev_q, lo);
-                    iq = qbase + (uint32_t)Q;
-                    lo1 = qbase + (uint32_t)lo + 1u;
-                    span = hi > lo + 1 ? (uint32_t)(hi - lo - 1) : 0u;
-                    v = PMAX, mxk = PMAX, dir = 1;
-                    alive = true;
-                } else {
-                    gscore[gi] = (uint32_t)total;
-                    if (vals) grank[gi] = rank_min;
-                    has = false;
+                if (seed_done) {
+                    bool more = false;
+                    if (multi) {
+                        // next seed of the chain: seeds at or below max_qed extend nothing and leave it unchanged
+                        for (;;) {
+                            e++;
+                            if (e >= nhits) break;
+                            const uint64_t k2 = keys[e];
+                            if (((k2 ^ keys[e - 1]) >> qst_bits) != 0) break;
+                            if (vals) grank[gi] = min(grank[gi], vals[e]);
+                            const int qst = (int)((uint32_t)k2 & qmask);
+                            if (qst <= lo) continue;
+                            const uint32_t delta = (uint32_t)(qst - qcur);
+                            xt += delta, uq += delta;
+                            qcur = qst;
+                            more = true;
+                            break;
+                        }
+                    }
+                    if (more) {
+                        phase = 0, noleft = false, chained = true, lim = kNoLimit;
+                        setup = true;
+                    } else {
+                        gscore[gi] = (uint32_t)acc;
+                        has = false;
+                    }
                 }
             }
+            const unsigned need = __ballot_sync(0xffffffffu, !has && !fin);
+            if (need) {
+                if (pool_next == pool_end && !exhausted) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(counters + 2, kBatch);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base >= G)
+                        exhausted = true;
+                    else {
+                        pool_next = (uint32_t)base;
+                        pool_end = (uint32_t)min((unsigned long long)G, base + kBatch);
+                    }
+                }
+                if (!has && !fin) {
+                    const uint32_t mine = pool_next + __popc(need & ((1u << lane) - 1));
+                    if (mine < pool_end) {
+                        const uint2 ds = desc[mine];
+                        gi = mine;
+                        xt = ds.x;
+                        uq = ds.y & 0xffffffu;
+                        noleft = (ds.y & kDescNoLeft) != 0;
+                        multi = (ds.y & kDescSingle) == 0;
+                        qcur = 0;
+                        if (multi) {
+                            e = gheads[mine];
+                            qcur = (int)((uint32_t)keys[e] & qmask);
+                        }
+                        phase = 0, acc = 0, chained = false, lim = kNoLimit;
+                        has = true;
+                        setup = true;
+                    } else if (exhausted)
+                        fin = true;  // otherwise the pool is refilled at the next service
+                }
+                pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
+            }
+            if (__all_sync(0xffffffffu, fin)) break;
+            if (setup) {
+                const uint32_t tpos = (phase ? toffR + (R - xt) : toffF + xt);
+                const int o = (int)(tpos & 15u);
+                const uint32_t qpos = (phase ? qoffR + (Lq - uq) : qoffF + uq) - (uint32_t)o;
+                tci = tpos >> 4;
+                qci = qpos >> 4;
+                w1 = (qpos & 4u) != 0, w2 = (qpos & 8u) != 0, bs8 = (qpos & 3u) * 8u;
+                tc = T4[tci];
+                const uint4 a = Q4[qci];
+                carry = Q4[qci + 1];
+                tci += 1, qci += 2;
+                ung_qwindow(a, carry, w1, w2, bs8, W);
+                ung_mask_below(tc, o, kUngSkip);  // bytes before the start score nothing
+                if (lim < 16 - o) ung_mask_from(tc, o + lim, kUngStop);
+                lim -= 16 - o;
+                v = 0, d = 0;
+                alive = 1;
+            }
         }
+        // ---- 16 extension steps on the current chunk; the next chunk is fetched meanwhile
+        uint4 nt = tc, nq = carry;
+        if (alive) {
+            nt = T4[tci];
+            nq = Q4[qci];
+        }
+        {
+            int ev[16];
+            const uint32_t tw[4] = {tc.x, tc.y, tc.z, tc.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                ev[4 * j + 0] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xCC40u) << 4));
+                ev[4 * j + 1] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xDD51u) << 4));
+                ev[4 * j + 2] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xEE62u) << 4));
+                ev[4 * j + 3] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xFF73u) << 4));
+            }
+            ung_steps16(v, d, alive, one, ev);
+        }
+        tc = nt;
+        if (__any_sync(0xffffffffu, alive && lim < 16)) {
+            if (lim < 16) ung_mask_from(tc, lim, kUngStop);
+        }
+        lim -= 16;
+        ung_qwindow(carry, nq, w1, w2, bs8, W);
+        carry = nq;
+        tci += 1, qci += 1;
     }
     unsigned long long st64 = steps;
 #pragma unroll
@@ -749,7 +942,10 @@ __device__ __forceinline__ uint32_t recompute_rank(const RankCtx &rc, int qi, in
     return (uint32_t)rc.slot_out[slot] + lo;
 }
 
+// gkey (optional): the head key of every group, written by k_group_desc, so the scan over a pair's
+// groups reads consecutive words instead of chasing gheads into the hit array
 __global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gheads,
+                                                     const uint64_t *__restrict__ gkey,
                                                      uint32_t G, BlockGeom g, const uint32_t *__restrict__ gscore,
                                                      const uint32_t *__restrict__ grank, RankCtx rctx,
                                                      uint64_t *__restrict__ ckeys, uint64_t *__restrict__ cvals,
@@ -760,14 +956,14 @@ __global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict_
     bool head = false;
     uint64_t pair = 0;
     if (gi < G) {
-        pair = keys[gheads[gi]] >> pair_shift;
-        head = gi == 0 || (keys[gheads[gi - 1]] >> pair_shift) != pair;
+        pair = (gkey ? gkey[gi] : keys[gheads[gi]]) >> pair_shift;
+        head = gi == 0 || ((gkey ? gkey[gi - 1] : keys[gheads[gi - 1]]) >> pair_shift) != pair;
     }
     int best_score = 0, best_diag = 0;
     uint32_t best_rank = 0xffffffffu, first_rank = 0xffffffffu;
     if (head) {
         for (uint32_t k = gi; k < G; k++) {
-            const uint64_t kk = keys[gheads[k]];
+            const uint64_t kk = gkey ? gkey[k] : keys[gheads[k]];
             if ((kk >> pair_shift) != pair) break;
             const int sc = (int)gscore[k];
             if (sc >= 25) {  // self.min (fsearch.py:2224, 2707)
@@ -850,7 +1046,7 @@ static int bits_for(uint64_t maxval) {  // bits needed to hold values 0..maxval
 }
 
 enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TMP, SC_CKA, SC_CKB, SC_CVA, SC_CVB, SC_MISC,
-       SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK };
+       SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK, SC_QUNG, SC_DESC, SC_MLIST, SC_GKEY };
 
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
 
@@ -922,7 +1118,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
         if ((rc = c->scratch[SC_ST].reserve((size_t)nslots * 4)) != SO_OK) return rc;
         if ((rc = c->scratch[SC_CNT].reserve(((size_t)nslots + 1) * 4)) != SO_OK) return rc;
         if ((rc = c->scratch[SC_OUT].reserve(((size_t)nslots + 1) * 8)) != SO_OK) return rc;
-        if ((rc = c->scratch[SC_MISC].reserve(((size_t)nq + 2) * 4 + 64)) != SO_OK) return rc;
+        if ((rc = c->scratch[SC_MISC].reserve(((size_t)nq + 2) * 4 + 128)) != SO_OK) return rc;
         uint32_t *d_slot_off = (uint32_t *)c->scratch[SC_SLOTOFF].p;
         uint32_t *d_st = (uint32_t *)c->scratch[SC_ST].p, *d_cnt = (uint32_t *)c->scratch[SC_CNT].p;
         uint64_t *d_out = (uint64_t *)c->scratch[SC_OUT].p;
@@ -994,8 +1190,8 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             uint64_t *cka = (uint64_t *)c->scratch[SC_CKA].p, *ckb = (uint64_t *)c->scratch[SC_CKB].p;
             uint64_t *cva = (uint64_t *)c->scratch[SC_CVA].p, *cvb = (uint64_t *)c->scratch[SC_CVB].p;
             unsigned long long *d_counter = (unsigned long long *)(c->scratch[SC_MISC].p);
-            uint32_t *d_bounds = (uint32_t *)(c->scratch[SC_MISC].p + 32);
-            SO_CUDA(cudaMemsetAsync(d_counter, 0, 32, st));
+            uint32_t *d_bounds = (uint32_t *)(c->scratch[SC_MISC].p + 64);
+            SO_CUDA(cudaMemsetAsync(d_counter, 0, 64, st));
             // diagonal groups: head flags -> exclusive scan -> compact head positions
             const int grp_shift = g.qst_bits;
             if ((rc = c->scratch[SC_GIDX].reserve(((size_t)H + 1) * 4)) != SO_OK) return rc;
@@ -1028,35 +1224,68 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             uint32_t *d_gheads = (uint32_t *)c->scratch[SC_GHEAD].p, *d_gscore = (uint32_t *)c->scratch[SC_GSCORE].p;
             uint32_t *d_grank = (uint32_t *)c->scratch[SC_GRANK].p;
             if (G > 0) {
-                k_scatter_heads<<<(uint32_t)((H + 255) / 256), 256, 0, st>>>(dk.Current(), (uint32_t)H, grp_shift, d_gidx, d_gheads);
-                // packed fast variant needs < 8192 steps per extension and 32-bit residue indices
+                // packed fast variants need < 8192 steps per extension and 32-bit residue indices
                 const bool fast_ungap = maxql < 8192 && ix.max_tlen < 8192 && c->q_off[(size_t)c->n_q] < 0xfff00000ull &&
                                         c->t_off[(size_t)c->n_t] < 0xfff00000ull && !getenv("SO_GENERIC_UNGAP");
-                int per_sm = 4;
-                if (fast_ungap)
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_group_ungap, 256, 0);
-                else
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_group_ungap_generic, 256, 0);
-                const int ublocks = 148 * std::max(1, per_sm);
+                const uint64_t qa = c->q_off[(size_t)b0], Lq64 = c->q_off[(size_t)b1] - qa;
+                const bool single_path = fast_ungap && c->d_tung && Lq64 + 2 * kUngPad < (1ull << 24) && !getenv("SO_NO_SINGLE");
                 const uint32_t *d_vals = keys_only ? nullptr : dv.Current();
-                if (fast_ungap)
-                    k_group_ungap<<<ublocks, 256, 0, st>>>(dk.Current(), d_vals, (uint32_t)H, d_gheads, G, g, c->d_qcls, c->d_qoff,
-                                                           c->d_tcls, c->d_toff, d_gscore, d_grank, d_counter);
-                else
+                const uint64_t *d_gkey = nullptr;
+                if (single_path) {
+                    // X-drop view of the sub-block's queries: (class << 3), forward + reversed
+                    uint32_t qoff2[2], qtotal;
+                    ung_layout((uint32_t)Lq64, qoff2, qtotal);
+                    if ((rc = c->scratch[SC_QUNG].reserve(qtotal)) != SO_OK) return rc;
+                    if ((rc = c->scratch[SC_DESC].reserve(((size_t)G + 1) * 8)) != SO_OK) return rc;
+                    if ((rc = c->scratch[SC_GKEY].reserve(((size_t)G + 1) * 8)) != SO_OK) return rc;
+                    uint8_t *d_qung = c->scratch[SC_QUNG].p;
+                    uint2 *d_desc = (uint2 *)c->scratch[SC_DESC].p;
+                    if ((rc = ung_build(c, c->d_qcls + qa, c->d_qoff + b0, (uint32_t)nq, qa, (uint32_t)Lq64, d_qung, qoff2, qtotal,
+                                        3)) != SO_OK)
+                        return rc;
+                    k_group_desc<<<(uint32_t)((H + 255) / 256), 256, 0, st>>>(dk.Current(), d_vals, (uint32_t)H, g, d_gidx, c->d_qoff,
+                                                                             c->d_toff, qa, d_gheads, d_desc,
+                                                                             (uint64_t *)c->scratch[SC_GKEY].p, d_grank,
+                                                                             d_counter);
+                    SO_CUDA(cudaEventRecord(c->ev[5], st));
+                    static bool attr_done = false;
+                    if (!attr_done) {
+                        SO_CUDA(cudaFuncSetAttribute(k_xdrop<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+                        attr_done = true;
+                    }
+                    k_xdrop<12><<<148 * 2, 512, kUngTabBytes, st>>>(d_desc, G, dk.Current(), d_vals, (uint32_t)H, d_gheads, g.qst_bits,
+                                                                   (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
+                                                                   (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung,
+                                                                   qoff2[0], qoff2[1], (uint32_t)Lq64, d_gscore, d_grank, d_counter, 1);
+                    d_gkey = (const uint64_t *)c->scratch[SC_GKEY].p;
+                    c->stats.kernel_launches += 2;
+                } else {
+                    k_scatter_heads<<<(uint32_t)((H + 255) / 256), 256, 0, st>>>(dk.Current(), (uint32_t)H, grp_shift, d_gidx, d_gheads);
+                    SO_CUDA(cudaEventRecord(c->ev[5], st));
+                    c->stats.kernel_launches += 1;
+                }
+                if (!single_path) {
+                    int per_sm = 4;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_group_ungap_generic, 256, 0);
+                    const int ublocks = 148 * std::max(1, per_sm);
                     k_group_ungap_generic<<<ublocks, 256, 0, st>>>(dk.Current(), d_vals, (uint32_t)H, d_gheads, G, g, c->d_qcls,
                                                                    c->d_qoff, c->d_tcls, c->d_toff, d_gscore, d_grank, d_counter);
+                    c->stats.kernel_launches += 1;
+                }
+                SO_CUDA(cudaEventRecord(c->ev[6], st));
                 RankCtx rctx{d_slot_off, d_st, d_cnt, d_out, ix.d_hdsst};
-                k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, G, g, d_gscore, keys_only ? nullptr : d_grank,
+                k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, d_gkey, G, g, d_gscore, keys_only ? nullptr : d_grank,
                                                                rctx, cka, cva, d_counter);
-                c->stats.kernel_launches += 3;
+                c->stats.kernel_launches += 1;
                 c->stats.lib_launches += 1;
             }
             SO_CUDA(cudaEventRecord(c->ev[3], st));
-            unsigned long long h_counter[2] = {0, 0};
-            SO_CUDA(cudaMemcpyAsync(h_counter, d_counter, 16, cudaMemcpyDeviceToHost, st));
+            unsigned long long h_counter[4] = {0, 0, 0, 0};
+            SO_CUDA(cudaMemcpyAsync(h_counter, d_counter, 32, cudaMemcpyDeviceToHost, st));
             SO_CUDA(cudaStreamSynchronize(st));
             const unsigned long long ncand = h_counter[0];
             c->stats.ungap_steps += (i64)h_counter[1];
+            c->stats.multi_groups += (i64)h_counter[3];
             SO_CUDA(cudaGetLastError());
             c->stats.kernel_launches += 1;
             c->stats.lib_launches += 1;
@@ -1092,6 +1321,10 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             c->stats.ms_sort += ms;
             cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
             c->stats.ms_ungap += ms;
+            if (G > 0) {
+                cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]);
+                c->stats.ms_ungap_kernel += ms;
+            }
             for (int k = 0; k < nq; k++)
                 out.offsets[(size_t)(b0 - q_begin + k + 1)] = (uint64_t)base_c + bounds[(size_t)k + 1];
         }
