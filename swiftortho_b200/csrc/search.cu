@@ -433,6 +433,12 @@ __global__ void __launch_bounds__(256) k_scatter_heads(const uint64_t *__restric
     if (p == 0 || (keys[p - 1] >> shift) != (k >> shift)) gheads[gidx[p]] = p;
 }
 
+__global__ void __launch_bounds__(256) k_gather_keys(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gheads,
+                                                     uint32_t G, uint64_t *__restrict__ gkey) {
+    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi < G) gkey[gi] = keys[gheads[gi]];
+}
+
 __global__ void __launch_bounds__(256) k_group_ungap_generic(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                      uint32_t n, const uint32_t *__restrict__ gheads, uint32_t G, BlockGeom g,
                                                      const uint8_t *__restrict__ qcls, const uint64_t *__restrict__ qoff,
@@ -653,15 +659,13 @@ __global__ void __launch_bounds__(256) k_group_desc(const uint64_t *__restrict__
                                                     unsigned long long *__restrict__ counters) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const int shift = g.qst_bits;
-    bool multi = false;
-    uint32_t gi = 0;
     if (p < n) {
         const uint64_t k = keys[p];
         if (k != ~0ull && (p == 0 || (keys[p - 1] >> shift) != (k >> shift))) {
-            gi = gidx[p];
+            const uint32_t gi = gidx[p];
             gheads[gi] = p;
             gkey[gi] = k;
-            multi = p + 1 < n && (keys[p + 1] >> shift) == (k >> shift);
+            const bool multi = p + 1 < n && (keys[p + 1] >> shift) == (k >> shift);
             const int qst = (int)(k & ((1ull << g.qst_bits) - 1));
             const int diag = (int)((k >> g.qst_bits) & ((1ull << g.diag_bits) - 1)) - g.diag_bias;
             const uint64_t pair = k >> (g.qst_bits + g.diag_bits);
@@ -674,8 +678,6 @@ __global__ void __launch_bounds__(256) k_group_desc(const uint64_t *__restrict__
             if (vals) grank[gi] = vals[p];  // k_xdrop folds the other hits of a chained group in
         }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, multi);
-    if (m && (threadIdx.x & 31) == 0) atomicAdd(counters + 3, (unsigned long long)__popc(m));  // statistic only
 }
 
 __device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
@@ -699,28 +701,37 @@ __device__ __forceinline__ void ung_qwindow(const uint4 &a, const uint4 &b, bool
 #pragma unroll
     for (int j = 0; j < 4; j++) W[j] = __funnelshift_r(Z[j], Z[j + 1], bs8);
 }
-// bytes [0, lo) of the chunk -> class `below`, bytes [hi, 16) -> class `above` (lo <= hi)
-__device__ __forceinline__ uint32_t ung_low_mask(int nbytes) {  // low `nbytes` bytes set (clamped to 0..4)
-    const int sh = min(max(nbytes, 0), 4) * 8;
-    return sh >= 32 ? 0xffffffffu : ((1u << sh) - 1u);
+// shl.b32 clamps shift amounts above 31 (result 0), which C's << does not promise
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, int sh) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(sh));
+    return r;
 }
+// bytes [0, lo) of the chunk -> class `cls`
 __device__ __forceinline__ void ung_mask_below(uint4 &t, int lo, uint32_t cls) {
     uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const uint32_t m = ung_low_mask(lo - 4 * k);
-        w[k] = (w[k] & ~m) | ((cls * 0x01010101u) & m);
+        const uint32_t keep = shl_clamp(0xffffffffu, max(8 * lo - 32 * k, 0));  // bytes >= lo
+        w[k] = (w[k] & keep) | ((cls * 0x01010101u) & ~keep);
     }
     t = make_uint4(w[0], w[1], w[2], w[3]);
 }
+// bytes [hi, 16) of the chunk -> class `cls`
 __device__ __forceinline__ void ung_mask_from(uint4 &t, int hi, uint32_t cls) {
     uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const uint32_t m = ung_low_mask(hi - 4 * k);
-        w[k] = (w[k] & m) | ((cls * 0x01010101u) & ~m);
+        const uint32_t repl = shl_clamp(0xffffffffu, max(8 * hi - 32 * k, 0));  // bytes >= hi
+        w[k] = (w[k] & ~repl) | ((cls * 0x01010101u) & repl);
     }
     t = make_uint4(w[0], w[1], w[2], w[3]);
+}
+// predicated 16-byte loads (no branch around them)
+__device__ __forceinline__ void ldg128_if(uint4 &r, const uint4 *p, int pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w)
+                 : "l"(p), "r"(pred));
 }
 
 // 16 chained X-drop steps on table entries e0..e15 (see the header comment):
@@ -775,7 +786,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
     uint32_t gi = 0, xt = 0, uq = 0, tci = 0, qci = 0, bs8 = 0, e = 0;
     uint4 tc = make_uint4(0, 0, 0, 0), carry = make_uint4(0, 0, 0, 0);
     uint32_t W[4] = {0, 0, 0, 0};
-    unsigned int steps = 0;
+    unsigned int steps = 0, nmulti = 0;
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform
     bool exhausted = false;                // warp-uniform
     for (;;) {
@@ -851,6 +862,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                         multi = (ds.y & kDescSingle) == 0;
                         qcur = 0;
                         if (multi) {
+                            nmulti++;
                             e = gheads[mine];
                             qcur = (int)((uint32_t)keys[e] & qmask);
                         }
@@ -882,12 +894,8 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 alive = 1;
             }
         }
-        // ---- 16 extension steps on the current chunk; the next chunk is fetched meanwhile
-        uint4 nt = tc, nq = carry;
-        if (alive) {
-            nt = T4[tci];
-            nq = Q4[qci];
-        }
+        // ---- 16 extension steps on the current chunk: table lookups first (they consume the chunk
+        // registers), then the loads of the next chunk, then the dependent chain
         {
             int ev[16];
             const uint32_t tw[4] = {tc.x, tc.y, tc.z, tc.w};
@@ -898,21 +906,25 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 ev[4 * j + 2] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xEE62u) << 4));
                 ev[4 * j + 3] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xFF73u) << 4));
             }
+            uint4 nq = carry;
+            ldg128_if(tc, T4 + tci, alive);
+            ldg128_if(nq, Q4 + qci, alive);
             ung_steps16(v, d, alive, one, ev);
+            if (__any_sync(0xffffffffu, alive && lim < 16)) {
+                if (lim < 16) ung_mask_from(tc, lim, kUngStop);
+            }
+            lim -= 16;
+            ung_qwindow(carry, nq, w1, w2, bs8, W);
+            carry = nq;
+            tci += 1, qci += 1;
         }
-        tc = nt;
-        if (__any_sync(0xffffffffu, alive && lim < 16)) {
-            if (lim < 16) ung_mask_from(tc, lim, kUngStop);
-        }
-        lim -= 16;
-        ung_qwindow(carry, nq, w1, w2, bs8, W);
-        carry = nq;
-        tci += 1, qci += 1;
     }
     unsigned long long st64 = steps;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) st64 += __shfl_xor_sync(0xffffffffu, st64, o);
     if (lane == 0 && st64) atomicAdd(counters + 1, st64);
+    nmulti = __reduce_add_sync(0xffffffffu, nmulti);
+    if (lane == 0 && nmulti) atomicAdd(counters + 3, (unsigned long long)nmulti);  // statistic
 }
 
 // Keys-only path (one pattern, one alphabet): the hit ordinal is not carried through the sort.  The
@@ -942,14 +954,34 @@ __device__ __forceinline__ uint32_t recompute_rank(const RankCtx &rc, int qi, in
     return (uint32_t)rc.slot_out[slot] + lo;
 }
 
+// keys-only path: first-appearance rank of every group that passes the threshold (one thread per group;
+// the binary search runs in its own kernel so its dependent loads overlap across the whole grid)
+__global__ void __launch_bounds__(256) k_group_rank(const uint64_t *__restrict__ gkey, uint32_t G, BlockGeom g,
+                                                    const uint32_t *__restrict__ gscore, RankCtx rctx,
+                                                    uint32_t *__restrict__ grank) {
+    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= G || gscore[gi] < 25u) return;
+    const uint64_t kk = gkey[gi];
+    const int qst = (int)(kk & ((1ull << g.qst_bits) - 1));
+    const int dg = (int)((kk >> g.qst_bits) & ((1ull << g.diag_bits) - 1)) - g.diag_bias;
+    const uint64_t pair = kk >> (g.qst_bits + g.diag_bits);
+    grank[gi] = recompute_rank(rctx, (int)(pair >> g.hd_bits), qst, (uint32_t)(pair & ((1ull << g.hd_bits) - 1)),
+                               (uint32_t)(qst - dg));
+}
+
+// one thread per diagonal group; the first group of a (query, target) pair folds the pair:
+// threshold 25, best diagonal (first appearance wins ties), candidate order = first passing rank.
 // gkey (optional): the head key of every group, written by k_group_desc, so the scan over a pair's
-// groups reads consecutive words instead of chasing gheads into the hit array
+// groups reads consecutive words instead of chasing gheads into the hit array.  grank holds the rank of
+// every passing group.  Output slots are claimed with one atomic per block.
 __global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gheads,
                                                      const uint64_t *__restrict__ gkey,
                                                      uint32_t G, BlockGeom g, const uint32_t *__restrict__ gscore,
-                                                     const uint32_t *__restrict__ grank, RankCtx rctx,
+                                                     const uint32_t *__restrict__ grank,
                                                      uint64_t *__restrict__ ckeys, uint64_t *__restrict__ cvals,
                                                      unsigned long long *__restrict__ counters) {
+    __shared__ uint32_t s_wcount[8];
+    __shared__ unsigned long long s_base;
     const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
     const int pair_shift = g.qst_bits + g.diag_bits;
     const uint64_t dmask = (1ull << g.diag_bits) - 1;
@@ -967,15 +999,7 @@ __global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict_
             if ((kk >> pair_shift) != pair) break;
             const int sc = (int)gscore[k];
             if (sc >= 25) {  // self.min (fsearch.py:2224, 2707)
-                uint32_t rk;
-                if (grank)
-                    rk = grank[k];
-                else {
-                    const int dg = (int)((kk >> g.qst_bits) & dmask) - g.diag_bias;
-                    const int qst = (int)(kk & ((1ull << g.qst_bits) - 1));
-                    rk = recompute_rank(rctx, (int)(pair >> g.hd_bits), qst, (uint32_t)(pair & ((1ull << g.hd_bits) - 1)),
-                                        (uint32_t)(qst - dg));
-                }
+                const uint32_t rk = grank[k];
                 first_rank = min(first_rank, rk);
                 if (sc > best_score || (sc == best_score && rk < best_rank)) {
                     best_score = sc;
@@ -987,21 +1011,27 @@ __global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict_
     }
     const bool emit = head && best_score >= 25;
     const unsigned m = __ballot_sync(0xffffffffu, emit);
-    if (m) {
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(m) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(counters, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (emit) {
-            const unsigned long long o = base + __popc(m & ((1u << lane) - 1));
-            const int hd1 = (int)(pair & ((1ull << g.hd_bits) - 1));
-            const int qi = (int)(pair >> g.hd_bits);
-            ckeys[o] = ((uint64_t)qi << 32) | first_rank;
-            // value: target ordinal (24 bits) | score (20 bits) | diagonal + bias (20 bits)
-            cvals[o] = ((uint64_t)(uint32_t)(g.c0 + hd1 - 1) << 40) | ((uint64_t)(uint32_t)best_score << 20) |
-                       (uint64_t)(uint32_t)(best_diag + kCandDiagBias);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_wcount[warp] = (uint32_t)__popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; w++) {
+            const uint32_t n = s_wcount[w];
+            s_wcount[w] = tot;
+            tot += n;
         }
+        s_base = tot ? atomicAdd(counters, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (emit) {
+        const unsigned long long o = s_base + s_wcount[warp] + __popc(m & ((1u << lane) - 1));
+        const int hd1 = (int)(pair & ((1ull << g.hd_bits) - 1));
+        const int qi = (int)(pair >> g.hd_bits);
+        ckeys[o] = ((uint64_t)qi << 32) | first_rank;
+        // value: target ordinal (24 bits) | score (20 bits) | diagonal + bias (20 bits)
+        cvals[o] = ((uint64_t)(uint32_t)(g.c0 + hd1 - 1) << 40) | ((uint64_t)(uint32_t)best_score << 20) |
+                   (uint64_t)(uint32_t)(best_diag + kCandDiagBias);
     }
 }
 
@@ -1248,15 +1278,22 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                                                                              (uint64_t *)c->scratch[SC_GKEY].p, d_grank,
                                                                              d_counter);
                     SO_CUDA(cudaEventRecord(c->ev[5], st));
-                    static bool attr_done = false;
-                    if (!attr_done) {
+                    static int refill = 0;
+                    if (!refill) {
+                        const char *e = getenv("SO_XDROP_REFILL");  // tuning hook: idle lanes that trigger a refill
+                        refill = e ? atoi(e) : 16;
+                        SO_CUDA(cudaFuncSetAttribute(k_xdrop<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
                         SO_CUDA(cudaFuncSetAttribute(k_xdrop<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-                        attr_done = true;
+                        SO_CUDA(cudaFuncSetAttribute(k_xdrop<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+                        SO_CUDA(cudaFuncSetAttribute(k_xdrop<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+                        SO_CUDA(cudaFuncSetAttribute(k_xdrop<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
                     }
-                    k_xdrop<12><<<148 * 2, 512, kUngTabBytes, st>>>(d_desc, G, dk.Current(), d_vals, (uint32_t)H, d_gheads, g.qst_bits,
-                                                                   (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
-                                                                   (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung,
-                                                                   qoff2[0], qoff2[1], (uint32_t)Lq64, d_gscore, d_grank, d_counter, 1);
+                    auto kx = refill <= 8 ? k_xdrop<8> : refill <= 12 ? k_xdrop<12> : refill <= 16 ? k_xdrop<16>
+                              : refill <= 20 ? k_xdrop<20> : k_xdrop<24>;
+                    kx<<<148 * 2, 512, kUngTabBytes, st>>>(d_desc, G, dk.Current(), d_vals, (uint32_t)H, d_gheads, g.qst_bits,
+                                                          (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
+                                                          (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
+                                                          qoff2[1], (uint32_t)Lq64, d_gscore, d_grank, d_counter, 1);
                     d_gkey = (const uint64_t *)c->scratch[SC_GKEY].p;
                     c->stats.kernel_launches += 2;
                 } else {
@@ -1273,9 +1310,20 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                     c->stats.kernel_launches += 1;
                 }
                 SO_CUDA(cudaEventRecord(c->ev[6], st));
-                RankCtx rctx{d_slot_off, d_st, d_cnt, d_out, ix.d_hdsst};
-                k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, d_gkey, G, g, d_gscore, keys_only ? nullptr : d_grank,
-                                                               rctx, cka, cva, d_counter);
+                if (keys_only) {
+                    // ranks were not carried through the sort: recompute them for the passing groups
+                    RankCtx rctx{d_slot_off, d_st, d_cnt, d_out, ix.d_hdsst};
+                    if (!d_gkey) {
+                        if ((rc = c->scratch[SC_GKEY].reserve(((size_t)G + 1) * 8)) != SO_OK) return rc;
+                        k_gather_keys<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, G, (uint64_t *)c->scratch[SC_GKEY].p);
+                        d_gkey = (const uint64_t *)c->scratch[SC_GKEY].p;
+                        c->stats.kernel_launches += 1;
+                    }
+                    k_group_rank<<<(G + 255) / 256, 256, 0, st>>>(d_gkey, G, g, d_gscore, rctx, d_grank);
+                    c->stats.kernel_launches += 1;
+                }
+                k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, d_gkey, G, g, d_gscore, d_grank, cka, cva,
+                                                               d_counter);
                 c->stats.kernel_launches += 1;
                 c->stats.lib_launches += 1;
             }
