@@ -954,30 +954,18 @@ __device__ __forceinline__ uint32_t recompute_rank(const RankCtx &rc, int qi, in
     return (uint32_t)rc.slot_out[slot] + lo;
 }
 
-// keys-only path: first-appearance rank of every group that passes the threshold (one thread per group;
-// the binary search runs in its own kernel so its dependent loads overlap across the whole grid)
-__global__ void __launch_bounds__(256) k_group_rank(const uint64_t *__restrict__ gkey, uint32_t G, BlockGeom g,
-                                                    const uint32_t *__restrict__ gscore, RankCtx rctx,
-                                                    uint32_t *__restrict__ grank) {
-    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= G || gscore[gi] < 25u) return;
-    const uint64_t kk = gkey[gi];
-    const int qst = (int)(kk & ((1ull << g.qst_bits) - 1));
-    const int dg = (int)((kk >> g.qst_bits) & ((1ull << g.diag_bits) - 1)) - g.diag_bias;
-    const uint64_t pair = kk >> (g.qst_bits + g.diag_bits);
-    grank[gi] = recompute_rank(rctx, (int)(pair >> g.hd_bits), qst, (uint32_t)(pair & ((1ull << g.hd_bits) - 1)),
-                               (uint32_t)(qst - dg));
-}
-
 // one thread per diagonal group; the first group of a (query, target) pair folds the pair:
 // threshold 25, best diagonal (first appearance wins ties), candidate order = first passing rank.
 // gkey (optional): the head key of every group, written by k_group_desc, so the scan over a pair's
-// groups reads consecutive words instead of chasing gheads into the hit array.  grank holds the rank of
-// every passing group.  Output slots are claimed with one atomic per block.
+// groups reads consecutive words instead of chasing gheads into the hit array.  The first-appearance
+// rank of a group is grank[] when the hit ordinals were carried through the sort; on the keys-only path
+// (one pattern, one alphabet) the ordinal order is (qst ascending, then the bucket's descending
+// (sequence, position) order), so the rank is rebuilt from the key itself:
+// qst | (max - sequence) | (max - sst).  Output slots are claimed with one atomic per block.
 __global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gheads,
                                                      const uint64_t *__restrict__ gkey,
                                                      uint32_t G, BlockGeom g, const uint32_t *__restrict__ gscore,
-                                                     const uint32_t *__restrict__ grank,
+                                                     const uint32_t *__restrict__ grank, int rank_bits,
                                                      uint64_t *__restrict__ ckeys, uint64_t *__restrict__ cvals,
                                                      unsigned long long *__restrict__ counters) {
     __shared__ uint32_t s_wcount[8];
@@ -992,19 +980,28 @@ __global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict_
         head = gi == 0 || ((gkey ? gkey[gi - 1] : keys[gheads[gi - 1]]) >> pair_shift) != pair;
     }
     int best_score = 0, best_diag = 0;
-    uint32_t best_rank = 0xffffffffu, first_rank = 0xffffffffu;
+    uint64_t best_rank = ~0ull, first_rank = ~0ull;
+    const uint64_t hdmask = (1ull << g.hd_bits) - 1;
     if (head) {
         for (uint32_t k = gi; k < G; k++) {
             const uint64_t kk = gkey ? gkey[k] : keys[gheads[k]];
             if ((kk >> pair_shift) != pair) break;
             const int sc = (int)gscore[k];
             if (sc >= 25) {  // self.min (fsearch.py:2224, 2707)
-                const uint32_t rk = grank[k];
+                const int dg = (int)((kk >> g.qst_bits) & dmask) - g.diag_bias;
+                uint64_t rk;
+                if (grank)
+                    rk = grank[k];
+                else {
+                    const uint64_t qst = kk & ((1ull << g.qst_bits) - 1);
+                    rk = (qst << (g.hd_bits + g.diag_bits)) | ((hdmask - (pair & hdmask)) << g.diag_bits) |
+                         (dmask - (uint64_t)((int)qst - dg));
+                }
                 first_rank = min(first_rank, rk);
                 if (sc > best_score || (sc == best_score && rk < best_rank)) {
                     best_score = sc;
                     best_rank = rk;
-                    best_diag = (int)((kk >> g.qst_bits) & dmask) - g.diag_bias;
+                    best_diag = dg;
                 }
             }
         }
@@ -1026,9 +1023,9 @@ __global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict_
     __syncthreads();
     if (emit) {
         const unsigned long long o = s_base + s_wcount[warp] + __popc(m & ((1u << lane) - 1));
-        const int hd1 = (int)(pair & ((1ull << g.hd_bits) - 1));
+        const int hd1 = (int)(pair & hdmask);
         const int qi = (int)(pair >> g.hd_bits);
-        ckeys[o] = ((uint64_t)qi << 32) | first_rank;
+        ckeys[o] = ((uint64_t)qi << rank_bits) | first_rank;
         // value: target ordinal (24 bits) | score (20 bits) | diagonal + bias (20 bits)
         cvals[o] = ((uint64_t)(uint32_t)(g.c0 + hd1 - 1) << 40) | ((uint64_t)(uint32_t)best_score << 20) |
                    (uint64_t)(uint32_t)(best_diag + kCandDiagBias);
@@ -1050,14 +1047,15 @@ int classify_residues(so_ctx *c, const uint8_t *d_in, uint8_t *d_out, size_t n) 
     return SO_OK;
 }
 
-__global__ void k_query_bounds(const uint64_t *__restrict__ ckeys, uint32_t n, int nq, uint32_t *__restrict__ bounds) {
+__global__ void k_query_bounds(const uint64_t *__restrict__ ckeys, uint32_t n, int nq, int rank_bits,
+                               uint32_t *__restrict__ bounds) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q > nq) return;
     // first index whose query field is >= q
     uint32_t lo = 0, hi = n;
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if ((uint32_t)(ckeys[mid] >> 32) < (uint32_t)q)
+        if ((uint32_t)(ckeys[mid] >> rank_bits) < (uint32_t)q)
             lo = mid + 1;
         else
             hi = mid;
@@ -1196,6 +1194,8 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                                                         va);
             SO_CUDA(cudaEventRecord(c->ev[1], st));
             const int key_bits = g.qst_bits + g.diag_bits + g.hd_bits + q_bits;
+            // candidate sort key: query | first-appearance rank (see k_pair_select)
+            const int rank_bits = (AS == 1 && !getenv("SO_FORCE_PAIRS")) ? g.qst_bits + g.diag_bits + g.hd_bits : 32;
             // dropped hits carry ~0 and must sort last: include one extra bit above the fields
             const int end_bit = std::min(64, key_bits + 1);
             cub::DoubleBuffer<uint64_t> dk(ka, kb);
@@ -1310,20 +1310,8 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                     c->stats.kernel_launches += 1;
                 }
                 SO_CUDA(cudaEventRecord(c->ev[6], st));
-                if (keys_only) {
-                    // ranks were not carried through the sort: recompute them for the passing groups
-                    RankCtx rctx{d_slot_off, d_st, d_cnt, d_out, ix.d_hdsst};
-                    if (!d_gkey) {
-                        if ((rc = c->scratch[SC_GKEY].reserve(((size_t)G + 1) * 8)) != SO_OK) return rc;
-                        k_gather_keys<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, G, (uint64_t *)c->scratch[SC_GKEY].p);
-                        d_gkey = (const uint64_t *)c->scratch[SC_GKEY].p;
-                        c->stats.kernel_launches += 1;
-                    }
-                    k_group_rank<<<(G + 255) / 256, 256, 0, st>>>(d_gkey, G, g, d_gscore, rctx, d_grank);
-                    c->stats.kernel_launches += 1;
-                }
-                k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, d_gkey, G, g, d_gscore, d_grank, cka, cva,
-                                                               d_counter);
+                k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, d_gkey, G, g, d_gscore,
+                                                               keys_only ? nullptr : d_grank, rank_bits, cka, cva, d_counter);
                 c->stats.kernel_launches += 1;
                 c->stats.lib_launches += 1;
             }
@@ -1342,10 +1330,10 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             if (ncand > 0) {
                 cub::DoubleBuffer<uint64_t> ck(cka, ckb), cv(cva, cvb);
                 tmp = 0;
-                cub::DeviceRadixSort::SortPairs(nullptr, tmp, ck, cv, (int)ncand, 0, 32 + q_bits, st);
+                cub::DeviceRadixSort::SortPairs(nullptr, tmp, ck, cv, (int)ncand, 0, rank_bits + q_bits, st);
                 if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
-                SO_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch[SC_TMP].p, tmp, ck, cv, (int)ncand, 0, 32 + q_bits, st));
-                k_query_bounds<<<(nq + 1 + 127) / 128, 128, 0, st>>>(ck.Current(), (uint32_t)ncand, nq, d_bounds);
+                SO_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch[SC_TMP].p, tmp, ck, cv, (int)ncand, 0, rank_bits + q_bits, st));
+                k_query_bounds<<<(nq + 1 + 127) / 128, 128, 0, st>>>(ck.Current(), (uint32_t)ncand, nq, rank_bits, d_bounds);
                 SO_CUDA(cudaEventRecord(c->ev[4], st));
                 Timer td;
                 if ((rc = out.reserve(base_c + (size_t)ncand)) != SO_OK) return rc;
