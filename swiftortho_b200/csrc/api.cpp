@@ -8,6 +8,7 @@
 #include <condition_variable>
 #include <deque>
 #include <functional>
+#include <map>
 #include <mutex>
 #include <cmath>
 #include <thread>
@@ -157,6 +158,8 @@ int so_ctx_create(int device, const so_params *p, so_ctx **out) {
     c->P = P;
     SO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SO_CUDA(cudaStreamCreateWithFlags(&c->stream_aln, cudaStreamNonBlocking));
+    SO_CUDA(cudaStreamCreateWithFlags(&c->stream1, cudaStreamNonBlocking));
+    for (auto &e : c->ev1) SO_CUDA(cudaEventCreate(&e));
     for (auto &e : c->ev) SO_CUDA(cudaEventCreate(&e));
     for (auto &e : c->ev_aln) SO_CUDA(cudaEventCreate(&e));
     if ((rc = so::upload_tables()) != SO_OK) {
@@ -172,6 +175,10 @@ void so_ctx_destroy(so_ctx *c) {
     cudaSetDevice(c->device);
     for (auto &ix : c->chunks) so::free_chunk_index(ix);
     for (auto &s : c->scratch) s.release();
+    for (auto &s : c->scratch1) s.release();
+    for (auto &e : c->ev1)
+        if (e) cudaEventDestroy(e);
+    if (c->stream1) cudaStreamDestroy(c->stream1);
     c->trace.release();
     if (c->d_tres) cudaFree(c->d_tres);
     if (c->d_qres) cudaFree(c->d_qres);
@@ -350,7 +357,9 @@ int so_candidates(so_ctx *c, int64_t chunk, int64_t q_begin, int64_t q_end, uint
     }
     SO_CUDA(cudaSetDevice(c->device));
     so::PackedCands bc;
-    int rc = so::chunk_candidates(c, c->chunks[(size_t)chunk], q_begin, q_end, bc);
+    int rc = so::upload_search_config(c);
+    if (rc == SO_OK) rc = so::chunk_candidates(c, c->chunks[(size_t)chunk], q_begin, q_end, bc);
+    so::merge_lane_stats(c);
     if (rc != SO_OK) {
         bc.release();
         return rc;
@@ -417,17 +426,26 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     const size_t nch = c->chunks.size();
     // query block size: candidates of a block are held packed in pinned memory, one buffer per chunk
     const i64 QB = std::max<i64>(64, std::min<i64>(512, 4096 / (i64)std::max<size_t>(1, nch)));
-    if (c->cand_pool.size() < 2 * nch) c->cand_pool.resize(2 * nch);
-    // Two-stage pipeline: this thread produces the candidates of block b+1 on the GPU while a worker
-    // thread sorts / selects / aligns (own stream) / filters block b.  Rows are appended in block order.
+    const int kSlots = 4;
+    if (c->cand_pool.size() < (size_t)kSlots * nch) c->cand_pool.resize((size_t)kSlots * nch);
+    {
+        int rc = so::upload_search_config(c);
+        if (rc != SO_OK) return rc;
+    }
+    // Pipeline: two producer threads (one stream + scratch set each) produce the candidates of alternating
+    // query blocks on the GPU, so one lane's host synchronisations and D2H copies overlap the other lane's
+    // kernels; a worker thread sorts / selects / aligns (own stream) / filters the blocks in block order.
     struct Job {
         i64 b0, b1;
         int slot;
     };
     std::mutex mu;
     std::condition_variable cv;
-    std::deque<Job> jobs;
-    bool producer_done = false, slot_busy[2] = {false, false};
+    std::map<int, Job> jobs;  // by block number
+    int next_blk = 0;         // next block the worker consumes
+    int producers_left = 2;
+    bool abort_all = false;
+    bool producer_done = false, slot_busy[kSlots] = {false, false, false, false};
     int worker_rc = SO_OK;
     std::string worker_err;
     so_stats wstats;
@@ -627,10 +645,11 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             Job j;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return !jobs.empty() || producer_done; });
-                if (jobs.empty()) break;
-                j = jobs.front();
-                jobs.pop_front();
+                cv.wait(lk, [&] { return jobs.count(next_blk) || producer_done; });
+                if (!jobs.count(next_blk)) break;
+                j = jobs[next_blk];
+                jobs.erase(next_blk);
+                next_blk++;
             }
             bool released = false;
             auto release = [&]() {
@@ -644,13 +663,14 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             bool last;
             {
                 std::lock_guard<std::mutex> lk(mu);
-                last = jobs.empty() && producer_done;
+                last = jobs.empty() && producer_done;  // (a producer still running re-checks with the next block)
             }
             if (rc == SO_OK && worker_rc == SO_OK && (pending.size() >= kAlignBatch || last)) rc = align_pending();
             if (rc != SO_OK && worker_rc == SO_OK) {
                 std::lock_guard<std::mutex> lk(mu);
                 worker_rc = rc;
                 worker_err = so::get_error();
+                cv.notify_all();
             }
             release();
         }
@@ -662,39 +682,51 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             }
         }
     });
-    int prod_rc = SO_OK;
-    int blk = 0;
-    for (i64 b0 = q_begin; b0 < q_end && prod_rc == SO_OK; b0 += QB, blk++) {
-        const i64 b1 = std::min<i64>(q_end, b0 + QB);
-        const int slot = blk & 1;
-        {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return !slot_busy[slot]; });
-            if (worker_rc != SO_OK) break;
-            slot_busy[slot] = true;
+    int prod_rcs[2] = {SO_OK, SO_OK};
+    std::string prod_errs[2];
+    auto produce = [&](int pid) {
+        cudaSetDevice(c->device);
+        int rc = SO_OK;
+        for (int blk = pid;; blk += 2) {
+            const i64 b0 = q_begin + (i64)blk * QB;
+            if (b0 >= q_end || rc != SO_OK) break;
+            const i64 b1 = std::min<i64>(q_end, b0 + QB);
+            const int slot = blk % kSlots;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !slot_busy[slot] || abort_all || worker_rc != SO_OK; });
+                if (worker_rc != SO_OK || abort_all) break;
+                slot_busy[slot] = true;
+            }
+            // PASS 1 (fsearch.py:2990-3016): candidates of every chunk (packed, pinned, reference order)
+            Timer tc;
+            for (size_t ch = 0; ch < nch && rc == SO_OK; ch++)
+                rc = so::chunk_candidates(c, c->chunks[ch], b0, b1, c->cand_pool[(size_t)slot * nch + ch], pid);
+            std::lock_guard<std::mutex> lk(mu);
+            c->prof.cand_ms += tc.ms();
+            if (rc == SO_OK)
+                jobs[blk] = Job{b0, b1, slot};
+            else
+                slot_busy[slot] = false;
+            cv.notify_all();
         }
-        // PASS 1 (fsearch.py:2990-3016): candidates of every chunk (packed, pinned, reference order)
-        Timer tc;
-        for (size_t ch = 0; ch < nch && prod_rc == SO_OK; ch++)
-            prod_rc = so::chunk_candidates(c, c->chunks[ch], b0, b1, c->cand_pool[(size_t)slot * nch + ch]);
-        c->prof.cand_ms += tc.ms();
+        if (rc != SO_OK) prod_errs[pid] = so::get_error();
+        prod_rcs[pid] = rc;
         std::lock_guard<std::mutex> lk(mu);
-        if (prod_rc == SO_OK)
-            jobs.push_back(Job{b0, b1, slot});
-        else
-            slot_busy[slot] = false;
+        if (rc != SO_OK) producer_done = abort_all = true;  // a missing block must not stall the worker
+        if (--producers_left == 0) producer_done = true;
         cv.notify_all();
-    }
-    std::string prod_err = prod_rc != SO_OK ? std::string(so::get_error()) : std::string();
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        producer_done = true;
-        cv.notify_all();
-    }
+    };
+    std::thread producer1(produce, 1);
+    produce(0);
+    producer1.join();
+    const int prod_rc = prod_rcs[0] != SO_OK ? prod_rcs[0] : prod_rcs[1];
+    const std::string prod_err = prod_rcs[0] != SO_OK ? prod_errs[0] : prod_errs[1];
     worker.join();
     c->stats.ms_host += wstats.ms_host;
     c->stats.queries += wstats.queries;
     so::merge_align_stats(c);
+    so::merge_lane_stats(c);
     if (prod_rc != SO_OK) {
         set_error("%s", prod_err.c_str());
         return prod_rc;

@@ -140,6 +140,13 @@ struct so_ctx {
 
     // scratch (grown on demand, reused)
     so::DBuf<uint8_t> scratch[40];
+    // second candidate-production lane (so_search runs two producer threads on alternating query blocks so
+    // that one lane's host synchronisations and D2H copies overlap the other lane's kernels)
+    so::DBuf<uint8_t> scratch1[40];
+    cudaStream_t stream1 = nullptr;
+    cudaEvent_t ev1[8] = {};
+    so_stats stats_lane[2] = {};
+    double d2h_ms_lane[2] = {0, 0};
     so::DBuf<uint64_t> trace;
     void *h_pinned = nullptr;
     size_t h_pinned_cap = 0;
@@ -156,7 +163,9 @@ int upload_tables();
 int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out);
 int build_chunk_index(so_ctx *c, ChunkIndex &ix);
 void free_chunk_index(ChunkIndex &ix);
-int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out);
+int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out, int lane = 0);
+int upload_search_config(so_ctx *c);
+void merge_lane_stats(so_ctx *c);
 int ensure_pinned(so_ctx *c, size_t bytes);
 void merge_align_stats(so_ctx *c);
 int classify_residues(so_ctx *c, const uint8_t *d_in, uint8_t *d_out, size_t n);

@@ -627,12 +627,12 @@ static void ung_layout(uint32_t n, uint32_t off[2], uint32_t &total) {
     total = off[1] + r + kUngPad;
 }
 
-static int ung_build(so_ctx *c, const uint8_t *d_cls, const uint64_t *d_off, uint32_t nseq, uint64_t base, uint32_t n,
-                     uint8_t *dst, const uint32_t off[2], uint32_t total, int shift) {
-    k_ung_fill<<<(total + 255) / 256, 256, 0, c->stream>>>(d_cls, n, dst, off[0], off[1], total, shift);
-    if (nseq) k_ung_marks<<<(nseq + 255) / 256, 256, 0, c->stream>>>(d_off, nseq, base, n, dst, off[0], off[1], shift);
+static int ung_build(cudaStream_t st, so_stats &stats, const uint8_t *d_cls, const uint64_t *d_off, uint32_t nseq,
+                     uint64_t base, uint32_t n, uint8_t *dst, const uint32_t off[2], uint32_t total, int shift) {
+    k_ung_fill<<<(total + 255) / 256, 256, 0, st>>>(d_cls, n, dst, off[0], off[1], total, shift);
+    if (nseq) k_ung_marks<<<(nseq + 255) / 256, 256, 0, st>>>(d_off, nseq, base, n, dst, off[0], off[1], shift);
     SO_CUDA(cudaGetLastError());
-    c->stats.kernel_launches += 2;
+    stats.kernel_launches += 2;
     return SO_OK;
 }
 
@@ -644,7 +644,7 @@ int build_ungap_targets(so_ctx *c) {
     uint32_t total;
     ung_layout((uint32_t)R, c->tung_off, total);
     SO_CUDA(cudaMalloc((void **)&c->d_tung, total));
-    return ung_build(c, c->d_tcls, c->d_toff, (uint32_t)c->n_t, 0, (uint32_t)R, c->d_tung, c->tung_off, total, 0);
+    return ung_build(c->stream, c->stats, c->d_tcls, c->d_toff, (uint32_t)c->n_t, 0, (uint32_t)R, c->d_tung, c->tung_off, total, 0);
 }
 
 // one thread per sorted hit: group heads, the X-drop descriptor of the group (global target residue
@@ -1078,7 +1078,38 @@ enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TM
 
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
 
-int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out) {
+static int g_xdrop_refill = 20;  // idle lanes that trigger a refill in k_xdrop (SO_XDROP_REFILL: tuning hook)
+
+int upload_search_config(so_ctx *c) {
+    const char *e = getenv("SO_XDROP_REFILL");
+    if (e) g_xdrop_refill = atoi(e);
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    return upload_cfg(c->P);
+}
+
+void merge_lane_stats(so_ctx *c) {
+    for (int l = 0; l < 2; l++) {
+        so_stats &a = c->stats_lane[l], &d = c->stats;
+        d.seed_hits += a.seed_hits, d.groups += a.groups, d.candidates += a.candidates, d.ungap_steps += a.ungap_steps;
+        d.kernel_launches += a.kernel_launches, d.lib_launches += a.lib_launches;
+        d.ms_seed += a.ms_seed, d.ms_sort += a.ms_sort, d.ms_ungap += a.ms_ungap, d.ms_select += a.ms_select;
+        d.ms_ungap_kernel += a.ms_ungap_kernel, d.multi_groups += a.multi_groups;
+        d.h2d_bytes += a.h2d_bytes, d.d2h_bytes += a.d2h_bytes;
+        c->prof.d2h_ms += c->d2h_ms_lane[l];
+        memset(&a, 0, sizeof a);
+        c->d2h_ms_lane[l] = 0;
+    }
+}
+
+// The caller uploads the search configuration (upload_search_config) once before the first call.
+int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out, int lane) {
+    so::DBuf<uint8_t> *scratch = lane ? c->scratch1 : c->scratch;
+    cudaEvent_t *ev = lane ? c->ev1 : c->ev;
+    so_stats &stats = c->stats_lane[lane];
     const Params &P = c->P;
     const i64 nq_total = q_end - q_begin;
     out.offsets.assign((size_t)nq_total + 1, 0);
@@ -1086,12 +1117,11 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
     if (nq_total <= 0) return SO_OK;
     if (ix.n_seeds == 0) return SO_OK;
     int rc;
-    if ((rc = upload_cfg(P)) != SO_OK) return rc;
     const int AS = (int)(P.alphabets.size() * P.patterns.size());
     const i64 M = ix.c1 - ix.c0;
     i64 sub = c->sub_block > 0 ? c->sub_block : 256;
     i64 b0 = q_begin;
-    cudaStream_t st = c->stream;
+    cudaStream_t st = lane ? c->stream1 : c->stream;
     while (b0 < q_end) {
         i64 b1 = std::min<i64>(q_end, b0 + sub);
         const int nq = (int)(b1 - b0);
@@ -1142,17 +1172,17 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
         g.thr_mul = ix.threshold;
         g.mink = P.mink;
         g.c0 = (int)ix.c0;
-        if ((rc = c->scratch[SC_SLOTOFF].reserve(((size_t)nq + 1) * 4)) != SO_OK) return rc;
-        if ((rc = c->scratch[SC_ST].reserve((size_t)nslots * 4)) != SO_OK) return rc;
-        if ((rc = c->scratch[SC_CNT].reserve(((size_t)nslots + 1) * 4)) != SO_OK) return rc;
-        if ((rc = c->scratch[SC_OUT].reserve(((size_t)nslots + 1) * 8)) != SO_OK) return rc;
-        if ((rc = c->scratch[SC_MISC].reserve(((size_t)nq + 2) * 4 + 128)) != SO_OK) return rc;
-        uint32_t *d_slot_off = (uint32_t *)c->scratch[SC_SLOTOFF].p;
-        uint32_t *d_st = (uint32_t *)c->scratch[SC_ST].p, *d_cnt = (uint32_t *)c->scratch[SC_CNT].p;
-        uint64_t *d_out = (uint64_t *)c->scratch[SC_OUT].p;
+        if ((rc = scratch[SC_SLOTOFF].reserve(((size_t)nq + 1) * 4)) != SO_OK) return rc;
+        if ((rc = scratch[SC_ST].reserve((size_t)nslots * 4)) != SO_OK) return rc;
+        if ((rc = scratch[SC_CNT].reserve(((size_t)nslots + 1) * 4)) != SO_OK) return rc;
+        if ((rc = scratch[SC_OUT].reserve(((size_t)nslots + 1) * 8)) != SO_OK) return rc;
+        if ((rc = scratch[SC_MISC].reserve(((size_t)nq + 2) * 4 + 128)) != SO_OK) return rc;
+        uint32_t *d_slot_off = (uint32_t *)scratch[SC_SLOTOFF].p;
+        uint32_t *d_st = (uint32_t *)scratch[SC_ST].p, *d_cnt = (uint32_t *)scratch[SC_CNT].p;
+        uint64_t *d_out = (uint64_t *)scratch[SC_OUT].p;
         SO_CUDA(cudaMemcpyAsync(d_slot_off, slot_off.data(), ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, st));
-        c->stats.h2d_bytes += ((i64)nq + 1) * 4;
-        SO_CUDA(cudaEventRecord(c->ev[0], st));
+        stats.h2d_bytes += ((i64)nq + 1) * 4;
+        SO_CUDA(cudaEventRecord(ev[0], st));
         k_query_seeds<<<(nslots + 255) / 256, 256, 0, st>>>(c->d_qres, c->d_qoff, d_slot_off, g, ix.d_start, nslots, d_st,
                                                             d_cnt);
         k_filter<<<(nq * 32 + 255) / 256, 256, 0, st>>>(c->d_qoff, d_slot_off, c->d_perm, g, d_cnt);
@@ -1160,10 +1190,10 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
         size_t tmp = 0;
         cub::TransformInputIterator<uint64_t, Widen, const uint32_t *> cnt64(d_cnt, Widen());
         cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt64, d_out, (int)nslots + 1, st);
-        if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
-        SO_CUDA(cub::DeviceScan::ExclusiveSum(c->scratch[SC_TMP].p, tmp, cnt64, d_out, (int)nslots + 1, st));
-        c->stats.kernel_launches += 2;
-        c->stats.lib_launches += 1;
+        if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+        SO_CUDA(cub::DeviceScan::ExclusiveSum(scratch[SC_TMP].p, tmp, cnt64, d_out, (int)nslots + 1, st));
+        stats.kernel_launches += 2;
+        stats.lib_launches += 1;
         uint64_t H = 0;
         SO_CUDA(cudaMemcpyAsync(&H, d_out + nslots, 8, cudaMemcpyDeviceToHost, st));
         SO_CUDA(cudaStreamSynchronize(st));
@@ -1176,23 +1206,23 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             set_error("query %lld produces too many seed hits", (long long)b0);
             return SO_ELIMIT;
         }
-        c->stats.seed_hits += (i64)H;
+        stats.seed_hits += (i64)H;
         if (H > 0) {
-            if ((rc = c->scratch[SC_KA].reserve((size_t)H * 8)) != SO_OK) return rc;
-            if ((rc = c->scratch[SC_KB].reserve((size_t)H * 8)) != SO_OK) return rc;
+            if ((rc = scratch[SC_KA].reserve((size_t)H * 8)) != SO_OK) return rc;
+            if ((rc = scratch[SC_KB].reserve((size_t)H * 8)) != SO_OK) return rc;
             // one pattern + one alphabet: keys-only sort that skips the qst bits (see RankCtx)
             const bool keys_only = AS == 1 && !getenv("SO_FORCE_PAIRS");
             if (!keys_only) {
-                if ((rc = c->scratch[SC_VA].reserve((size_t)H * 4)) != SO_OK) return rc;
-                if ((rc = c->scratch[SC_VB].reserve((size_t)H * 4)) != SO_OK) return rc;
+                if ((rc = scratch[SC_VA].reserve((size_t)H * 4)) != SO_OK) return rc;
+                if ((rc = scratch[SC_VB].reserve((size_t)H * 4)) != SO_OK) return rc;
             }
-            uint64_t *ka = (uint64_t *)c->scratch[SC_KA].p, *kb = (uint64_t *)c->scratch[SC_KB].p;
-            uint32_t *va = keys_only ? nullptr : (uint32_t *)c->scratch[SC_VA].p;
-            uint32_t *vb = keys_only ? nullptr : (uint32_t *)c->scratch[SC_VB].p;
+            uint64_t *ka = (uint64_t *)scratch[SC_KA].p, *kb = (uint64_t *)scratch[SC_KB].p;
+            uint32_t *va = keys_only ? nullptr : (uint32_t *)scratch[SC_VA].p;
+            uint32_t *vb = keys_only ? nullptr : (uint32_t *)scratch[SC_VB].p;
             const int ewarps = 148 * 64;
             k_expand<<<ewarps * 32 / 256, 256, 0, st>>>(d_slot_off, g, nslots, c->d_qoff, d_st, d_cnt, d_out, ix.d_hdsst, ka,
                                                         va);
-            SO_CUDA(cudaEventRecord(c->ev[1], st));
+            SO_CUDA(cudaEventRecord(ev[1], st));
             const int key_bits = g.qst_bits + g.diag_bits + g.hd_bits + q_bits;
             // candidate sort key: query | first-appearance rank (see k_pair_select)
             const int rank_bits = (AS == 1 && !getenv("SO_FORCE_PAIRS")) ? g.qst_bits + g.diag_bits + g.hd_bits : 32;
@@ -1203,37 +1233,37 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             tmp = 0;
             if (keys_only) {
                 cub::DeviceRadixSort::SortKeys(nullptr, tmp, dk, (int)H, g.qst_bits, end_bit, st);
-                if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
-                SO_CUDA(cub::DeviceRadixSort::SortKeys(c->scratch[SC_TMP].p, tmp, dk, (int)H, g.qst_bits, end_bit, st));
+                if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+                SO_CUDA(cub::DeviceRadixSort::SortKeys(scratch[SC_TMP].p, tmp, dk, (int)H, g.qst_bits, end_bit, st));
             } else {
                 cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)H, 0, end_bit, st);
-                if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
-                SO_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch[SC_TMP].p, tmp, dk, dv, (int)H, 0, end_bit, st));
+                if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+                SO_CUDA(cub::DeviceRadixSort::SortPairs(scratch[SC_TMP].p, tmp, dk, dv, (int)H, 0, end_bit, st));
             }
-            SO_CUDA(cudaEventRecord(c->ev[2], st));
+            SO_CUDA(cudaEventRecord(ev[2], st));
             // candidates: at most one per (query, target) pair
             const uint64_t ccap = std::min<uint64_t>(H, (uint64_t)nq * (uint64_t)(M + 1));
-            if ((rc = c->scratch[SC_CKA].reserve((size_t)ccap * 8)) != SO_OK) return rc;
-            if ((rc = c->scratch[SC_CKB].reserve((size_t)ccap * 8)) != SO_OK) return rc;
-            if ((rc = c->scratch[SC_CVA].reserve((size_t)ccap * 8)) != SO_OK) return rc;
-            if ((rc = c->scratch[SC_CVB].reserve((size_t)ccap * 8)) != SO_OK) return rc;
-            uint64_t *cka = (uint64_t *)c->scratch[SC_CKA].p, *ckb = (uint64_t *)c->scratch[SC_CKB].p;
-            uint64_t *cva = (uint64_t *)c->scratch[SC_CVA].p, *cvb = (uint64_t *)c->scratch[SC_CVB].p;
-            unsigned long long *d_counter = (unsigned long long *)(c->scratch[SC_MISC].p);
-            uint32_t *d_bounds = (uint32_t *)(c->scratch[SC_MISC].p + 64);
+            if ((rc = scratch[SC_CKA].reserve((size_t)ccap * 8)) != SO_OK) return rc;
+            if ((rc = scratch[SC_CKB].reserve((size_t)ccap * 8)) != SO_OK) return rc;
+            if ((rc = scratch[SC_CVA].reserve((size_t)ccap * 8)) != SO_OK) return rc;
+            if ((rc = scratch[SC_CVB].reserve((size_t)ccap * 8)) != SO_OK) return rc;
+            uint64_t *cka = (uint64_t *)scratch[SC_CKA].p, *ckb = (uint64_t *)scratch[SC_CKB].p;
+            uint64_t *cva = (uint64_t *)scratch[SC_CVA].p, *cvb = (uint64_t *)scratch[SC_CVB].p;
+            unsigned long long *d_counter = (unsigned long long *)(scratch[SC_MISC].p);
+            uint32_t *d_bounds = (uint32_t *)(scratch[SC_MISC].p + 64);
             SO_CUDA(cudaMemsetAsync(d_counter, 0, 64, st));
             // diagonal groups: head flags -> exclusive scan -> compact head positions
             const int grp_shift = g.qst_bits;
-            if ((rc = c->scratch[SC_GIDX].reserve(((size_t)H + 1) * 4)) != SO_OK) return rc;
-            uint32_t *d_gidx = (uint32_t *)c->scratch[SC_GIDX].p;
+            if ((rc = scratch[SC_GIDX].reserve(((size_t)H + 1) * 4)) != SO_OK) return rc;
+            uint32_t *d_gidx = (uint32_t *)scratch[SC_GIDX].p;
             {
                 HeadFlag hf{dk.Current(), grp_shift};
                 cub::CountingInputIterator<uint32_t> cnt(0);
                 cub::TransformInputIterator<uint32_t, HeadFlag, cub::CountingInputIterator<uint32_t>> flags(cnt, hf);
                 tmp = 0;
                 cub::DeviceScan::ExclusiveSum(nullptr, tmp, flags, d_gidx, (int)H, st);
-                if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
-                SO_CUDA(cub::DeviceScan::ExclusiveSum(c->scratch[SC_TMP].p, tmp, flags, d_gidx, (int)H, st));
+                if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+                SO_CUDA(cub::DeviceScan::ExclusiveSum(scratch[SC_TMP].p, tmp, flags, d_gidx, (int)H, st));
             }
             // number of groups = gidx[H-1] + flag(H-1); read it back to size the group arrays
             uint32_t last_idx = 0;
@@ -1247,12 +1277,12 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                 bool flag = kl != ~0ull && (H < 2 || (last_keys[0] >> grp_shift) != (kl >> grp_shift));
                 G = last_idx + (flag ? 1u : 0u);
             }
-            c->stats.groups += (i64)G;
-            if ((rc = c->scratch[SC_GHEAD].reserve(((size_t)G + 1) * 4)) != SO_OK) return rc;
-            if ((rc = c->scratch[SC_GSCORE].reserve(((size_t)G + 1) * 4)) != SO_OK) return rc;
-            if ((rc = c->scratch[SC_GRANK].reserve(((size_t)G + 1) * 4)) != SO_OK) return rc;
-            uint32_t *d_gheads = (uint32_t *)c->scratch[SC_GHEAD].p, *d_gscore = (uint32_t *)c->scratch[SC_GSCORE].p;
-            uint32_t *d_grank = (uint32_t *)c->scratch[SC_GRANK].p;
+            stats.groups += (i64)G;
+            if ((rc = scratch[SC_GHEAD].reserve(((size_t)G + 1) * 4)) != SO_OK) return rc;
+            if ((rc = scratch[SC_GSCORE].reserve(((size_t)G + 1) * 4)) != SO_OK) return rc;
+            if ((rc = scratch[SC_GRANK].reserve(((size_t)G + 1) * 4)) != SO_OK) return rc;
+            uint32_t *d_gheads = (uint32_t *)scratch[SC_GHEAD].p, *d_gscore = (uint32_t *)scratch[SC_GSCORE].p;
+            uint32_t *d_grank = (uint32_t *)scratch[SC_GRANK].p;
             if (G > 0) {
                 // packed fast variants need < 8192 steps per extension and 32-bit residue indices
                 const bool fast_ungap = maxql < 8192 && ix.max_tlen < 8192 && c->q_off[(size_t)c->n_q] < 0xfff00000ull &&
@@ -1265,41 +1295,32 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                     // X-drop view of the sub-block's queries: (class << 3), forward + reversed
                     uint32_t qoff2[2], qtotal;
                     ung_layout((uint32_t)Lq64, qoff2, qtotal);
-                    if ((rc = c->scratch[SC_QUNG].reserve(qtotal)) != SO_OK) return rc;
-                    if ((rc = c->scratch[SC_DESC].reserve(((size_t)G + 1) * 8)) != SO_OK) return rc;
-                    if ((rc = c->scratch[SC_GKEY].reserve(((size_t)G + 1) * 8)) != SO_OK) return rc;
-                    uint8_t *d_qung = c->scratch[SC_QUNG].p;
-                    uint2 *d_desc = (uint2 *)c->scratch[SC_DESC].p;
-                    if ((rc = ung_build(c, c->d_qcls + qa, c->d_qoff + b0, (uint32_t)nq, qa, (uint32_t)Lq64, d_qung, qoff2, qtotal,
+                    if ((rc = scratch[SC_QUNG].reserve(qtotal)) != SO_OK) return rc;
+                    if ((rc = scratch[SC_DESC].reserve(((size_t)G + 1) * 8)) != SO_OK) return rc;
+                    if ((rc = scratch[SC_GKEY].reserve(((size_t)G + 1) * 8)) != SO_OK) return rc;
+                    uint8_t *d_qung = scratch[SC_QUNG].p;
+                    uint2 *d_desc = (uint2 *)scratch[SC_DESC].p;
+                    if ((rc = ung_build(st, stats, c->d_qcls + qa, c->d_qoff + b0, (uint32_t)nq, qa, (uint32_t)Lq64, d_qung, qoff2, qtotal,
                                         3)) != SO_OK)
                         return rc;
                     k_group_desc<<<(uint32_t)((H + 255) / 256), 256, 0, st>>>(dk.Current(), d_vals, (uint32_t)H, g, d_gidx, c->d_qoff,
                                                                              c->d_toff, qa, d_gheads, d_desc,
-                                                                             (uint64_t *)c->scratch[SC_GKEY].p, d_grank,
+                                                                             (uint64_t *)scratch[SC_GKEY].p, d_grank,
                                                                              d_counter);
-                    SO_CUDA(cudaEventRecord(c->ev[5], st));
-                    static int refill = 0;
-                    if (!refill) {
-                        const char *e = getenv("SO_XDROP_REFILL");  // tuning hook: idle lanes that trigger a refill
-                        refill = e ? atoi(e) : 16;
-                        SO_CUDA(cudaFuncSetAttribute(k_xdrop<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-                        SO_CUDA(cudaFuncSetAttribute(k_xdrop<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-                        SO_CUDA(cudaFuncSetAttribute(k_xdrop<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-                        SO_CUDA(cudaFuncSetAttribute(k_xdrop<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-                        SO_CUDA(cudaFuncSetAttribute(k_xdrop<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-                    }
+                    SO_CUDA(cudaEventRecord(ev[5], st));
+                    const int refill = g_xdrop_refill;
                     auto kx = refill <= 8 ? k_xdrop<8> : refill <= 12 ? k_xdrop<12> : refill <= 16 ? k_xdrop<16>
                               : refill <= 20 ? k_xdrop<20> : k_xdrop<24>;
                     kx<<<148 * 2, 512, kUngTabBytes, st>>>(d_desc, G, dk.Current(), d_vals, (uint32_t)H, d_gheads, g.qst_bits,
                                                           (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
                                                           (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
                                                           qoff2[1], (uint32_t)Lq64, d_gscore, d_grank, d_counter, 1);
-                    d_gkey = (const uint64_t *)c->scratch[SC_GKEY].p;
-                    c->stats.kernel_launches += 2;
+                    d_gkey = (const uint64_t *)scratch[SC_GKEY].p;
+                    stats.kernel_launches += 2;
                 } else {
                     k_scatter_heads<<<(uint32_t)((H + 255) / 256), 256, 0, st>>>(dk.Current(), (uint32_t)H, grp_shift, d_gidx, d_gheads);
-                    SO_CUDA(cudaEventRecord(c->ev[5], st));
-                    c->stats.kernel_launches += 1;
+                    SO_CUDA(cudaEventRecord(ev[5], st));
+                    stats.kernel_launches += 1;
                 }
                 if (!single_path) {
                     int per_sm = 4;
@@ -1307,34 +1328,34 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                     const int ublocks = 148 * std::max(1, per_sm);
                     k_group_ungap_generic<<<ublocks, 256, 0, st>>>(dk.Current(), d_vals, (uint32_t)H, d_gheads, G, g, c->d_qcls,
                                                                    c->d_qoff, c->d_tcls, c->d_toff, d_gscore, d_grank, d_counter);
-                    c->stats.kernel_launches += 1;
+                    stats.kernel_launches += 1;
                 }
-                SO_CUDA(cudaEventRecord(c->ev[6], st));
+                SO_CUDA(cudaEventRecord(ev[6], st));
                 k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, d_gkey, G, g, d_gscore,
                                                                keys_only ? nullptr : d_grank, rank_bits, cka, cva, d_counter);
-                c->stats.kernel_launches += 1;
-                c->stats.lib_launches += 1;
+                stats.kernel_launches += 1;
+                stats.lib_launches += 1;
             }
-            SO_CUDA(cudaEventRecord(c->ev[3], st));
+            SO_CUDA(cudaEventRecord(ev[3], st));
             unsigned long long h_counter[4] = {0, 0, 0, 0};
             SO_CUDA(cudaMemcpyAsync(h_counter, d_counter, 32, cudaMemcpyDeviceToHost, st));
             SO_CUDA(cudaStreamSynchronize(st));
             const unsigned long long ncand = h_counter[0];
-            c->stats.ungap_steps += (i64)h_counter[1];
-            c->stats.multi_groups += (i64)h_counter[3];
+            stats.ungap_steps += (i64)h_counter[1];
+            stats.multi_groups += (i64)h_counter[3];
             SO_CUDA(cudaGetLastError());
-            c->stats.kernel_launches += 1;
-            c->stats.lib_launches += 1;
+            stats.kernel_launches += 1;
+            stats.lib_launches += 1;
             std::vector<uint32_t> bounds((size_t)nq + 1, 0);
             const size_t base_c = out.n;
             if (ncand > 0) {
                 cub::DoubleBuffer<uint64_t> ck(cka, ckb), cv(cva, cvb);
                 tmp = 0;
                 cub::DeviceRadixSort::SortPairs(nullptr, tmp, ck, cv, (int)ncand, 0, rank_bits + q_bits, st);
-                if ((rc = c->scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
-                SO_CUDA(cub::DeviceRadixSort::SortPairs(c->scratch[SC_TMP].p, tmp, ck, cv, (int)ncand, 0, rank_bits + q_bits, st));
+                if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+                SO_CUDA(cub::DeviceRadixSort::SortPairs(scratch[SC_TMP].p, tmp, ck, cv, (int)ncand, 0, rank_bits + q_bits, st));
                 k_query_bounds<<<(nq + 1 + 127) / 128, 128, 0, st>>>(ck.Current(), (uint32_t)ncand, nq, rank_bits, d_bounds);
-                SO_CUDA(cudaEventRecord(c->ev[4], st));
+                SO_CUDA(cudaEventRecord(ev[4], st));
                 Timer td;
                 if ((rc = out.reserve(base_c + (size_t)ncand)) != SO_OK) return rc;
                 SO_CUDA(cudaMemcpyAsync(out.vals + base_c, cv.Current(), (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
@@ -1342,24 +1363,24 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                 SO_CUDA(cudaStreamSynchronize(st));
                 SO_CUDA(cudaGetLastError());
                 out.n = base_c + (size_t)ncand;
-                c->stats.kernel_launches += 1;
-                c->stats.lib_launches += 1;
-                c->stats.d2h_bytes += (i64)ncand * 8 + ((i64)nq + 1) * 4;
+                stats.kernel_launches += 1;
+                stats.lib_launches += 1;
+                stats.d2h_bytes += (i64)ncand * 8 + ((i64)nq + 1) * 4;
                 float ms = 0;
-                cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
-                c->stats.ms_select += ms;
-                c->prof.d2h_ms += td.ms();
+                cudaEventElapsedTime(&ms, ev[3], ev[4]);
+                stats.ms_select += ms;
+                c->d2h_ms_lane[lane] += td.ms();
             }
             float ms = 0;
-            cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-            c->stats.ms_seed += ms;
-            cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
-            c->stats.ms_sort += ms;
-            cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
-            c->stats.ms_ungap += ms;
+            cudaEventElapsedTime(&ms, ev[0], ev[1]);
+            stats.ms_seed += ms;
+            cudaEventElapsedTime(&ms, ev[1], ev[2]);
+            stats.ms_sort += ms;
+            cudaEventElapsedTime(&ms, ev[2], ev[3]);
+            stats.ms_ungap += ms;
             if (G > 0) {
-                cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]);
-                c->stats.ms_ungap_kernel += ms;
+                cudaEventElapsedTime(&ms, ev[5], ev[6]);
+                stats.ms_ungap_kernel += ms;
             }
             for (int k = 0; k < nq; k++)
                 out.offsets[(size_t)(b0 - q_begin + k + 1)] = (uint64_t)base_c + bounds[(size_t)k + 1];
@@ -1378,7 +1399,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
         }
         b0 = b1;
     }
-    c->stats.candidates += (i64)out.n;
+    stats.candidates += (i64)out.n;
     return SO_OK;
 }
 
