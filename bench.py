@@ -179,7 +179,7 @@ def workload_config(args, block):
 
 # ----------------------------------------------------------------------------------------- GPU arm
 # positions in the per-rank value vector that are combined with MAX (times); the rest are summed (work)
-MAX_IDX = (0, 1, 5, 6, 7, 8, 9, 10, 11, 16, 17)  # 18, 19 (GCUPS) are summed over ranks
+MAX_IDX = (0, 1, 5, 6, 7, 8, 9, 10, 11, 16, 17, 20)  # 18, 19 (GCUPS) are summed over ranks
 
 
 def reduce_over_ranks(vals, dist, device):
@@ -241,6 +241,21 @@ def run_ours(args, rank, world, local):
     st = S.stats(reset=True)
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- kernel-timing pass: the same steps with ONE production lane, so the CUDA-event stage times
+    #      inside so_search are not inflated by the second lane's kernels sharing the GPU.  The roofline
+    #      figures (kernel durations) come from this pass; `value` above is the two-lane pipeline.
+    S.set_lanes(1)
+    S.search(*block_of(args.warmup + args.steps))
+    S.stats(reset=True)
+    ksteps = max(1, min(2, args.steps))
+    for s in range(ksteps):
+        S.search(*block_of(args.warmup + s))
+    st = dict(st)
+    stk = S.stats(reset=True)
+    S.set_lanes(2)
+    for k in ('ms_ungap', 'ms_ungap_kernel', 'ms_sort', 'ms_seed', 'ms_select'):
+        st[k] = stk[k] * args.steps / ksteps      # same blocks as the first `ksteps` timed steps
+
     # ---- end-to-end arm: host buffers -> public API -> text rows, every step
     import ctypes as C
     import numpy as np
@@ -298,28 +313,44 @@ def run_ours(args, rank, world, local):
     vals = [dt, dt2, float(nq), float(e2e_q), float(st['dp_cells']), st['ms_dp'], st['ms_ungap'], st['ms_sort'],
             st['ms_seed'], st['ms_select'], st['ms_traceback'], st['ms_host'], float(st['seed_hits']),
             float(st['kernel_launches']), float(st['ungap_steps']), float(st['alignments']),
-            float(st2['h2d_bytes']), float(st2['d2h_bytes']), gcups_alone, gcups_alone_tb]
+            float(st2['h2d_bytes']), float(st2['d2h_bytes']), gcups_alone, gcups_alone_tb,
+            st['ms_ungap_kernel'], float(st['groups']), float(st['multi_groups'])]
     vals = reduce_over_ranks(vals, dist, 'cuda' if dist is not None else None)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     (dt, dt2, nq, e2e_q, cells, ms_dp, ms_ungap, ms_sort, ms_seed, ms_select, ms_tb, ms_host, seed_hits, launches,
-     ungap_steps, alignments, h2d, d2h, gcups_alone, gcups_alone_tb) = vals
+     ungap_steps, alignments, h2d, d2h, gcups_alone, gcups_alone_tb, ms_xdrop, groups, multi_groups) = vals
     value = nq / dt
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(
         os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     int_peak = json.load(open(os.path.join(ROOT, 'profiles', 'int_peak.json')))
-    # dominant kernel of the step = chained X-drop scoring (k_group_ungap): integer-pipe bound
-    # (6 INT ops per extension step); peak = measured INT32 op rate of this chip
+    # dominant kernel of the step = chained X-drop scoring (k_xdrop): integer-pipe bound
+    # (6 INT ops per extension step); peak = measured INT32 op rate of this chip.
+    # Durations: CUDA events around the kernel inside so_search, single-lane pass (see above).
     ops = 6.0 * ungap_steps / max(world, 1)
-    ach = ops / (ms_ungap * 1e-3) / 1e9 if ms_ungap > 0 else 0.0
-    roof = {'kernel': 'k_group_ungap', 'bound': 'int32', 'achieved': ach, 'peak': int_peak['gops_measured'],
-            'unit': 'Gop/s', 'frac': ach / int_peak['gops_measured'], 'traffic': None,
+    ach = ops / (ms_xdrop * 1e-3) / 1e9 if ms_xdrop > 0 else 0.0
+    dev_ms = max(1e-9, ms_ungap + ms_sort + ms_seed + ms_select + ms_dp + ms_tb)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_xdrop_r01.json')))
+    except Exception:  # noqa: BLE001
+        pass
+    roof = {'kernel': 'k_xdrop', 'bound': 'int32', 'achieved': ach, 'peak': int_peak['gops_measured'],
+            'unit': 'Gop/s', 'frac': ach / int_peak['gops_measured'],
+            'traffic': traffic.get('dram_bytes_per_launch') if traffic else None,
+            'traffic_note': traffic.get('note') if traffic else None,
             'peak_source': 'tools/int_peak.cu measured on this pool (profiles/int_peak.json)',
-            'share_of_step_device_time': ms_ungap / max(1e-9, ms_ungap + ms_sort + ms_seed + ms_select + ms_dp + ms_tb)}
-    # HBM view of the library radix sort (second largest): 8 passes x (12 B read + 12 B write) per hit
-    sort_bytes = seed_hits / max(world, 1) * 24.0 * 7
+            'algorithmic_ops': '6 INT ops per X-drop extension step (SURVEY.md 8d) x %.3g steps per step' % (
+                ungap_steps / max(world, 1) / args.steps),
+            'ms_per_step': ms_xdrop / args.steps, 'share_of_step_device_time': ms_xdrop / dev_ms,
+            'groups_per_step': groups / max(world, 1) / args.steps,
+            'chained_groups_per_step': multi_groups / max(world, 1) / args.steps,
+            'timing': 'CUDA events on the launching stream inside so_search, one production lane'}
+    # HBM view of the library radix sort (second largest): keys-only onesweep, 5 passes x (8 B read + 8 B
+    # write) + one 8 B histogram read per seed hit
+    sort_bytes = seed_hits / max(world, 1) * (16.0 * 5 + 8.0)
     hbm = {'kernel': 'cub radix sort (library)', 'bound': 'hbm', 'achieved': sort_bytes / (ms_sort * 1e-3) / 1e9 if ms_sort else 0,
            'peak': peaks.get('hbm_gbs', 6650.0), 'unit': 'GB/s',
            'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback B200_PROFILING.md'}

@@ -185,6 +185,10 @@ typedef struct so_stats {
     int64_t multi_groups;    /* diagonal groups holding more than one seed (chained path)            */
 } so_stats;
 int so_stats_get(const so_ctx *c, so_stats *s);
+/* tuning hooks (no reference counterpart): queries per seeding sub-block (0 = adaptive), and the number
+ * of candidate-production lanes (streams) so_search overlaps (1 or 2, default 2) */
+int so_set_sub_block(so_ctx *c, int64_t n);
+int so_set_lanes(so_ctx *c, int n);
 int so_stats_reset(so_ctx *c);
 
 #ifdef __cplusplus

@@ -91,6 +91,8 @@ SYMBOLS = {
     'so_write_rows': (C.c_int, [_P(so_hit), C.c_int64, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]),
     'so_stats_get': (C.c_int, [C.c_void_p, _P(so_stats)]),
     'so_stats_reset': (C.c_int, [C.c_void_p]),
+    'so_set_sub_block': (C.c_int, [C.c_void_p, C.c_int64]),
+    'so_set_lanes': (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 _lib = None
@@ -109,8 +111,6 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    lib.so_set_sub_block.restype = C.c_int
-    lib.so_set_sub_block.argtypes = [C.c_void_p, C.c_int64]
     if lib.so_abi_version() != 1:
         raise SoError('ABI mismatch')
     _lib = lib

@@ -407,6 +407,14 @@ int so_set_sub_block(so_ctx *c, int64_t n) {
     return SO_OK;
 }
 
+// test / tuning hook: number of candidate-production lanes used by so_search (1 or 2; default 2).  bench.py
+// uses 1 to time the kernels of a step without a second stream sharing the GPU.
+int so_set_lanes(so_ctx *c, int n) {
+    if (!c || n < 1 || n > 2) return SO_EINVAL;
+    c->n_lanes = n;
+    return SO_OK;
+}
+
 int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int64_t *n_rows) {
     if (!c || !rows_out || !n_rows || q_begin < 0 || q_end > c->n_q || q_begin > q_end) {
         set_error("so_search: bad argument");
@@ -443,7 +451,8 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     std::condition_variable cv;
     std::map<int, Job> jobs;  // by block number
     int next_blk = 0;         // next block the worker consumes
-    int producers_left = 2;
+    const int nprod = c->n_lanes >= 2 ? 2 : 1;
+    int producers_left = nprod;
     bool abort_all = false;
     bool producer_done = false, slot_busy[kSlots] = {false, false, false, false};
     int worker_rc = SO_OK;
@@ -687,7 +696,7 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     auto produce = [&](int pid) {
         cudaSetDevice(c->device);
         int rc = SO_OK;
-        for (int blk = pid;; blk += 2) {
+        for (int blk = pid;; blk += nprod) {
             const i64 b0 = q_begin + (i64)blk * QB;
             if (b0 >= q_end || rc != SO_OK) break;
             const i64 b1 = std::min<i64>(q_end, b0 + QB);
@@ -717,9 +726,10 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
         if (--producers_left == 0) producer_done = true;
         cv.notify_all();
     };
-    std::thread producer1(produce, 1);
+    std::thread producer1;
+    if (nprod == 2) producer1 = std::thread(produce, 1);
     produce(0);
-    producer1.join();
+    if (nprod == 2) producer1.join();
     const int prod_rc = prod_rcs[0] != SO_OK ? prod_rcs[0] : prod_rcs[1];
     const std::string prod_err = prod_rcs[0] != SO_OK ? prod_errs[0] : prod_errs[1];
     worker.join();

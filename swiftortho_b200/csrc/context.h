@@ -146,6 +146,7 @@ struct so_ctx {
     cudaStream_t stream1 = nullptr;
     cudaEvent_t ev1[8] = {};
     so_stats stats_lane[2] = {};
+    int n_lanes = 2;
     double d2h_ms_lane[2] = {0, 0};
     so::DBuf<uint64_t> trace;
     void *h_pinned = nullptr;

@@ -49,6 +49,9 @@ class Fasta:
             return ['', '']
         return [self.header(i), self.sequence(i)]
 
+    def set_lanes(self, n):
+        check(self.lib.so_set_lanes(self.h, int(n)))
+
     def close(self):
         if self.h:
             self.lib.so_fasta_close(self.h)
@@ -142,6 +145,9 @@ class Searcher:
 
     def set_sub_block(self, n):
         check(self.lib.so_set_sub_block(self.h, int(n)))
+
+    def set_lanes(self, n):
+        check(self.lib.so_set_lanes(self.h, int(n)))
 
     def close(self):
         if self.h:
