@@ -954,40 +954,47 @@ __device__ __forceinline__ uint32_t recompute_rank(const RankCtx &rc, int qi, in
     return (uint32_t)rc.slot_out[slot] + lo;
 }
 
-// one thread per diagonal group; the first group of a (query, target) pair folds the pair:
-// threshold 25, best diagonal (first appearance wins ties), candidate order = first passing rank.
-// gkey (optional): the head key of every group, written by k_group_desc, so the scan over a pair's
-// groups reads consecutive words instead of chasing gheads into the hit array.  The first-appearance
-// rank of a group is grank[] when the hit ordinals were carried through the sort; on the keys-only path
-// (one pattern, one alphabet) the ordinal order is (qst ascending, then the bucket's descending
-// (sequence, position) order), so the rank is rebuilt from the key itself:
+// Pair selection over the PASSING groups only (score >= 25, self.min: fsearch.py:2224, 2707): `plist` holds
+// their group indices in ascending order (ordered stream compaction, cub::DeviceSelect), ~8 % of all groups.
+// One thread per passing group; the first passing group of a (query, target) pair folds the pair: best
+// diagonal (first appearance wins ties), candidate order = first passing rank.  gkey = head key of every
+// group.  The first-appearance rank of a group is grank[] when the hit ordinals were carried through the
+// sort; on the keys-only path (one pattern, one alphabet) the ordinal order is (qst ascending, then the
+// bucket's descending (sequence, position) order), so the rank is rebuilt from the key itself:
 // qst | (max - sequence) | (max - sst).  Output slots are claimed with one atomic per block.
-__global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ gheads,
-                                                     const uint64_t *__restrict__ gkey,
-                                                     uint32_t G, BlockGeom g, const uint32_t *__restrict__ gscore,
+struct PassPred {
+    const uint32_t *gscore;
+    __host__ __device__ __forceinline__ bool operator()(const uint32_t &gi) const { return gscore[gi] >= 25u; }
+};
+
+__global__ void __launch_bounds__(256) k_pair_select(const uint32_t *__restrict__ plist, const uint32_t *__restrict__ pcount,
+                                                     const uint64_t *__restrict__ gkey, BlockGeom g,
+                                                     const uint32_t *__restrict__ gscore,
                                                      const uint32_t *__restrict__ grank, int rank_bits,
                                                      uint64_t *__restrict__ ckeys, uint64_t *__restrict__ cvals,
                                                      unsigned long long *__restrict__ counters) {
     __shared__ uint32_t s_wcount[8];
     __shared__ unsigned long long s_base;
-    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = *pcount;
     const int pair_shift = g.qst_bits + g.diag_bits;
-    const uint64_t dmask = (1ull << g.diag_bits) - 1;
-    bool head = false;
-    uint64_t pair = 0;
-    if (gi < G) {
-        pair = (gkey ? gkey[gi] : keys[gheads[gi]]) >> pair_shift;
-        head = gi == 0 || ((gkey ? gkey[gi - 1] : keys[gheads[gi - 1]]) >> pair_shift) != pair;
-    }
-    int best_score = 0, best_diag = 0;
-    uint64_t best_rank = ~0ull, first_rank = ~0ull;
-    const uint64_t hdmask = (1ull << g.hd_bits) - 1;
-    if (head) {
-        for (uint32_t k = gi; k < G; k++) {
-            const uint64_t kk = gkey ? gkey[k] : keys[gheads[k]];
-            if ((kk >> pair_shift) != pair) break;
-            const int sc = (int)gscore[k];
-            if (sc >= 25) {  // self.min (fsearch.py:2224, 2707)
+    const uint64_t dmask = (1ull << g.diag_bits) - 1, hdmask = (1ull << g.hd_bits) - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {  // block-uniform trip count
+        const uint32_t i = i0 + threadIdx.x;
+        bool head = false;
+        uint64_t pair = 0;
+        if (i < n) {
+            pair = gkey[plist[i]] >> pair_shift;
+            head = i == 0 || (gkey[plist[i - 1]] >> pair_shift) != pair;
+        }
+        int best_score = 0, best_diag = 0;
+        uint64_t best_rank = ~0ull, first_rank = ~0ull;
+        if (head) {
+            for (uint32_t j = i; j < n; j++) {
+                const uint32_t k = plist[j];
+                const uint64_t kk = gkey[k];
+                if ((kk >> pair_shift) != pair) break;
+                const int sc = (int)gscore[k];
                 const int dg = (int)((kk >> g.qst_bits) & dmask) - g.diag_bias;
                 uint64_t rk;
                 if (grank)
@@ -1005,30 +1012,29 @@ __global__ void __launch_bounds__(256) k_pair_select(const uint64_t *__restrict_
                 }
             }
         }
-    }
-    const bool emit = head && best_score >= 25;
-    const unsigned m = __ballot_sync(0xffffffffu, emit);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) s_wcount[warp] = (uint32_t)__popc(m);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int w = 0; w < 8; w++) {
-            const uint32_t n = s_wcount[w];
-            s_wcount[w] = tot;
-            tot += n;
+        const unsigned m = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) s_wcount[warp] = (uint32_t)__popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; w++) {
+                const uint32_t c = s_wcount[w];
+                s_wcount[w] = tot;
+                tot += c;
+            }
+            s_base = tot ? atomicAdd(counters, (unsigned long long)tot) : 0ull;
         }
-        s_base = tot ? atomicAdd(counters, (unsigned long long)tot) : 0ull;
-    }
-    __syncthreads();
-    if (emit) {
-        const unsigned long long o = s_base + s_wcount[warp] + __popc(m & ((1u << lane) - 1));
-        const int hd1 = (int)(pair & hdmask);
-        const int qi = (int)(pair >> g.hd_bits);
-        ckeys[o] = ((uint64_t)qi << rank_bits) | first_rank;
-        // value: target ordinal (24 bits) | score (20 bits) | diagonal + bias (20 bits)
-        cvals[o] = ((uint64_t)(uint32_t)(g.c0 + hd1 - 1) << 40) | ((uint64_t)(uint32_t)best_score << 20) |
-                   (uint64_t)(uint32_t)(best_diag + kCandDiagBias);
+        __syncthreads();
+        if (head) {
+            const unsigned long long o = s_base + s_wcount[warp] + __popc(m & ((1u << lane) - 1));
+            const int hd1 = (int)(pair & hdmask);
+            const int qi = (int)(pair >> g.hd_bits);
+            ckeys[o] = ((uint64_t)qi << rank_bits) | first_rank;
+            // value: target ordinal (24 bits) | score (20 bits) | diagonal + bias (20 bits)
+            cvals[o] = ((uint64_t)(uint32_t)(g.c0 + hd1 - 1) << 40) | ((uint64_t)(uint32_t)best_score << 20) |
+                       (uint64_t)(uint32_t)(best_diag + kCandDiagBias);
+        }
+        __syncthreads();
     }
 }
 
@@ -1074,7 +1080,7 @@ static int bits_for(uint64_t maxval) {  // bits needed to hold values 0..maxval
 }
 
 enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TMP, SC_CKA, SC_CKB, SC_CVA, SC_CVB, SC_MISC,
-       SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK, SC_QUNG, SC_DESC, SC_MLIST, SC_GKEY };
+       SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK, SC_QUNG, SC_DESC, SC_MLIST, SC_GKEY, SC_PLIST };
 
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
 
@@ -1331,8 +1337,26 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                     stats.kernel_launches += 1;
                 }
                 SO_CUDA(cudaEventRecord(ev[6], st));
-                k_pair_select<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, d_gkey, G, g, d_gscore,
-                                                               keys_only ? nullptr : d_grank, rank_bits, cka, cva, d_counter);
+                if (!d_gkey) {
+                    if ((rc = scratch[SC_GKEY].reserve(((size_t)G + 1) * 8)) != SO_OK) return rc;
+                    k_gather_keys<<<(G + 255) / 256, 256, 0, st>>>(dk.Current(), d_gheads, G, (uint64_t *)scratch[SC_GKEY].p);
+                    d_gkey = (const uint64_t *)scratch[SC_GKEY].p;
+                    stats.kernel_launches += 1;
+                }
+                // ordered compaction of the passing groups (library), then the pair fold over that list
+                if ((rc = scratch[SC_PLIST].reserve(((size_t)G + 2) * 4)) != SO_OK) return rc;
+                uint32_t *d_plist = (uint32_t *)scratch[SC_PLIST].p;
+                uint32_t *d_pcount = (uint32_t *)(d_counter + 5);
+                {
+                    cub::CountingInputIterator<uint32_t> gi0(0);
+                    PassPred pred{d_gscore};
+                    tmp = 0;
+                    cub::DeviceSelect::If(nullptr, tmp, gi0, d_plist, d_pcount, (int)G, pred, st);
+                    if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+                    SO_CUDA(cub::DeviceSelect::If(scratch[SC_TMP].p, tmp, gi0, d_plist, d_pcount, (int)G, pred, st));
+                }
+                k_pair_select<<<148 * 8, 256, 0, st>>>(d_plist, d_pcount, d_gkey, g, d_gscore, keys_only ? nullptr : d_grank,
+                                                       rank_bits, cka, cva, d_counter);
                 stats.kernel_launches += 1;
                 stats.lib_launches += 1;
             }
