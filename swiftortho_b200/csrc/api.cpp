@@ -24,7 +24,8 @@ static void parallel_for(i64 n, F f) {
     unsigned nt = std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;
     if (nt > 32) nt = 32;
-    if (n < 64 || nt == 1) {
+    if ((i64)nt > n) nt = (unsigned)std::max<i64>(n, 1);
+    if (n < 4 || nt == 1) {
         for (i64 i = 0; i < n; i++) f(i);
         return;
     }
@@ -33,9 +34,10 @@ static void parallel_for(i64 n, F f) {
     for (unsigned t = 0; t < nt; t++)
         th.emplace_back([&]() {
             for (;;) {
-                i64 i0 = next.fetch_add(16);
+                const i64 step = n >= 1024 ? 16 : 1;
+                i64 i0 = next.fetch_add(step);
                 if (i0 >= n) return;
-                for (i64 i = i0; i < std::min<i64>(n, i0 + 16); i++) f(i);
+                for (i64 i = i0; i < std::min<i64>(n, i0 + step); i++) f(i);
             }
         });
     for (auto &t : th) t.join();
@@ -284,6 +286,7 @@ int so_set_queries(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, 
         uint32_t *pp = perm.data() + qo[q];
         for (i64 i = 0; i < P; i++) pp[i] = (uint32_t)v[(size_t)i];
     });
+    const double t_host = tm.ms();
     SO_CUDA(cudaMalloc((void **)&c->d_qres, bytes + 64));
     SO_CUDA(cudaMalloc((void **)&c->d_qoff, ((size_t)n + 1) * 8));
     SO_CUDA(cudaMalloc((void **)&c->d_perm, (bytes + 16) * 4));
@@ -295,6 +298,7 @@ int so_set_queries(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, 
     SO_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.h2d_bytes += (i64)bytes * 5 + ((i64)n + 1) * 8;
     c->stats.ms_host += tm.ms();
+    if (getenv("SO_PROFILE")) fprintf(stderr, "so_set_queries: host (seg + S3 order) %.1f ms, total %.1f ms\n", t_host, tm.ms());
     return SO_OK;
 }
 
@@ -774,48 +778,53 @@ int so_write_rows(const so_hit *rows, int64_t n, const so_fasta *queries, const 
         set_error("cannot open %s for writing", path);
         return SO_EIO;
     }
-    std::string buf;
-    buf.reserve(1 << 20);
-    char num[256];
-    for (int64_t k = 0; k < n; k++) {
-        const so_hit &r = rows[k];
-        const char *hq, *ht;
-        int64_t lq, lt;
-        if (so_fasta_header(queries, r.query, &hq, &lq) != SO_OK || so_fasta_header(targets, r.target, &ht, &lt) != SO_OK) {
-            fclose(f);
-            return SO_EINVAL;
-        }
-        // ids = header up to the first space (fsearch.py:3066)
-        int64_t iq = 0, it = 0;
-        while (iq < lq && hq[iq] != ' ') iq++;
-        while (it < lt && ht[it] != ' ') it++;
-        buf.append(hq, (size_t)iq);
-        buf += '\t';
-        buf.append(ht, (size_t)it);
-        buf += '\t';
-        buf += so::fmt_identity(r.identity);
-        snprintf(num, sizeof num, "\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t", r.aln_len, r.mismatch, r.gaps, r.qst, r.qed, r.sst,
-                 r.sed);
-        buf += num;
-        buf += so::f2s(r.evalue);
-        snprintf(num, sizeof num, "\t%lld\t%d\t%d\t%lld\t", (long long)r.bit, r.qlen, r.tlen, (long long)r.query);
-        buf += num;
-        buf.append(ht, (size_t)lt);
-        buf += '\n';
-        if (buf.size() > (1 << 20) - 4096) {
-            if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
-                fclose(f);
-                set_error("short write on %s", path);
-                return SO_EIO;
+    // rows are formatted by all host threads in contiguous slices and written in order
+    const int64_t kSlice = 2048;
+    const int64_t nslices = (n + kSlice - 1) / kSlice;
+    std::vector<std::string> bufs((size_t)nslices);
+    std::atomic<int> bad(0);
+    so::parallel_for(nslices, [&](so::i64 sl) {
+        std::string &buf = bufs[(size_t)sl];
+        buf.reserve((size_t)kSlice * 160);
+        char num[256];
+        const int64_t k1 = std::min<int64_t>(n, (sl + 1) * kSlice);
+        for (int64_t k = sl * kSlice; k < k1; k++) {
+            const so_hit &r = rows[k];
+            const char *hq, *ht;
+            int64_t lq, lt;
+            if (so_fasta_header(queries, r.query, &hq, &lq) != SO_OK || so_fasta_header(targets, r.target, &ht, &lt) != SO_OK) {
+                bad = 1;
+                return;
             }
-            buf.clear();
+            // ids = header up to the first space (fsearch.py:3066)
+            int64_t iq = 0, it = 0;
+            while (iq < lq && hq[iq] != ' ') iq++;
+            while (it < lt && ht[it] != ' ') it++;
+            buf.append(hq, (size_t)iq);
+            buf += '\t';
+            buf.append(ht, (size_t)it);
+            buf += '\t';
+            buf += so::fmt_identity(r.identity);
+            snprintf(num, sizeof num, "\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t", r.aln_len, r.mismatch, r.gaps, r.qst, r.qed, r.sst,
+                     r.sed);
+            buf += num;
+            buf += so::f2s(r.evalue);
+            snprintf(num, sizeof num, "\t%lld\t%d\t%d\t%lld\t", (long long)r.bit, r.qlen, r.tlen, (long long)r.query);
+            buf += num;
+            buf.append(ht, (size_t)lt);
+            buf += '\n';
         }
-    }
-    if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
+    });
+    if (bad) {
         fclose(f);
-        set_error("short write on %s", path);
-        return SO_EIO;
+        return SO_EINVAL;
     }
+    for (const std::string &buf : bufs)
+        if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
+            fclose(f);
+            set_error("short write on %s", path);
+            return SO_EIO;
+        }
     fclose(f);
     return SO_OK;
 }

@@ -147,6 +147,23 @@ int parse_params(const so_params *p, Params &o) {
 // first appearance, and the sliding update keeps the reference's `b != 0 and X or Y` fall-through
 // (a zero X selects Y).  All arithmetic in double, libm log, same operation order.
 // ---------------------------------------------------------------------------------------------
+// (k / 12) * log(k / 12) for integer-valued k in [0, 64), computed once with the expressions seg_mask uses
+struct XLogXTable {
+    double v[64];
+    XLogXTable() {
+        for (int k = 0; k < 64; k++) {
+            double a = (double)k / 12.;
+            v[k] = a * std::log(a);
+        }
+    }
+};
+static const XLogXTable kXLogX;
+static inline double xlogx(double count, double a) {
+    const int k = (int)count;
+    if (k >= 0 && k < 64 && (double)k == count) return kXLogX.v[k];
+    return a * std::log(a);
+}
+
 void seg_mask(const uint8_t *in, i64 n, uint8_t *out) {
     if (n <= 0) return;
     const double W = 12., MINENT = 2.2;
@@ -188,20 +205,22 @@ void seg_mask(const uint8_t *in, i64 n, uint8_t *out) {
         double in_before = known[in_c] ? tally[in_c] : 0.0;
         if (!known[in_c]) known[in_c] = true, tally[in_c] = 0;
         tally[in_c] += 1;
+        // a * log(a) for a = k / 12 comes from a table filled with the same expression (same libm call, same
+        // bits); tallies are small integers by construction
         double a = before / W, b = tally[out_c] / W;
-        double alt = a * std::log(a) / ln2;
+        double alt = xlogx(before, a) / ln2;
         double delta = alt;
         if (b != 0) {
-            double x = (a * std::log(a) - b * std::log(b)) / ln2;
+            double x = (xlogx(before, a) - xlogx(tally[out_c], b)) / ln2;
             if (x != 0) delta = x;
         }
         ent += delta;
         a = in_before / W;
         b = tally[in_c] / W;
-        alt = -b * std::log(b) / ln2;
+        alt = -xlogx(tally[in_c], b) / ln2;
         delta = alt;
         if (a != 0) {
-            double x = (a * std::log(a) - b * std::log(b)) / ln2;
+            double x = (xlogx(in_before, a) - xlogx(tally[in_c], b)) / ln2;
             if (x != 0) delta = x;
         }
         ent += delta;
