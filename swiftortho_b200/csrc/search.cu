@@ -401,6 +401,126 @@ __global__ void __launch_bounds__(256) k_expand(const uint32_t *__restrict__ slo
 }
 
 // ---------------------------------------------------------------------------------------------
+// Hit grouping without a global sort (keys-only path).
+//
+// The seed hits of a query arrive as ~200 bucket lists, each already in descending (sequence, position)
+// order.  Instead of a 5-pass device-wide radix sort of 64-bit keys, they are
+//   1. counted per (query, target block) cell, target block = sequence >> S  (k_cell_pass<false>: one CTA
+//      per query, shared-memory histogram, runs of equal cells inside a warp-row folded into one atomic),
+//   2. exclusive-scanned (cub::DeviceScan on the small cell array),
+//   3. scattered into their cell (k_cell_pass<true>: same traversal, shared-memory cursors), and
+//   4. sorted inside each cell in shared memory (k_cell_sort: cub::BlockRadixSort on the 32-bit cell-local
+//      part of the key: sequence low bits | diagonal | qst).
+// Each hit is read twice from the index (8 B) and its key written/read/written once more; the result is the
+// same fully sorted key array the radix sort produced, minus the hits the reference attributes to
+// "sequence -1" (they can never score and were only sorted to the end before).
+// Cells larger than kCellMax fall back to the device-wide sort for that sub-block.
+// ---------------------------------------------------------------------------------------------
+enum { kCellMax = 16384 };
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(512) k_cell_pass(const uint32_t *__restrict__ slot_off, BlockGeom g,
+                                                   const uint64_t *__restrict__ qoff,
+                                                   const uint32_t *__restrict__ slot_st, const uint32_t *__restrict__ slot_cnt,
+                                                   const uint2 *__restrict__ hdsst, int S, uint32_t NB,
+                                                   uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ cell_base,
+                                                   uint64_t *__restrict__ keys, uint32_t *__restrict__ max_cell) {
+    extern __shared__ uint32_t s_cell[];  // [NB] histogram (count pass) or write cursors (scatter pass)
+    const int qi = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cell[b] = SCATTER ? cell_base[(size_t)qi * NB + b] : 0u;
+    __syncthreads();
+    const uint32_t so0 = slot_off[qi], nsl = slot_off[qi + 1] - so0;
+    const int L = (int)(qoff[g.qb0 + qi + 1] - qoff[g.qb0 + qi]);
+    const uint64_t hi = (uint64_t)qi << (g.hd_bits + g.diag_bits + g.qst_bits);
+    for (uint32_t sl = warp; sl < nsl; sl += nwarps) {
+        const uint32_t cnt = slot_cnt[so0 + sl];
+        if (cnt == 0) continue;
+        const uint32_t st = slot_st[so0 + sl];
+        const int qst = (int)(sl % (uint32_t)L);
+        for (uint32_t k0 = 0; k0 < cnt; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            uint2 e = make_uint2(0u, 0u);
+            if (k < cnt) e = hdsst[st + k];
+            // e.x == 0: the reference's "sequence -1" (never scores): dropped
+            const uint32_t cell = e.x ? (e.x >> S) : 0xffffffffu;
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, cell, 1);
+            const bool head = lane == 0 || cell != prev;
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+            const int hl = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));  // head lane of my run
+            uint32_t pos = 0;
+            if (head && cell != 0xffffffffu) {
+                const unsigned later = lane == 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));
+                const uint32_t runlen = (uint32_t)((later ? __ffs((int)later) - 1 : 32) - lane);
+                pos = atomicAdd(&s_cell[cell], runlen);
+            }
+            if (SCATTER) {
+                pos = __shfl_sync(0xffffffffu, pos, hl) + (uint32_t)(lane - hl);
+                if (cell != 0xffffffffu) {
+                    const int diag = qst - (int)e.y + g.diag_bias;
+                    keys[pos] = hi | ((uint64_t)e.x << (g.diag_bits + g.qst_bits)) | ((uint64_t)diag << g.qst_bits) | (uint64_t)qst;
+                }
+            }
+        }
+    }
+    if (!SCATTER) {
+        __syncthreads();
+        uint32_t mx = 0;
+        for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) {
+            const uint32_t v = s_cell[b];
+            cell_count[(size_t)qi * NB + b] = v;
+            mx = max(mx, v);
+        }
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0 && mx) atomicMax(max_cell, mx);
+    }
+}
+
+// one CTA per cell (grid-stride): keys of the cell -> shared-memory radix sort of the cell-local 32 bits
+template <int THREADS, int ITEMS>
+__device__ __forceinline__ void cell_sort_tile(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint32_t off,
+                                               uint32_t n, int Lb, void *smem) {
+    typedef cub::BlockRadixSort<uint32_t, THREADS, ITEMS> Sort;
+    typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem);
+    const uint32_t mask = Lb >= 32 ? 0xffffffffu : ((1u << Lb) - 1u);
+    const uint64_t upper = in[off] & ~(uint64_t)mask;  // identical for every key of the cell
+    uint32_t k[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t idx = (uint32_t)i * THREADS + threadIdx.x;  // striped, coalesced
+        k[i] = idx < n ? ((uint32_t)in[off + idx] & mask) : 0xffffffffu;
+    }
+    Sort(tmp).SortBlockedToStriped(k, 0, Lb);
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t idx = (uint32_t)i * THREADS + threadIdx.x;
+        if (idx < n) out[off + idx] = upper | (uint64_t)k[i];
+    }
+    __syncthreads();
+}
+
+template <int THREADS, int I0, int I1, int I2, int I3>
+__global__ void __launch_bounds__(THREADS) k_cell_sort(const uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ cell_base,
+                                                       uint32_t ncells, const uint64_t *__restrict__ in,
+                                                       uint64_t *__restrict__ out, int Lb, uint32_t lo) {
+    // cells with lo < n <= THREADS * I3 are sorted here, in the smallest of the four tile sizes that fits
+    extern __shared__ __align__(16) unsigned char smem[];  // sizeof(BlockRadixSort<uint32_t, THREADS, I3>::TempStorage)
+    for (uint32_t b = blockIdx.x; b < ncells; b += gridDim.x) {
+        const uint32_t n = cell_count[b];
+        if (n <= lo || n > (uint32_t)THREADS * I3) continue;
+        const uint32_t off = cell_base[b];
+        if (n <= (uint32_t)THREADS * I0)
+            cell_sort_tile<THREADS, I0>(in, out, off, n, Lb, smem);
+        else if (n <= (uint32_t)THREADS * I1)
+            cell_sort_tile<THREADS, I1>(in, out, off, n, Lb, smem);
+        else if (n <= (uint32_t)THREADS * I2)
+            cell_sort_tile<THREADS, I2>(in, out, off, n, Lb, smem);
+        else
+            cell_sort_tile<THREADS, I3>(in, out, off, n, Lb, smem);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Chained X-drop scoring, lane-persistent.
 //
 // The sorted hit array is cut into diagonal groups (query, target, diagonal).  A group costs anything
@@ -1080,7 +1200,7 @@ static int bits_for(uint64_t maxval) {  // bits needed to hold values 0..maxval
 }
 
 enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TMP, SC_CKA, SC_CKB, SC_CVA, SC_CVB, SC_MISC,
-       SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK, SC_QUNG, SC_DESC, SC_MLIST, SC_GKEY, SC_PLIST };
+       SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK, SC_QUNG, SC_DESC, SC_MLIST, SC_GKEY, SC_PLIST, SC_CELLCNT, SC_CELLBASE };
 
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
 
@@ -1094,6 +1214,8 @@ int upload_search_config(so_ctx *c) {
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_cell_sort<512, 8, 16, 24, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(cub::BlockRadixSort<uint32_t, 512, 32>::TempStorage)));
     return upload_cfg(c->P);
 }
 
@@ -1225,26 +1347,84 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             uint64_t *ka = (uint64_t *)scratch[SC_KA].p, *kb = (uint64_t *)scratch[SC_KB].p;
             uint32_t *va = keys_only ? nullptr : (uint32_t *)scratch[SC_VA].p;
             uint32_t *vb = keys_only ? nullptr : (uint32_t *)scratch[SC_VB].p;
-            const int ewarps = 148 * 64;
-            k_expand<<<ewarps * 32 / 256, 256, 0, st>>>(d_slot_off, g, nslots, c->d_qoff, d_st, d_cnt, d_out, ix.d_hdsst, ka,
-                                                        va);
-            SO_CUDA(cudaEventRecord(ev[1], st));
             const int key_bits = g.qst_bits + g.diag_bits + g.hd_bits + q_bits;
             // candidate sort key: query | first-appearance rank (see k_pair_select)
             const int rank_bits = (AS == 1 && !getenv("SO_FORCE_PAIRS")) ? g.qst_bits + g.diag_bits + g.hd_bits : 32;
-            // dropped hits carry ~0 and must sort last: include one extra bit above the fields
-            const int end_bit = std::min(64, key_bits + 1);
             cub::DoubleBuffer<uint64_t> dk(ka, kb);
             cub::DoubleBuffer<uint32_t> dv(va, vb);
-            tmp = 0;
-            if (keys_only) {
-                cub::DeviceRadixSort::SortKeys(nullptr, tmp, dk, (int)H, g.qst_bits, end_bit, st);
+            unsigned long long *d_counter = (unsigned long long *)(scratch[SC_MISC].p);
+            SO_CUDA(cudaMemsetAsync(d_counter, 0, 64, st));
+            // ---- grouping: cell partition + in-cell sort (keys-only), else the device-wide radix sort
+            // (opt-in, SO_CELL_SORT=1: correct, but not yet faster than the device-wide sort on config 2)
+            bool cell_path = keys_only && getenv("SO_CELL_SORT") != nullptr;
+            int S = 0;
+            uint32_t NB = 0;
+            if (cell_path) {
+                // target-block width 2^S: ~512 hits per (query, target block) cell on average
+                const double cells_per_q = std::max(1.0, (double)H / (double)nq / 512.0);
+                const double width = std::max(1.0, (double)(M + 1) / cells_per_q);
+                while (S < 16 && (double)(2u << S) <= width) S++;
+                while ((((uint64_t)M + 1) >> S) + 1 > 8192) S++;
+                while (S > 0 && g.qst_bits + g.diag_bits + S > 32) S--;
+                NB = (uint32_t)((((uint64_t)M + 1) >> S) + 1);
+                if (g.qst_bits + g.diag_bits + S > 32 || NB > 8192) cell_path = false;
+            }
+            if (cell_path) {
+                const uint32_t ncells = (uint32_t)nq * NB;
+                if ((rc = scratch[SC_CELLCNT].reserve(((size_t)ncells + 1) * 4)) != SO_OK) return rc;
+                if ((rc = scratch[SC_CELLBASE].reserve(((size_t)ncells + 1) * 4)) != SO_OK) return rc;
+                uint32_t *d_ccnt = (uint32_t *)scratch[SC_CELLCNT].p, *d_cbase = (uint32_t *)scratch[SC_CELLBASE].p;
+                uint32_t *d_maxcell = (uint32_t *)(d_counter + 6);
+                SO_CUDA(cudaMemsetAsync(d_ccnt + ncells, 0, 4, st));
+                k_cell_pass<false><<<nq, 512, NB * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, S, NB, d_ccnt,
+                                                          nullptr, nullptr, d_maxcell);
+                tmp = 0;
+                cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_ccnt, d_cbase, (int)ncells + 1, st);
                 if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
-                SO_CUDA(cub::DeviceRadixSort::SortKeys(scratch[SC_TMP].p, tmp, dk, (int)H, g.qst_bits, end_bit, st));
-            } else {
-                cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)H, 0, end_bit, st);
-                if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
-                SO_CUDA(cub::DeviceRadixSort::SortPairs(scratch[SC_TMP].p, tmp, dk, dv, (int)H, 0, end_bit, st));
+                SO_CUDA(cub::DeviceScan::ExclusiveSum(scratch[SC_TMP].p, tmp, d_ccnt, d_cbase, (int)ncells + 1, st));
+                uint32_t h_cell[2] = {0, 0};  // valid hits, largest cell
+                SO_CUDA(cudaMemcpyAsync(&h_cell[0], d_cbase + ncells, 4, cudaMemcpyDeviceToHost, st));
+                SO_CUDA(cudaMemcpyAsync(&h_cell[1], d_maxcell, 4, cudaMemcpyDeviceToHost, st));
+                SO_CUDA(cudaStreamSynchronize(st));
+                SO_CUDA(cudaGetLastError());
+                stats.kernel_launches += 1;
+                stats.lib_launches += 1;
+                if (h_cell[0] == 0 || h_cell[1] > (uint32_t)kCellMax)
+                    cell_path = false;  // nothing valid / a cell too large for shared memory: device-wide sort
+                else {
+                    SO_CUDA(cudaEventRecord(ev[1], st));
+                    k_cell_pass<true><<<nq, 512, NB * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, S, NB, nullptr,
+                                                             d_cbase, ka, nullptr);
+                    const int Lb = g.qst_bits + g.diag_bits + S;
+                    const size_t sm_small = sizeof(cub::BlockRadixSort<uint32_t, 256, 8>::TempStorage);
+                    const size_t sm_large = sizeof(cub::BlockRadixSort<uint32_t, 512, 32>::TempStorage);
+                    k_cell_sort<256, 1, 2, 4, 8><<<148 * 8, 256, sm_small, st>>>(d_ccnt, d_cbase, ncells, ka, kb, Lb, 0u);
+                    if (h_cell[1] > 2048u)
+                        k_cell_sort<512, 8, 16, 24, 32><<<148 * 2, 512, sm_large, st>>>(d_ccnt, d_cbase, ncells, ka, kb, Lb, 2048u);
+                    dk.selector = 1;
+                    H = h_cell[0];  // the hits of "sequence -1" are gone
+                    stats.kernel_launches += 3;
+                }
+            }
+            if (!cell_path) {
+                const int ewarps = 148 * 64;
+                k_expand<<<ewarps * 32 / 256, 256, 0, st>>>(d_slot_off, g, nslots, c->d_qoff, d_st, d_cnt, d_out, ix.d_hdsst, ka,
+                                                            va);
+                SO_CUDA(cudaEventRecord(ev[1], st));
+                // dropped hits carry ~0 and must sort last: include one extra bit above the fields
+                const int end_bit = std::min(64, key_bits + 1);
+                tmp = 0;
+                if (keys_only) {
+                    cub::DeviceRadixSort::SortKeys(nullptr, tmp, dk, (int)H, g.qst_bits, end_bit, st);
+                    if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+                    SO_CUDA(cub::DeviceRadixSort::SortKeys(scratch[SC_TMP].p, tmp, dk, (int)H, g.qst_bits, end_bit, st));
+                } else {
+                    cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)H, 0, end_bit, st);
+                    if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
+                    SO_CUDA(cub::DeviceRadixSort::SortPairs(scratch[SC_TMP].p, tmp, dk, dv, (int)H, 0, end_bit, st));
+                }
+                stats.kernel_launches += 1;
+                stats.lib_launches += 1;
             }
             SO_CUDA(cudaEventRecord(ev[2], st));
             // candidates: at most one per (query, target) pair
@@ -1255,9 +1435,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             if ((rc = scratch[SC_CVB].reserve((size_t)ccap * 8)) != SO_OK) return rc;
             uint64_t *cka = (uint64_t *)scratch[SC_CKA].p, *ckb = (uint64_t *)scratch[SC_CKB].p;
             uint64_t *cva = (uint64_t *)scratch[SC_CVA].p, *cvb = (uint64_t *)scratch[SC_CVB].p;
-            unsigned long long *d_counter = (unsigned long long *)(scratch[SC_MISC].p);
             uint32_t *d_bounds = (uint32_t *)(scratch[SC_MISC].p + 64);
-            SO_CUDA(cudaMemsetAsync(d_counter, 0, 64, st));
             // diagonal groups: head flags -> exclusive scan -> compact head positions
             const int grp_shift = g.qst_bits;
             if ((rc = scratch[SC_GIDX].reserve(((size_t)H + 1) * 4)) != SO_OK) return rc;
