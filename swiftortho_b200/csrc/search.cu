@@ -401,122 +401,206 @@ __global__ void __launch_bounds__(256) k_expand(const uint32_t *__restrict__ slo
 }
 
 // ---------------------------------------------------------------------------------------------
-// Hit grouping without a global sort (keys-only path).
+// Hit grouping without a global sort (keys-only path; SO_CUB_SORT=1 forces the device-wide radix sort).
 //
 // The seed hits of a query arrive as ~200 bucket lists, each already in descending (sequence, position)
-// order.  Instead of a 5-pass device-wide radix sort of 64-bit keys, they are
-//   1. counted per (query, target block) cell, target block = sequence >> S  (k_cell_pass<false>: one CTA
-//      per query, shared-memory histogram, runs of equal cells inside a warp-row folded into one atomic),
-//   2. exclusive-scanned (cub::DeviceScan on the small cell array),
-//   3. scattered into their cell (k_cell_pass<true>: same traversal, shared-memory cursors), and
-//   4. sorted inside each cell in shared memory (k_cell_sort: cub::BlockRadixSort on the 32-bit cell-local
-//      part of the key: sequence low bits | diagonal | qst).
-// Each hit is read twice from the index (8 B) and its key written/read/written once more; the result is the
-// same fully sorted key array the radix sort produced, minus the hits the reference attributes to
-// "sequence -1" (they can never score and were only sorted to the end before).
-// Cells larger than kCellMax fall back to the device-wide sort for that sub-block.
+// order.  Instead of a 5-pass device-wide radix sort of 64-bit keys they are partitioned straight into
+// (query, target) cells -- a cell holds everything pair selection later folds together:
+//   1. k_cell_pass<false>: one CTA per query, one shared-memory counter per target of the chunk
+//      (4 B x (M + 2) <= 227 KB), one shared-memory atomic per hit;
+//   2. cub::DeviceScan over the [query][target] counts -> cell bases;
+//   3. k_cell_pass<true>: same traversal, the counters are now write cursors; the 64-bit key goes to its cell;
+//   4. in-cell order (diagonal, qst): cells hold ~2.7 hits on average, so k_cell_small sorts cells of up to 8
+//      hits with one THREAD per cell (sorting network on the 32-bit cell-local bits), k_cell_warp sorts cells
+//      of up to kCellWarp hits with one warp per cell (rank sort out of shared memory), k_cell_block the rest
+//      (cub::BlockRadixSort).  All in place.
+// Each hit is read twice from the index (8 B) and its key is written once and touched once more, against
+// 5 x (8 B + 8 B) for the radix sort; the hits the reference attributes to "sequence -1" (they can never
+// score and were only sorted to the end before) are not materialised at all.
+// A cell above kCellMax hits falls back to the device-wide sort for that sub-block.
 // ---------------------------------------------------------------------------------------------
-enum { kCellMax = 16384 };
+enum { kCellSmall = 8, kCellWarp = 192, kCellMax = 16384 };
 
 template <bool SCATTER>
-__global__ void __launch_bounds__(512) k_cell_pass(const uint32_t *__restrict__ slot_off, BlockGeom g,
-                                                   const uint64_t *__restrict__ qoff,
-                                                   const uint32_t *__restrict__ slot_st, const uint32_t *__restrict__ slot_cnt,
-                                                   const uint2 *__restrict__ hdsst, int S, uint32_t NB,
-                                                   uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ cell_base,
-                                                   uint64_t *__restrict__ keys, uint32_t *__restrict__ max_cell) {
-    extern __shared__ uint32_t s_cell[];  // [NB] histogram (count pass) or write cursors (scatter pass)
-    const int qi = blockIdx.x;
+__global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__ slot_off, BlockGeom g,
+                                                    const uint64_t *__restrict__ qoff,
+                                                    const uint32_t *__restrict__ slot_st, const uint32_t *__restrict__ slot_cnt,
+                                                    const uint2 *__restrict__ hdsst, uint32_t NB,
+                                                    uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ cell_base,
+                                                    uint32_t *__restrict__ sub, uint32_t *__restrict__ max_cell,
+                                                    uint32_t *__restrict__ next_query) {
+    extern __shared__ uint32_t s_cell[];  // [NB] per-target counters (count pass) or write cursors (scatter pass)
+    __shared__ int s_qi;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cell[b] = SCATTER ? cell_base[(size_t)qi * NB + b] : 0u;
-    __syncthreads();
-    const uint32_t so0 = slot_off[qi], nsl = slot_off[qi + 1] - so0;
-    const int L = (int)(qoff[g.qb0 + qi + 1] - qoff[g.qb0 + qi]);
-    const uint64_t hi = (uint64_t)qi << (g.hd_bits + g.diag_bits + g.qst_bits);
-    for (uint32_t sl = warp; sl < nsl; sl += nwarps) {
-        const uint32_t cnt = slot_cnt[so0 + sl];
-        if (cnt == 0) continue;
-        const uint32_t st = slot_st[so0 + sl];
-        const int qst = (int)(sl % (uint32_t)L);
-        for (uint32_t k0 = 0; k0 < cnt; k0 += 32) {
-            const uint32_t k = k0 + lane;
-            uint2 e = make_uint2(0u, 0u);
-            if (k < cnt) e = hdsst[st + k];
-            // e.x == 0: the reference's "sequence -1" (never scores): dropped
-            const uint32_t cell = e.x ? (e.x >> S) : 0xffffffffu;
-            const uint32_t prev = __shfl_up_sync(0xffffffffu, cell, 1);
-            const bool head = lane == 0 || cell != prev;
-            const unsigned heads = __ballot_sync(0xffffffffu, head);
-            const int hl = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));  // head lane of my run
-            uint32_t pos = 0;
-            if (head && cell != 0xffffffffu) {
-                const unsigned later = lane == 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));
-                const uint32_t runlen = (uint32_t)((later ? __ffs((int)later) - 1 : 32) - lane);
-                pos = atomicAdd(&s_cell[cell], runlen);
-            }
-            if (SCATTER) {
-                pos = __shfl_sync(0xffffffffu, pos, hl) + (uint32_t)(lane - hl);
-                if (cell != 0xffffffffu) {
-                    const int diag = qst - (int)e.y + g.diag_bias;
-                    keys[pos] = hi | ((uint64_t)e.x << (g.diag_bits + g.qst_bits)) | ((uint64_t)diag << g.qst_bits) | (uint64_t)qst;
+    constexpr int U = 4;  // bucket rows in flight per warp (the loop is latency bound)
+    for (;;) {            // CTAs draw queries from a counter: no wave quantisation with one 200 KB CTA per SM
+        if (threadIdx.x == 0) s_qi = (int)atomicAdd(next_query, 1u);
+        __syncthreads();
+        const int qi = s_qi;
+        if (qi >= g.nq) break;
+        for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cell[b] = SCATTER ? cell_base[(size_t)qi * NB + b] : 0u;
+        __syncthreads();
+        const uint32_t so0 = slot_off[qi], nsl = slot_off[qi + 1] - so0;
+        const int L = (int)(qoff[g.qb0 + qi + 1] - qoff[g.qb0 + qi]);
+        for (uint32_t sl = warp; sl < nsl; sl += nwarps) {
+            const uint32_t cnt = slot_cnt[so0 + sl];
+            if (cnt == 0) continue;
+            const uint32_t st = slot_st[so0 + sl];
+            const int qst = (int)(sl % (uint32_t)L);
+            for (uint32_t k0 = lane; k0 < cnt; k0 += 32 * U) {
+                uint2 e[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t k = k0 + 32u * u;
+                    e[u] = k < cnt ? hdsst[st + k] : make_uint2(0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (e[u].x == 0) continue;  // past the end, or the reference's "sequence -1" (never scores): dropped
+                    if (!SCATTER)
+                        atomicAdd(&s_cell[e[u].x], 1u);
+                    else {
+                        // only the cell-local part (diagonal | qst) is stored: 4 B per hit keep the partially
+                        // written sectors of the queries in flight inside L2
+                        const uint32_t pos = atomicAdd(&s_cell[e[u].x], 1u);
+                        const int diag = qst - (int)e[u].y + g.diag_bias;
+                        sub[pos] = ((uint32_t)diag << g.qst_bits) | (uint32_t)qst;
+                    }
                 }
             }
         }
-    }
-    if (!SCATTER) {
         __syncthreads();
-        uint32_t mx = 0;
-        for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) {
-            const uint32_t v = s_cell[b];
-            cell_count[(size_t)qi * NB + b] = v;
-            mx = max(mx, v);
+        if (!SCATTER) {
+            uint32_t mx = 0;
+            for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) {
+                const uint32_t v = s_cell[b];
+                cell_count[(size_t)qi * NB + b] = v;
+                mx = max(mx, v);
+            }
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0 && mx > (uint32_t)kCellSmall) atomicMax(max_cell, mx);
+            __syncthreads();
         }
-        mx = __reduce_max_sync(0xffffffffu, mx);
-        if (lane == 0 && mx) atomicMax(max_cell, mx);
     }
 }
 
-// one CTA per cell (grid-stride): keys of the cell -> shared-memory radix sort of the cell-local 32 bits
+__device__ __forceinline__ void cex(uint32_t &a, uint32_t &b) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo, b = hi;
+}
+
+__device__ __forceinline__ uint64_t cell_upper(uint32_t c, uint32_t NB, const BlockGeom &g) {
+    const uint32_t qi = c / NB, hd1 = c - qi * NB;
+    return ((uint64_t)qi << (g.hd_bits + g.diag_bits + g.qst_bits)) | ((uint64_t)hd1 << (g.diag_bits + g.qst_bits));
+}
+
+// one thread per cell: cells of 1..8 hits are sorted in registers on their cell-local 32 bits (diagonal | qst) and
+// written out as full 64-bit keys; larger cells are queued for k_cell_warp / k_cell_block
+__global__ void __launch_bounds__(256) k_cell_small(const uint32_t *__restrict__ cell_base, uint32_t ncells, uint32_t NB,
+                                                    BlockGeom g, const uint32_t *__restrict__ sub, uint64_t *__restrict__ keys,
+                                                    uint32_t *__restrict__ wlist, uint32_t *__restrict__ blist,
+                                                    uint32_t *__restrict__ lcount) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const uint32_t off = cell_base[c], n = cell_base[c + 1] - off;
+    if (n == 0) return;
+    if (n > (uint32_t)kCellSmall) {
+        if (n <= (uint32_t)kCellWarp)
+            wlist[atomicAdd(lcount, 1u)] = c;
+        else
+            blist[atomicAdd(lcount + 1, 1u)] = c;
+        return;
+    }
+    const uint64_t upper = cell_upper(c, NB, g);
+    uint32_t k[kCellSmall];
+#pragma unroll
+    for (int i = 0; i < kCellSmall; i++) k[i] = (uint32_t)i < n ? sub[off + i] : 0xffffffffu;
+    if (n > 4) {  // 19-comparator network on 8
+        cex(k[0], k[1]), cex(k[2], k[3]), cex(k[4], k[5]), cex(k[6], k[7]);
+        cex(k[0], k[2]), cex(k[1], k[3]), cex(k[4], k[6]), cex(k[5], k[7]);
+        cex(k[1], k[2]), cex(k[5], k[6]), cex(k[0], k[4]), cex(k[3], k[7]);
+        cex(k[1], k[5]), cex(k[2], k[6]);
+        cex(k[1], k[4]), cex(k[3], k[6]);
+        cex(k[2], k[4]), cex(k[3], k[5]);
+        cex(k[3], k[4]);
+    } else if (n > 1) {  // 5-comparator network on 4
+        cex(k[0], k[1]), cex(k[2], k[3]), cex(k[0], k[2]), cex(k[1], k[3]), cex(k[1], k[2]);
+    }
+#pragma unroll
+    for (int i = 0; i < kCellSmall; i++)
+        if ((uint32_t)i < n) keys[off + i] = upper | (uint64_t)k[i];
+}
+
+// one warp per queued cell (9..kCellWarp hits): rank sort out of shared memory (keys of a cell are distinct)
+__global__ void __launch_bounds__(256) k_cell_warp(const uint32_t *__restrict__ cell_base, const uint32_t *__restrict__ wlist,
+                                                   const uint32_t *__restrict__ lcount, uint32_t NB, BlockGeom g,
+                                                   const uint32_t *__restrict__ sub, uint64_t *__restrict__ keys) {
+    __shared__ uint32_t s_keys[8][kCellWarp];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nlist = lcount[0];
+    uint32_t *sk = s_keys[warp];
+    for (uint32_t w = blockIdx.x * 8 + warp; w < nlist; w += gridDim.x * 8) {
+        const uint32_t c = wlist[w];
+        const uint32_t off = cell_base[c], n = cell_base[c + 1] - off;
+        const uint64_t upper = cell_upper(c, NB, g);
+        for (uint32_t i = lane; i < n; i += 32) sk[i] = sub[off + i];
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t x = sk[i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n; j++) {
+                const uint32_t y = sk[j];
+                rank += (y < x || (y == x && j < i)) ? 1u : 0u;
+            }
+            keys[off + rank] = upper | (uint64_t)x;
+        }
+        __syncwarp();
+    }
+}
+
+// one CTA per queued cell (kCellWarp < hits <= kCellMax): shared-memory radix sort of the cell-local bits
 template <int THREADS, int ITEMS>
-__device__ __forceinline__ void cell_sort_tile(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint32_t off,
-                                               uint32_t n, int Lb, void *smem) {
+__device__ __forceinline__ void cell_sort_tile(const uint32_t *__restrict__ sub, uint64_t *__restrict__ keys, uint64_t upper,
+                                               uint32_t off, uint32_t n, int Lb, void *smem) {
     typedef cub::BlockRadixSort<uint32_t, THREADS, ITEMS> Sort;
     typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem);
-    const uint32_t mask = Lb >= 32 ? 0xffffffffu : ((1u << Lb) - 1u);
-    const uint64_t upper = in[off] & ~(uint64_t)mask;  // identical for every key of the cell
     uint32_t k[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = (uint32_t)i * THREADS + threadIdx.x;  // striped, coalesced
-        k[i] = idx < n ? ((uint32_t)in[off + idx] & mask) : 0xffffffffu;
+        k[i] = idx < n ? sub[off + idx] : 0xffffffffu;
     }
     Sort(tmp).SortBlockedToStriped(k, 0, Lb);
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = (uint32_t)i * THREADS + threadIdx.x;
-        if (idx < n) out[off + idx] = upper | (uint64_t)k[i];
+        if (idx < n) keys[off + idx] = upper | (uint64_t)k[i];
     }
     __syncthreads();
 }
 
-template <int THREADS, int I0, int I1, int I2, int I3>
-__global__ void __launch_bounds__(THREADS) k_cell_sort(const uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ cell_base,
-                                                       uint32_t ncells, const uint64_t *__restrict__ in,
-                                                       uint64_t *__restrict__ out, int Lb, uint32_t lo) {
-    // cells with lo < n <= THREADS * I3 are sorted here, in the smallest of the four tile sizes that fits
-    extern __shared__ __align__(16) unsigned char smem[];  // sizeof(BlockRadixSort<uint32_t, THREADS, I3>::TempStorage)
-    for (uint32_t b = blockIdx.x; b < ncells; b += gridDim.x) {
-        const uint32_t n = cell_count[b];
-        if (n <= lo || n > (uint32_t)THREADS * I3) continue;
-        const uint32_t off = cell_base[b];
-        if (n <= (uint32_t)THREADS * I0)
-            cell_sort_tile<THREADS, I0>(in, out, off, n, Lb, smem);
-        else if (n <= (uint32_t)THREADS * I1)
-            cell_sort_tile<THREADS, I1>(in, out, off, n, Lb, smem);
-        else if (n <= (uint32_t)THREADS * I2)
-            cell_sort_tile<THREADS, I2>(in, out, off, n, Lb, smem);
+__global__ void __launch_bounds__(512) k_cell_block(const uint32_t *__restrict__ cell_base, const uint32_t *__restrict__ blist,
+                                                    const uint32_t *__restrict__ lcount, uint32_t NB, BlockGeom g,
+                                                    const uint32_t *__restrict__ sub, uint64_t *__restrict__ keys) {
+    extern __shared__ __align__(16) unsigned char smem[];  // sizeof(BlockRadixSort<uint32_t, 512, 32>::TempStorage)
+    const uint32_t nlist = lcount[1];
+    const int Lb = g.qst_bits + g.diag_bits;
+    for (uint32_t w = blockIdx.x; w < nlist; w += gridDim.x) {
+        const uint32_t c = blist[w];
+        const uint32_t off = cell_base[c], n = cell_base[c + 1] - off;
+        const uint64_t upper = cell_upper(c, NB, g);
+        if (n <= 512u * 1)
+            cell_sort_tile<512, 1>(sub, keys, upper, off, n, Lb, smem);
+        else if (n <= 512u * 2)
+            cell_sort_tile<512, 2>(sub, keys, upper, off, n, Lb, smem);
+        else if (n <= 512u * 4)
+            cell_sort_tile<512, 4>(sub, keys, upper, off, n, Lb, smem);
+        else if (n <= 512u * 8)
+            cell_sort_tile<512, 8>(sub, keys, upper, off, n, Lb, smem);
+        else if (n <= 512u * 16)
+            cell_sort_tile<512, 16>(sub, keys, upper, off, n, Lb, smem);
         else
-            cell_sort_tile<THREADS, I3>(in, out, off, n, Lb, smem);
+            cell_sort_tile<512, 32>(sub, keys, upper, off, n, Lb, smem);
     }
 }
 
@@ -1214,8 +1298,10 @@ int upload_search_config(so_ctx *c) {
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-    SO_CUDA(cudaFuncSetAttribute(k_cell_sort<512, 8, 16, 24, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SO_CUDA(cudaFuncSetAttribute(k_cell_block, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(cub::BlockRadixSort<uint32_t, 512, 32>::TempStorage)));
+    SO_CUDA(cudaFuncSetAttribute(k_cell_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SO_CUDA(cudaFuncSetAttribute(k_cell_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     return upload_cfg(c->P);
 }
 
@@ -1304,7 +1390,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
         if ((rc = scratch[SC_ST].reserve((size_t)nslots * 4)) != SO_OK) return rc;
         if ((rc = scratch[SC_CNT].reserve(((size_t)nslots + 1) * 4)) != SO_OK) return rc;
         if ((rc = scratch[SC_OUT].reserve(((size_t)nslots + 1) * 8)) != SO_OK) return rc;
-        if ((rc = scratch[SC_MISC].reserve(((size_t)nq + 2) * 4 + 128)) != SO_OK) return rc;
+        if ((rc = scratch[SC_MISC].reserve(((size_t)nq + 2) * 4 + 256)) != SO_OK) return rc;
         uint32_t *d_slot_off = (uint32_t *)scratch[SC_SLOTOFF].p;
         uint32_t *d_st = (uint32_t *)scratch[SC_ST].p, *d_cnt = (uint32_t *)scratch[SC_CNT].p;
         uint64_t *d_out = (uint64_t *)scratch[SC_OUT].p;
@@ -1353,36 +1439,30 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             cub::DoubleBuffer<uint64_t> dk(ka, kb);
             cub::DoubleBuffer<uint32_t> dv(va, vb);
             unsigned long long *d_counter = (unsigned long long *)(scratch[SC_MISC].p);
-            SO_CUDA(cudaMemsetAsync(d_counter, 0, 64, st));
-            // ---- grouping: cell partition + in-cell sort (keys-only), else the device-wide radix sort
-            // (opt-in, SO_CELL_SORT=1: correct, but not yet faster than the device-wide sort on config 2)
-            bool cell_path = keys_only && getenv("SO_CELL_SORT") != nullptr;
-            int S = 0;
-            uint32_t NB = 0;
-            if (cell_path) {
-                // target-block width 2^S: ~512 hits per (query, target block) cell on average
-                const double cells_per_q = std::max(1.0, (double)H / (double)nq / 512.0);
-                const double width = std::max(1.0, (double)(M + 1) / cells_per_q);
-                while (S < 16 && (double)(2u << S) <= width) S++;
-                while ((((uint64_t)M + 1) >> S) + 1 > 8192) S++;
-                while (S > 0 && g.qst_bits + g.diag_bits + S > 32) S--;
-                NB = (uint32_t)((((uint64_t)M + 1) >> S) + 1);
-                if (g.qst_bits + g.diag_bits + S > 32 || NB > 8192) cell_path = false;
-            }
+            SO_CUDA(cudaMemsetAsync(d_counter, 0, 128, st));
+            // ---- grouping: (query, target) cell partition + in-cell sort (keys-only), else the device-wide radix sort
+            // (SO_CUB_SORT=1 forces the device-wide sort)
+            const uint32_t NB = (uint32_t)(M + 2);
+            const int Lb = g.qst_bits + g.diag_bits;
+            bool cell_path = keys_only && !getenv("SO_CUB_SORT") && (size_t)NB * 4 <= 220 * 1024 && Lb <= 32 &&
+                             (uint64_t)nq * NB < 0x7fffff00ull;
             if (cell_path) {
                 const uint32_t ncells = (uint32_t)nq * NB;
                 if ((rc = scratch[SC_CELLCNT].reserve(((size_t)ncells + 1) * 4)) != SO_OK) return rc;
                 if ((rc = scratch[SC_CELLBASE].reserve(((size_t)ncells + 1) * 4)) != SO_OK) return rc;
                 uint32_t *d_ccnt = (uint32_t *)scratch[SC_CELLCNT].p, *d_cbase = (uint32_t *)scratch[SC_CELLBASE].p;
                 uint32_t *d_maxcell = (uint32_t *)(d_counter + 6);
+                uint32_t *d_lcount = (uint32_t *)(d_counter + 7);  // two u32: warp-list / block-list lengths
+                uint32_t *d_nextq = (uint32_t *)(d_counter + 8);   // two u32: query counters of the two passes
                 SO_CUDA(cudaMemsetAsync(d_ccnt + ncells, 0, 4, st));
-                k_cell_pass<false><<<nq, 512, NB * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, S, NB, d_ccnt,
-                                                          nullptr, nullptr, d_maxcell);
+                const int pblocks = std::min(nq, 148);
+                k_cell_pass<false><<<pblocks, 1024, NB * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, d_ccnt,
+                                                                nullptr, nullptr, d_maxcell, d_nextq);
                 tmp = 0;
                 cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_ccnt, d_cbase, (int)ncells + 1, st);
                 if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
                 SO_CUDA(cub::DeviceScan::ExclusiveSum(scratch[SC_TMP].p, tmp, d_ccnt, d_cbase, (int)ncells + 1, st));
-                uint32_t h_cell[2] = {0, 0};  // valid hits, largest cell
+                uint32_t h_cell[2] = {0, 0};  // valid hits, largest cell (0 when none exceeds kCellSmall)
                 SO_CUDA(cudaMemcpyAsync(&h_cell[0], d_cbase + ncells, 4, cudaMemcpyDeviceToHost, st));
                 SO_CUDA(cudaMemcpyAsync(&h_cell[1], d_maxcell, 4, cudaMemcpyDeviceToHost, st));
                 SO_CUDA(cudaStreamSynchronize(st));
@@ -1393,17 +1473,24 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                     cell_path = false;  // nothing valid / a cell too large for shared memory: device-wide sort
                 else {
                     SO_CUDA(cudaEventRecord(ev[1], st));
-                    k_cell_pass<true><<<nq, 512, NB * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, S, NB, nullptr,
-                                                             d_cbase, ka, nullptr);
-                    const int Lb = g.qst_bits + g.diag_bits + S;
-                    const size_t sm_small = sizeof(cub::BlockRadixSort<uint32_t, 256, 8>::TempStorage);
-                    const size_t sm_large = sizeof(cub::BlockRadixSort<uint32_t, 512, 32>::TempStorage);
-                    k_cell_sort<256, 1, 2, 4, 8><<<148 * 8, 256, sm_small, st>>>(d_ccnt, d_cbase, ncells, ka, kb, Lb, 0u);
-                    if (h_cell[1] > 2048u)
-                        k_cell_sort<512, 8, 16, 24, 32><<<148 * 2, 512, sm_large, st>>>(d_ccnt, d_cbase, ncells, ka, kb, Lb, 2048u);
-                    dk.selector = 1;
+                    k_cell_pass<true><<<pblocks, 1024, NB * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nullptr,
+                                                                   d_cbase, (uint32_t *)kb, nullptr, d_nextq + 1);
+                    // queue of the warp-sorted cells = the (now free) count array; CTA-sorted cells: own small buffer
+                    if ((rc = scratch[SC_MLIST].reserve(((size_t)h_cell[0] / kCellWarp + 2) * 4)) != SO_OK) return rc;
+                    uint32_t *d_wlist = d_ccnt, *d_blist = (uint32_t *)scratch[SC_MLIST].p;
+                    k_cell_small<<<(ncells + 255) / 256, 256, 0, st>>>(d_cbase, ncells, NB, g, (const uint32_t *)kb, ka, d_wlist,
+                                                                      d_blist, d_lcount);
+                    stats.kernel_launches += 2;
+                    if (h_cell[1] > (uint32_t)kCellSmall) {
+                        k_cell_warp<<<148 * 4, 256, 0, st>>>(d_cbase, d_wlist, d_lcount, NB, g, (const uint32_t *)kb, ka);
+                        stats.kernel_launches += 1;
+                    }
+                    if (h_cell[1] > (uint32_t)kCellWarp) {
+                        k_cell_block<<<148 * 2, 512, sizeof(cub::BlockRadixSort<uint32_t, 512, 32>::TempStorage), st>>>(
+                            d_cbase, d_blist, d_lcount, NB, g, (const uint32_t *)kb, ka);
+                        stats.kernel_launches += 1;
+                    }
                     H = h_cell[0];  // the hits of "sequence -1" are gone
-                    stats.kernel_launches += 3;
                 }
             }
             if (!cell_path) {
@@ -1435,7 +1522,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             if ((rc = scratch[SC_CVB].reserve((size_t)ccap * 8)) != SO_OK) return rc;
             uint64_t *cka = (uint64_t *)scratch[SC_CKA].p, *ckb = (uint64_t *)scratch[SC_CKB].p;
             uint64_t *cva = (uint64_t *)scratch[SC_CVA].p, *cvb = (uint64_t *)scratch[SC_CVB].p;
-            uint32_t *d_bounds = (uint32_t *)(scratch[SC_MISC].p + 64);
+            uint32_t *d_bounds = (uint32_t *)(scratch[SC_MISC].p + 128);
             // diagonal groups: head flags -> exclusive scan -> compact head positions
             const int grp_shift = g.qst_bits;
             if ((rc = scratch[SC_GIDX].reserve(((size_t)H + 1) * 4)) != SO_OK) return rc;
