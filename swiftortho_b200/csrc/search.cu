@@ -1292,7 +1292,7 @@ static int g_xdrop_refill = 20;  // idle lanes that trigger a refill in k_xdrop 
 
 int upload_search_config(so_ctx *c) {
     const char *e = getenv("SO_XDROP_REFILL");
-    if (e) g_xdrop_refill = atoi(e);
+    g_xdrop_refill = e ? atoi(e) : 20;
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));

@@ -232,6 +232,44 @@ def test_search_baseline_flags_against_oracle(so, oracle, tmp_path):
         last_q, last_bit = q, bit
 
 
+@pytest.mark.parametrize('env', [{'SO_CUB_SORT': '1'}, {'SO_GENERIC_UNGAP': '1'}, {'SO_NO_SINGLE': '1'},
+                                 {'SO_FORCE_PAIRS': '1'}, {'SO_XDROP_REFILL': '8'}])
+def test_alternative_code_paths_against_oracle(so, oracle, tmp_path, env):
+    """Every fallback / alternative device path gives the oracle's file too: device-wide radix sort instead of the
+    cell partition, the generic chained X-drop kernel instead of k_xdrop, hit ordinals carried through a pairs
+    sort, another refill threshold.  (The library reads these variables per call.)"""
+    p = _synth(tmp_path, 700, 8, 20261023)
+    ref = str(tmp_path / 'oracle.sc')
+    oracle.blastp(p, p, ref, {'-e': '1e-5', '-j': '1', '-M': '120000000', '-c': '400', '-s': '111111'})
+    out = str(tmp_path / 'gpu.sc')
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        so.blastp(p, p, out, expect=1e-5, step=1, ht=120000000, chk=400, ssd='111111')
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert open(out, 'rb').read() == open(ref, 'rb').read()
+
+
+def test_search_one_lane_equals_two_lanes(so, tmp_path):
+    """so_search with one candidate-production lane returns the rows of the default two-lane pipeline."""
+    p = _synth(tmp_path, 900, 9, 20261024)
+    F = so.Fasta(p)
+    S = so.Searcher(device=0, ssd='111111', expect=1e-5, chk=300)
+    S.set_targets(F)
+    S.set_queries(F)
+    S.build_index()
+    a = S.search(0, F.N).as_array().copy()
+    S.set_lanes(1)
+    b = S.search(0, F.N).as_array().copy()
+    assert len(a) > 900 and a.tobytes() == b.tobytes()
+    S.close()
+
+
 def test_search_long_tailed_config5_against_oracle(so, oracle, tmp_path):
     """Config 5 shape (log-normal lengths up to 5000: the >= 4096 tile path) scaled down."""
     p = _synth(tmp_path, 300, 6, 20261022, lengths='lognormal')
