@@ -539,22 +539,32 @@ __global__ void __launch_bounds__(256) k_cell_warp(const uint32_t *__restrict__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nlist = lcount[0];
     uint32_t *sk = s_keys[warp];
-    for (uint32_t w = blockIdx.x * 8 + warp; w < nlist; w += gridDim.x * 8) {
-        const uint32_t c = wlist[w];
-        const uint32_t off = cell_base[c], n = cell_base[c + 1] - off;
-        const uint64_t upper = cell_upper(c, NB, g);
-        for (uint32_t i = lane; i < n; i += 32) sk[i] = sub[off + i];
-        __syncwarp();
-        for (uint32_t i = lane; i < n; i += 32) {
-            const uint32_t x = sk[i];
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < n; j++) {
-                const uint32_t y = sk[j];
-                rank += (y < x || (y == x && j < i)) ? 1u : 0u;
-            }
-            keys[off + rank] = upper | (uint64_t)x;
+    for (uint32_t w0 = (blockIdx.x * 8 + warp) * 32; w0 < nlist; w0 += gridDim.x * 8 * 32) {
+        // 32 queued cells per warp at a time: their list entries and bounds are fetched by the lanes in parallel
+        uint32_t my_c = 0, my_off = 0, my_n = 0;
+        if (w0 + lane < nlist) {
+            my_c = wlist[w0 + lane];
+            my_off = cell_base[my_c];
+            my_n = cell_base[my_c + 1] - my_off;
         }
-        __syncwarp();
+        const int cells = (int)min(32u, nlist - w0);
+        for (int t = 0; t < cells; t++) {
+            const uint32_t c = __shfl_sync(0xffffffffu, my_c, t), off = __shfl_sync(0xffffffffu, my_off, t);
+            const uint32_t n = __shfl_sync(0xffffffffu, my_n, t);
+            const uint64_t upper = cell_upper(c, NB, g);
+            for (uint32_t i = lane; i < n; i += 32) sk[i] = sub[off + i];
+            __syncwarp();
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint32_t x = sk[i];
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < n; j++) {
+                    const uint32_t y = sk[j];
+                    rank += (y < x || (y == x && j < i)) ? 1u : 0u;
+                }
+                keys[off + rank] = upper | (uint64_t)x;
+            }
+            __syncwarp();
+        }
     }
 }
 
