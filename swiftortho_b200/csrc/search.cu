@@ -431,10 +431,14 @@ __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__
                                                     uint32_t *__restrict__ next_query) {
     extern __shared__ uint32_t s_cell[];  // [NB] per-target counters (count pass) or write cursors (scatter pass)
     __shared__ int s_qi;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    __shared__ uint32_t s_next_slot;
+    const int lane = threadIdx.x & 31;
     constexpr int U = 4;  // bucket rows in flight per warp (the loop is latency bound)
     for (;;) {            // CTAs draw queries from a counter: no wave quantisation with one 200 KB CTA per SM
-        if (threadIdx.x == 0) s_qi = (int)atomicAdd(next_query, 1u);
+        if (threadIdx.x == 0) {
+            s_qi = (int)atomicAdd(next_query, 1u);
+            s_next_slot = 0;
+        }
         __syncthreads();
         const int qi = s_qi;
         if (qi >= g.nq) break;
@@ -442,7 +446,11 @@ __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__
         __syncthreads();
         const uint32_t so0 = slot_off[qi], nsl = slot_off[qi + 1] - so0;
         const int L = (int)(qoff[g.qb0 + qi + 1] - qoff[g.qb0 + qi]);
-        for (uint32_t sl = warp; sl < nsl; sl += nwarps) {
+        for (;;) {  // warps draw slots one at a time: bucket lists differ a lot in length
+            uint32_t sl = 0;
+            if (lane == 0) sl = atomicAdd(&s_next_slot, 1u);
+            sl = __shfl_sync(0xffffffffu, sl, 0);
+            if (sl >= nsl) break;
             const uint32_t cnt = slot_cnt[so0 + sl];
             if (cnt == 0) continue;
             const uint32_t st = slot_st[so0 + sl];
