@@ -270,6 +270,41 @@ def test_search_one_lane_equals_two_lanes(so, tmp_path):
     S.close()
 
 
+def test_full_size_config2_window_against_oracle(so, oracle, tmp_path):
+    """BASELINE config 2 at FULL size (100 000 synthetic proteins, 2 index chunks, NC = 120 M, the cell-partition
+    path with ~137 k seed hits per query and chunk): a window of queries against the complete target set must
+    give the oracle's file byte for byte (queries are independent, find_hit.py -l/-u), plus the size-independent
+    properties of the whole block the window lies in."""
+    from swiftortho_b200 import synth
+    p = str(tmp_path / 'c2.fsa')
+    synth.write_config(p, 2, n=100000, taxa=20)
+    flags = {'-e': '1e-5', '-j': '1', '-M': '120000000', '-c': '50000', '-s': '111111'}
+    ref = str(tmp_path / 'oracle.sc')
+    oracle.blastp(p, p, ref, dict(flags, **{'-l': '1000', '-u': '1024'}))
+    out = str(tmp_path / 'gpu.sc')
+    so.blastp(p, p, out, expect=1e-5, step=1, ht=120000000, chk=50000, ssd='111111', st=1000, ed=1024)
+    exp = open(ref, 'rb').read()
+    assert exp.count(b'\n') > 24
+    assert open(out, 'rb').read() == exp
+    # the same rows come out of a 1024-query block (other sub-block / lane / alignment-round boundaries)
+    out2 = str(tmp_path / 'gpu2.sc')
+    so.blastp(p, p, out2, expect=1e-5, step=1, ht=120000000, chk=50000, ssd='111111', st=512, ed=1536)
+    rows = [ln for ln in open(out2, 'rb').read().split(b'\n')[:-1]]
+    win = b''.join(ln + b'\n' for ln in rows if 1000 <= int(ln.split(b'\t')[14]) < 1024)
+    assert win == exp
+    last_q, last_bit, firsts = -1, None, 0
+    for ln in rows:
+        c = ln.split(b'\t')
+        q, bit = int(c[14]), int(c[11])
+        assert q >= last_q
+        if q == last_q:
+            assert bit <= last_bit
+        else:
+            firsts += c[0] == c[1]          # the best hit of an unmasked query is the query itself
+        last_q, last_bit = q, bit
+    assert firsts > 0.95 * 1024
+
+
 def test_search_long_tailed_config5_against_oracle(so, oracle, tmp_path):
     """Config 5 shape (log-normal lengths up to 5000: the >= 4096 tile path) scaled down."""
     p = _synth(tmp_path, 300, 6, 20261022, lengths='lognormal')
