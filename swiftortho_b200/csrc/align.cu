@@ -64,44 +64,71 @@ struct TbOut {
 //   Dc[d]  = vertical candidate of that cell: P - 4 if its code is '|' (extend, -1) else (P|3) - 46 (open, -11)
 //   Ip     = horizontal candidate of the cell to the left: P - 4 if its code is '-' else (P|3) - 45
 // Row maximum with "first column wins" = max over (P|3)*32 + (31 - d).
+// Instruction diet of the cell (ncu: the kernel is issue / alu-pipe bound):
+//   * substitution score: the table is [class1][256] int8, 256-byte aligned, so ONE PRMT splices the class-0
+//     byte of the window into the row's base address (no extract + add), then LDS.S8;
+//   * the two "extend or open" candidates are P - adj[t] with adj looked up by PRMT from a packed constant
+//     (t = trace code in the low bits of P), instead of compare + select + subtract;
+//   * the 2-bit trace codes are shifted into the row word with one funnel shift (SHF) per cell.
+__device__ __forceinline__ uint32_t prmt_u32(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ int lds_s8(uint32_t addr) {
+    int v;
+    asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 template <bool EDGE>
-__device__ __forceinline__ void dp_row(int i, int len0, bool live, int c1base, const int8_t *s_tbl4, int (&S3)[32],
+__device__ __forceinline__ void dp_row(int i, int len0, bool live, uint32_t rowbase, uint32_t ksel, int (&S3)[32],
                                        int (&Dc)[33], const uint32_t (&W)[8], uint32_t &tlo, uint32_t &thi,
                                        int &rowkey) {
+    // horizontal / vertical candidate = P - adj[t]:  extend (-1) when the trace code allows it, else open (-11);
+    // every candidate carries its own trace code in the low bits (I: 2, D: 1)
+    const uint32_t KI = 42u | (43u << 8) | (4u << 16) | (45u << 24);   // t = 0, 1, 2 ('-': P - 4), 3
+    const uint32_t KD = 43u | (4u << 8) | (45u << 16) | (46u << 24);   // t = 0, 1 ('|': P - 4), 2, 3
     int Ip = -42;  // left of lane 0: guard cell / column 0 -> score 0, not '-' -> (0 - 11) * 4 + 2
-    tlo = 0;
-    thi = 0;
+    uint32_t acc = 0;
+    int keyprev = 0;
     rowkey = 0;
 #pragma unroll
     for (int d = 0; d < 32; d++) {
-        const int c0 = (W[d >> 2] >> ((d & 3) * 8)) & 0xff;
-        const int sub4 = s_tbl4[c1base + c0];
-        const int Mp = S3[d] + sub4;
+        const uint32_t addr = prmt_u32(W[d >> 2], rowbase, 0x7650u | (uint32_t)(d & 3));
+        const int Mp = S3[d] + lds_s8(addr);
         int P = __vimax3_s32_relu(Ip, Mp, Dc[d + 1]);
         if (EDGE) {
             const bool valid = live && (unsigned)(i + d - 17) < (unsigned)len0;  // 1 <= j < l0
             if (!valid) P = 0;  // score 0, code '*': contributes I = D = open from 0, M from 0
         }
-        const int t = P & 3;
+        const uint32_t tsel = ((uint32_t)P & 3u) | ksel;
+        Ip = P - (int)prmt_u32(KI, 0u, tsel);
+        Dc[d] = P - (int)prmt_u32(KD, 0u, tsel);
         const int P3 = P | 3;
-        const int Pm4 = P - 4;
-        Ip = (t == 2) ? Pm4 : P3 - 45;
-        Dc[d] = (t == 1) ? Pm4 : P3 - 46;
         S3[d] = P3;
-        rowkey = max(rowkey, P3 * 32 + (31 - d));
-        if (d < 16)
-            tlo |= (uint32_t)t << (2 * d);
+        const int key = P3 * 32 + (31 - d);
+        if (d & 1)
+            rowkey = __vimax3_s32(rowkey, keyprev, key);
         else
-            thi |= (uint32_t)t << (2 * (d - 16));
+            keyprev = key;
+        acc = __funnelshift_r(acc, (uint32_t)P, 2);  // the code of cell d ends up at bits 2d (mod 32)
+        if (d == 15) tlo = acc, acc = 0;
     }
+    thi = acc;
 }
 
 __global__ void __launch_bounds__(128) k_banded_dp(const AlnTask *__restrict__ tasks, int n,
                                                    const uint64_t *__restrict__ warp_base,
-                                                   uint64_t *__restrict__ trace, DpOut *__restrict__ out) {
-    __shared__ int8_t s_tbl4[kClasses * kClasses];  // 4 * BLOSUM62 (fits int8: -16 .. 44)
+                                                   uint64_t *__restrict__ trace, DpOut *__restrict__ out, uint32_t ksel) {
+    // ksel = 0x4440 (PRMT selector: byte t of the constant, zeros above); a kernel argument so that it stays in a
+    // register and (P & 3) | ksel is ONE LOP3 instead of two with immediates
+    __shared__ __align__(256) int8_t s_tbl4[kClasses * 256];  // 4 * BLOSUM62 (fits int8: -16 .. 44), row stride 256
     __shared__ uint8_t s_code[256];
-    for (int k = threadIdx.x; k < kClasses * kClasses; k += blockDim.x) s_tbl4[k] = (int8_t)(4 * c_score[k]);
+    for (int k = threadIdx.x; k < kClasses * kClasses; k += blockDim.x)
+        s_tbl4[(k / kClasses) * 256 + (k % kClasses)] = (int8_t)(4 * c_score[k]);
+    const uint32_t tblbase = (uint32_t)__cvta_generic_to_shared(s_tbl4);
+
     for (int k = threadIdx.x; k < 256; k += blockDim.x) s_code[k] = c_code[k];
     __syncthreads();
 
@@ -139,14 +166,14 @@ __global__ void __launch_bounds__(128) k_banded_dp(const AlnTask *__restrict__ t
     int best3 = 3, besti = 0, bestd = 0;  // best3 = (best score) * 4 + 3
     for (int i = 1; i <= wrows; i++) {
         const bool live = i <= nrows;
-        const int c1base = live ? (int)s_code[tk.s1[i - 1]] * kClasses : 0;
+        const uint32_t rowbase = tblbase + (live ? (uint32_t)s_code[tk.s1[i - 1]] << 8 : 0u);
         uint32_t tlo, thi;
         int rowkey;
         const bool interior = live && i >= 17 && i + 15 <= len0;
         if (__all_sync(0xffffffffu, interior))
-            dp_row<false>(i, len0, live, c1base, s_tbl4, S3, Dc, W, tlo, thi, rowkey);
+            dp_row<false>(i, len0, live, rowbase, ksel, S3, Dc, W, tlo, thi, rowkey);
         else
-            dp_row<true>(i, len0, live, c1base, s_tbl4, S3, Dc, W, tlo, thi, rowkey);
+            dp_row<true>(i, len0, live, rowbase, ksel, S3, Dc, W, tlo, thi, rowkey);
         if (live) tr[(size_t)(i - 1) * 32] = ((uint64_t)thi << 32) | tlo;
         // first strict maximum in row-major order (fsearch.py:1401)
         const int rs = rowkey >> 5;
@@ -345,7 +372,7 @@ int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
     SO_CUDA(cudaMemcpyAsync(d_wb, wbase.data(), b_wb, cudaMemcpyHostToDevice, c->stream_aln));
     const int grid = (int)((n + 127) / 128);
     SO_CUDA(cudaEventRecord(c->ev_aln[0], c->stream_aln));
-    k_banded_dp<<<grid, 128, 0, c->stream_aln>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp);
+    k_banded_dp<<<grid, 128, 0, c->stream_aln>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp, 0x4440u);
     SO_CUDA(cudaEventRecord(c->ev_aln[1], c->stream_aln));
     k_traceback<<<grid, 128, 0, c->stream_aln>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp, d_tb);
     SO_CUDA(cudaEventRecord(c->ev_aln[2], c->stream_aln));
