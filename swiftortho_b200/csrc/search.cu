@@ -1251,7 +1251,9 @@ __global__ void __launch_bounds__(256) k_pair_select(const uint32_t *__restrict_
             const unsigned long long o = s_base + s_wcount[warp] + __popc(m & ((1u << lane) - 1));
             const int hd1 = (int)(pair & hdmask);
             const int qi = (int)(pair >> g.hd_bits);
-            ckeys[o] = ((uint64_t)qi << rank_bits) | first_rank;
+            // between the candidates of one query (distinct targets) qst | (max - sequence) already orders the first
+        // ranks, so the sst part is dropped from the sort key (one radix pass less)
+        ckeys[o] = ((uint64_t)qi << rank_bits) | (grank ? first_rank : first_rank >> g.diag_bits);
             // value: target ordinal (24 bits) | score (20 bits) | diagonal + bias (20 bits)
             cvals[o] = ((uint64_t)(uint32_t)(g.c0 + hd1 - 1) << 40) | ((uint64_t)(uint32_t)best_score << 20) |
                        (uint64_t)(uint32_t)(best_diag + kCandDiagBias);
@@ -1453,7 +1455,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             uint32_t *vb = keys_only ? nullptr : (uint32_t *)scratch[SC_VB].p;
             const int key_bits = g.qst_bits + g.diag_bits + g.hd_bits + q_bits;
             // candidate sort key: query | first-appearance rank (see k_pair_select)
-            const int rank_bits = (AS == 1 && !getenv("SO_FORCE_PAIRS")) ? g.qst_bits + g.diag_bits + g.hd_bits : 32;
+            const int rank_bits = (AS == 1 && !getenv("SO_FORCE_PAIRS")) ? g.qst_bits + g.hd_bits : 32;
             cub::DoubleBuffer<uint64_t> dk(ka, kb);
             cub::DoubleBuffer<uint32_t> dv(va, vb);
             unsigned long long *d_counter = (unsigned long long *)(scratch[SC_MISC].p);
