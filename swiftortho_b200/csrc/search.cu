@@ -818,6 +818,9 @@ __global__ void __launch_bounds__(256) k_group_ungap_generic(const uint64_t *__r
 // ---------------------------------------------------------------------------------------------
 enum { kUngPad = 64, kUngStop = 24, kUngSkip = 25, kUngRows = 26, kUngTabBytes = kUngRows * 32 * 32 * 4 };
 static const uint32_t kDescSingle = 1u << 24, kDescNoLeft = 1u << 25;
+// chained group of exactly two seeds whose qst differ by 1..32 (the usual chain: two overlapping k-mers):
+// bit 26 + (delta - 1) in bits 27..31, so k_xdrop never has to read the hits of such a group
+static const uint32_t kDescPair = 1u << 26;
 
 __global__ void __launch_bounds__(256) k_ung_fill(const uint8_t *__restrict__ cls, uint32_t n, uint8_t *__restrict__ dst,
                                                   uint32_t offF, uint32_t offR, uint32_t total, int shift) {
@@ -896,7 +899,12 @@ __global__ void __launch_bounds__(256) k_group_desc(const uint64_t *__restrict__
             const int sst = qst - diag;
             const uint32_t xt = (uint32_t)toff[g.c0 + hd1 - 1] + (uint32_t)sst;
             const uint32_t uq = (uint32_t)(qoff[g.qb0 + qi] - qa) + (uint32_t)qst;
-            desc[gi] = make_uint2(xt, uq | (multi ? 0u : kDescSingle) | ((qst == 0 || sst == 0) ? kDescNoLeft : 0u));
+            uint32_t flags = (multi ? 0u : kDescSingle) | ((qst == 0 || sst == 0) ? kDescNoLeft : 0u);
+            if (multi && !(p + 2 < n && (keys[p + 2] >> shift) == (k >> shift))) {
+                const uint32_t delta = (uint32_t)(keys[p + 1] & ((1ull << g.qst_bits) - 1)) - (uint32_t)qst;
+                if (delta >= 1 && delta <= 32) flags |= kDescPair | ((delta - 1) << 27);
+            }
+            desc[gi] = make_uint2(xt, uq | flags);
             if (vals) grank[gi] = vals[p];  // k_xdrop folds the other hits of a chained group in
         }
     }
@@ -1001,7 +1009,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
     constexpr int kNoLimit = 1 << 30;
     const unsigned long long kBatch = 512;  // group indices taken per atomic
     int alive = 0;
-    bool has = false, fin = false, noleft = false, multi = false, chained = false;
+    bool has = false, fin = false, noleft = false, multi = false, chained = false, pairm = false;
     bool w1 = false, w2 = false;
     int phase = 0, acc = 0, v = 0, d = 0, lim = kNoLimit;
     int qcur = 0, lo = 0;                  // chains: qst of the seed being extended, max_qed of the last segment
@@ -1034,7 +1042,14 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 }
                 if (seed_done) {
                     bool more = false;
-                    if (multi) {
+                    if (multi && pairm) {
+                        // two-seed chain described by k_group_desc: e = qst distance of the second seed
+                        if (!chained && (int)e > lo) {
+                            xt += e, uq += e;
+                            qcur = (int)e;
+                            more = true;
+                        }
+                    } else if (multi) {
                         // next seed of the chain: seeds at or below max_qed extend nothing and leave it unchanged
                         for (;;) {
                             e++;
@@ -1082,9 +1097,12 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                         uq = ds.y & 0xffffffu;
                         noleft = (ds.y & kDescNoLeft) != 0;
                         multi = (ds.y & kDescSingle) == 0;
-                        qcur = 0;
-                        if (multi) {
-                            nmulti++;
+                        qcur = 0;  // chains only use qst differences: the first seed of a described pair counts from 0
+                        pairm = multi && (ds.y & kDescPair) != 0 && vals == nullptr;
+                        if (multi) nmulti++;
+                        if (pairm)
+                            e = (ds.y >> 27) + 1u;
+                        else if (multi) {
                             e = gheads[mine];
                             qcur = (int)((uint32_t)keys[e] & qmask);
                         }
