@@ -556,10 +556,31 @@ __global__ void __launch_bounds__(256) k_cell_warp(const uint32_t *__restrict__ 
             my_n = cell_base[my_c + 1] - my_off;
         }
         const int cells = (int)min(32u, nlist - w0);
+        // cells of up to 32 hits (most of them): one key per lane, ranks by shuffles, the next cell's key is in
+        // flight while the current one is ranked; larger cells go through shared memory
+        uint32_t nx = 0;
+        {
+            const uint32_t off0 = __shfl_sync(0xffffffffu, my_off, 0), n0 = __shfl_sync(0xffffffffu, my_n, 0);
+            if ((uint32_t)lane < n0 && n0 <= 32u) nx = sub[off0 + lane];
+        }
         for (int t = 0; t < cells; t++) {
             const uint32_t c = __shfl_sync(0xffffffffu, my_c, t), off = __shfl_sync(0xffffffffu, my_off, t);
             const uint32_t n = __shfl_sync(0xffffffffu, my_n, t);
             const uint64_t upper = cell_upper(c, NB, g);
+            const uint32_t x1 = nx;
+            if (t + 1 < cells) {
+                const uint32_t off1 = __shfl_sync(0xffffffffu, my_off, t + 1), n1 = __shfl_sync(0xffffffffu, my_n, t + 1);
+                if ((uint32_t)lane < n1 && n1 <= 32u) nx = sub[off1 + lane];
+            }
+            if (n <= 32u) {
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < n; j++) {
+                    const uint32_t y = __shfl_sync(0xffffffffu, x1, (int)j);
+                    rank += (y < x1 || (y == x1 && j < (uint32_t)lane)) ? 1u : 0u;
+                }
+                if ((uint32_t)lane < n) keys[off + rank] = upper | (uint64_t)x1;
+                continue;
+            }
             for (uint32_t i = lane; i < n; i += 32) sk[i] = sub[off + i];
             __syncwarp();
             for (uint32_t i = lane; i < n; i += 32) {
@@ -1086,6 +1107,9 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                     else {
                         pool_next = (uint32_t)base;
                         pool_end = (uint32_t)min((unsigned long long)G, base + kBatch);
+                        // the batch's descriptors (512 x 8 B = 32 lines) are pulled into L2 ahead of their use
+                        if (pool_next + (uint32_t)lane * 16u < pool_end)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(desc + pool_next + lane * 16));
                     }
                 }
                 if (!has && !fin) {
@@ -1326,11 +1350,11 @@ enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TM
 
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
 
-static int g_xdrop_refill = 20;  // idle lanes that trigger a refill in k_xdrop (SO_XDROP_REFILL: tuning hook)
+static int g_xdrop_refill = 24;  // idle lanes that trigger a refill in k_xdrop (SO_XDROP_REFILL: tuning hook)
 
 int upload_search_config(so_ctx *c) {
     const char *e = getenv("SO_XDROP_REFILL");
-    g_xdrop_refill = e ? atoi(e) : 20;
+    g_xdrop_refill = e ? atoi(e) : 24;
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
