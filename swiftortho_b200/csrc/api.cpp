@@ -437,7 +437,8 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     std::vector<so_hit> all_rows;
     const size_t nch = c->chunks.size();
     // query block size: candidates of a block are held packed in pinned memory, one buffer per chunk
-    const i64 QB = std::max<i64>(64, std::min<i64>(512, 4096 / (i64)std::max<size_t>(1, nch)));
+    i64 QB = std::max<i64>(64, std::min<i64>(512, 4096 / (i64)std::max<size_t>(1, nch)));
+    if (const char *e = getenv("SO_QUERY_BLOCK")) QB = std::max<i64>(16, atoll(e));  // tuning hook
     const int kSlots = 4;
     if (c->cand_pool.size() < (size_t)kSlots * nch) c->cand_pool.resize((size_t)kSlots * nch);
     {

@@ -19,12 +19,17 @@
 //                    -kscs (order computed once on the host), keep while the running bucket total
 //                    is <= threshold*len (fsearch.py:2667-2677)
 //   exclusive scan   cub::DeviceScan (library)
-//   k_expand         one warp per kept seed: emits (query, target, diagonal, qst) keys + the hit's
-//                    ordinal in the reference's scan order (its "first appearance" rank)
-//   radix sort       cub::DeviceRadixSort (library) on the packed key
-//   k_pair_ungap     one thread per (query, target) run of the sorted hits: per diagonal the
-//                    chained X-drop-30 extension (ungap / get_ungap_scores, fsearch.py:2454-2509),
-//                    threshold 25, best diagonal with first-appearance tie break, candidate order
+//   grouping         one pattern + one alphabet: k_cell_pass<false/true> partition the hits into (query, target)
+//                    cells, k_cell_small / k_cell_warp / k_cell_block order every cell by (diagonal, qst) -> the
+//                    sorted 64-bit keys (query | target | diagonal | qst).  Otherwise: k_expand (key + the hit's
+//                    ordinal in the reference's scan order = its "first appearance" rank) and
+//                    cub::DeviceRadixSort (library) on the packed key
+//   head flags       cub::DeviceScan over "first hit of a (query, target, diagonal) group" -> group index
+//   k_group_desc     group heads, head keys, X-drop descriptors (two-seed chains carried inline)
+//   k_xdrop          chained X-drop-30 extension of every group (ungap / get_ungap_scores,
+//                    fsearch.py:2454-2509); k_group_ungap_generic for sequences >= 8192 residues
+//   compaction       cub::DeviceSelect: groups with score >= 25, in order
+//   k_pair_select    per (query, target): best diagonal with first-appearance tie break, candidate order
 //                    key = rank of the first passing diagonal (fsearch.py:2696-2719)
 //   radix sort       candidates by (query, first-passing rank) -> reference candidate order
 #include <cub/cub.cuh>
@@ -1191,33 +1196,6 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
     if (lane == 0 && nmulti) atomicAdd(counters + 3, (unsigned long long)nmulti);  // statistic
 }
 
-// Keys-only path (one pattern, one alphabet): the hit ordinal is not carried through the sort.  The
-// sort is stable and hits are generated in ordinal order, so the first hit of a group has the group's
-// smallest ordinal; it is recomputed here, only for groups that pass the threshold, as
-// slot_out[slot(query, qst)] + position of the locus entry (target, sst) inside the seed's bucket range
-// (bucket entries are in descending locus order = descending (sequence, position)).
-struct RankCtx {
-    const uint32_t *slot_off, *slot_st, *slot_cnt;
-    const uint64_t *slot_out;
-    const uint2 *hdsst;
-};
-
-__device__ __forceinline__ uint32_t recompute_rank(const RankCtx &rc, int qi, int qst, uint32_t hd1, uint32_t sst) {
-    const uint32_t slot = rc.slot_off[qi] + (uint32_t)qst;
-    const uint32_t st = rc.slot_st[slot];
-    uint32_t lo = 0, hi = rc.slot_cnt[slot];  // first entry <= (hd1, sst) in a descending list
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        const uint2 e = rc.hdsst[st + mid];
-        const bool greater = e.x > hd1 || (e.x == hd1 && e.y > sst);
-        if (greater)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    return (uint32_t)rc.slot_out[slot] + lo;
-}
-
 // Pair selection over the PASSING groups only (score >= 25, self.min: fsearch.py:2224, 2707): `plist` holds
 // their group indices in ascending order (ordered stream compaction, cub::DeviceSelect), ~8 % of all groups.
 // One thread per passing group; the first passing group of a (query, target) pair folds the pair: best
@@ -1396,6 +1374,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
     const int AS = (int)(P.alphabets.size() * P.patterns.size());
     const i64 M = ix.c1 - ix.c0;
     i64 sub = c->sub_block > 0 ? c->sub_block : 256;
+    if (const char *e = getenv("SO_SUB_BLOCK0")) sub = std::max<i64>(1, atoll(e));  // tuning hook: first sub-block
     i64 b0 = q_begin;
     cudaStream_t st = lane ? c->stream1 : c->stream;
     while (b0 < q_end) {
@@ -1486,7 +1465,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
         if (H > 0) {
             if ((rc = scratch[SC_KA].reserve((size_t)H * 8)) != SO_OK) return rc;
             if ((rc = scratch[SC_KB].reserve((size_t)H * 8)) != SO_OK) return rc;
-            // one pattern + one alphabet: keys-only sort that skips the qst bits (see RankCtx)
+            // one pattern + one alphabet: the hit ordinal is not carried along (k_pair_select rebuilds the rank from the key)
             const bool keys_only = AS == 1 && !getenv("SO_FORCE_PAIRS");
             if (!keys_only) {
                 if ((rc = scratch[SC_VA].reserve((size_t)H * 4)) != SO_OK) return rc;
