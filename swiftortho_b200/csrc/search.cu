@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__
     __shared__ int s_qi;
     __shared__ uint32_t s_next_slot;
     const int lane = threadIdx.x & 31;
-    constexpr int U = 4;  // bucket rows in flight per warp (the loop is latency bound)
+    constexpr int U = SCATTER ? 4 : 8;  // bucket rows in flight per warp (the loops are latency bound)
     for (;;) {            // CTAs draw queries from a counter: no wave quantisation with one 200 KB CTA per SM
         if (threadIdx.x == 0) {
             s_qi = (int)atomicAdd(next_query, 1u);
