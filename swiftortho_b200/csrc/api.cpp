@@ -245,18 +245,14 @@ int so_set_queries(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, 
     int rc = check_offsets(offsets, n, c->max_qlen, "query");
     if (rc != SO_OK) return rc;
     Timer tm;
-    if (c->d_qres) cudaFree(c->d_qres);
-    if (c->d_qoff) cudaFree(c->d_qoff);
-    if (c->d_perm) cudaFree(c->d_perm);
-    if (c->d_qcls) cudaFree(c->d_qcls);
-    c->d_qres = nullptr, c->d_qoff = nullptr, c->d_perm = nullptr, c->d_qcls = nullptr;
     c->n_q = n;
     c->q_off.assign(offsets, offsets + n + 1);
     const uint64_t base = offsets[0];
     for (auto &v : c->q_off) v -= base;
     const size_t bytes = (size_t)c->q_off[(size_t)n];
-    c->q_masked.assign(bytes, 0);
-    std::vector<uint32_t> perm(bytes, 0);
+    c->q_masked.resize(bytes);
+    std::vector<uint32_t> &perm = c->q_perm_host;
+    perm.resize(bytes);
     const bool flt = c->P.flt;
     const int mink = c->P.mink;
     const uint8_t *src = residues + base;
@@ -287,13 +283,28 @@ int so_set_queries(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, 
         for (i64 i = 0; i < P; i++) pp[i] = (uint32_t)v[(size_t)i];
     });
     const double t_host = tm.ms();
-    SO_CUDA(cudaMalloc((void **)&c->d_qres, bytes + 64));
-    SO_CUDA(cudaMalloc((void **)&c->d_qoff, ((size_t)n + 1) * 8));
-    SO_CUDA(cudaMalloc((void **)&c->d_perm, (bytes + 16) * 4));
+    // device buffers grow only: so_set_queries is called once per query block on the end-to-end path
+    if (bytes > c->q_cap_bytes || !c->d_qres) {
+        if (c->d_qres) cudaFree(c->d_qres);
+        if (c->d_perm) cudaFree(c->d_perm);
+        if (c->d_qcls) cudaFree(c->d_qcls);
+        c->d_qres = nullptr, c->d_perm = nullptr, c->d_qcls = nullptr;
+        const size_t cap = bytes + bytes / 4 + 4096;
+        SO_CUDA(cudaMalloc((void **)&c->d_qres, cap + 64));
+        SO_CUDA(cudaMalloc((void **)&c->d_perm, (cap + 16) * 4));
+        SO_CUDA(cudaMalloc((void **)&c->d_qcls, cap + 64));
+        c->q_cap_bytes = cap;
+    }
+    if ((size_t)n > c->q_cap_seqs || !c->d_qoff) {
+        if (c->d_qoff) cudaFree(c->d_qoff);
+        c->d_qoff = nullptr;
+        const size_t cap = (size_t)n + (size_t)n / 4 + 64;
+        SO_CUDA(cudaMalloc((void **)&c->d_qoff, (cap + 1) * 8));
+        c->q_cap_seqs = cap;
+    }
     SO_CUDA(cudaMemcpyAsync(c->d_qres, dst, bytes, cudaMemcpyHostToDevice, c->stream));
     SO_CUDA(cudaMemcpyAsync(c->d_qoff, qo, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     SO_CUDA(cudaMemcpyAsync(c->d_perm, perm.data(), bytes * 4, cudaMemcpyHostToDevice, c->stream));
-    SO_CUDA(cudaMalloc((void **)&c->d_qcls, bytes + 64));
     if ((rc = so::classify_residues(c, c->d_qres, c->d_qcls, bytes)) != SO_OK) return rc;
     SO_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.h2d_bytes += (i64)bytes * 5 + ((i64)n + 1) * 8;

@@ -133,6 +133,8 @@ struct so_ctx {
     uint32_t tung_off[2] = {0, 0};
     uint64_t *d_toff = nullptr, *d_qoff = nullptr;
     uint32_t *d_perm = nullptr;               // per query: positions in the reference quicksort order of -kscs (S3)
+    size_t q_cap_bytes = 0, q_cap_seqs = 0;   // capacity of the query buffers (grow-only: so_set_queries runs per block)
+    std::vector<uint32_t> q_perm_host;        // reused host staging of d_perm
     so::i64 sub_block = 0;                    // >0: fixed number of queries per seeding sub-block (tests)
     uint32_t max_qlen = 0, max_tlen = 0;
 

@@ -1288,8 +1288,14 @@ __global__ void __launch_bounds__(256) k_classify(const uint8_t *__restrict__ in
 }
 
 int classify_residues(so_ctx *c, const uint8_t *d_in, uint8_t *d_out, size_t n) {
-    int rc = upload_cfg(c->P);
-    if (rc != SO_OK) return rc;
+    // the byte -> class table does not depend on the search parameters: one upload per device
+    static bool uploaded[64] = {};
+    if (c->device < 0 || c->device >= 64 || !uploaded[c->device]) {
+        uint8_t code[256];
+        make_code_table(code);
+        SO_CUDA(cudaMemcpyToSymbol(c_code2, code, sizeof code));
+        if (c->device >= 0 && c->device < 64) uploaded[c->device] = true;
+    }
     if (n == 0) return SO_OK;
     k_classify<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_in, d_out, n);
     SO_CUDA(cudaGetLastError());
