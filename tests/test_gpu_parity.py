@@ -305,6 +305,25 @@ def test_full_size_config2_window_against_oracle(so, oracle, tmp_path):
     assert firsts > 0.95 * 1024
 
 
+@pytest.mark.parametrize('cfg,n,taxa,ssd,ev,lo', [(5, 100000, 20, '111111', '1e-5', 2000),
+                                                  (4, 100000, 20, '1110100111', '1e-3', 3000)])
+def test_full_size_configs_4_5_window_against_oracle(so, oracle, tmp_path, cfg, n, taxa, ssd, ev, lo):
+    """BASELINE config 5 (long-tailed lengths 50-5000: >= 4096 tiles, 13-bit qst, 100 000 targets) at full size and
+    config 4's flag set (spaced seed 1110100111, -e 1e-3: denser candidates) on 100 000 of its 250 000 proteins:
+    a 16-query window against the complete target set gives the oracle's file byte for byte."""
+    from swiftortho_b200 import synth
+    p = str(tmp_path / 'c.fsa')
+    synth.write_config(p, cfg, n=n, taxa=taxa)
+    flags = {'-e': ev, '-j': '1', '-M': '120000000', '-c': '50000', '-s': ssd, '-l': str(lo), '-u': str(lo + 16)}
+    ref = str(tmp_path / 'oracle.sc')
+    oracle.blastp(p, p, ref, flags)
+    out = str(tmp_path / 'gpu.sc')
+    so.blastp(p, p, out, expect=float(ev), step=1, ht=120000000, chk=50000, ssd=ssd, st=lo, ed=lo + 16)
+    exp = open(ref, 'rb').read()
+    assert exp.count(b'\n') >= 16
+    assert open(out, 'rb').read() == exp
+
+
 def test_search_long_tailed_config5_against_oracle(so, oracle, tmp_path):
     """Config 5 shape (log-normal lengths up to 5000: the >= 4096 tile path) scaled down."""
     p = _synth(tmp_path, 300, 6, 20261022, lengths='lognormal')
