@@ -276,10 +276,8 @@ def run_ours(args, rank, world, local):
         off = np.ascontiguousarray(F.offsets[a:b + 1])
         so.check(lib.so_set_queries(S.h, C.c_void_p(res_ptr), off.ctypes.data, b - a))
         rows = S.search(0, b - a)
-        arr = rows.as_array()      # result records are host memory already (D2H happened inside so_search)
-        arr['query'] += a
-        hits = (so.so_hit * max(1, len(arr))).from_buffer_copy(arr.tobytes() if len(arr) else bytes(C.sizeof(so.so_hit)))
-        so.check(lib.so_write_rows(hits, len(arr), F.h, F.h, outp.encode(), 0))
+        rows.view()['query'] += a  # result records are host memory already (D2H happened inside so_search)
+        so.check(lib.so_write_rows(rows.ptr, rows.n, F.h, F.h, outp.encode(), 0))
         if s >= args.warmup:
             e2e_q += b - a
     barrier()

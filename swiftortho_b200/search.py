@@ -49,9 +49,6 @@ class Fasta:
             return ['', '']
         return [self.header(i), self.sequence(i)]
 
-    def set_lanes(self, n):
-        check(self.lib.so_set_lanes(self.h, int(n)))
-
     def close(self):
         if self.h:
             self.lib.so_fasta_close(self.h)
@@ -165,12 +162,16 @@ class _Rows:
     def __init__(self, lib, ptr, n):
         self.lib, self.ptr, self.n = lib, ptr, n
 
-    def as_array(self):
+    def view(self):
+        """numpy structured view of the library-owned row records (no copy; valid while this object lives)."""
         dt = np.dtype([(k, np.dtype(t)) for k, t in so_hit._fields_])
         if self.n == 0:
             return np.zeros(0, dtype=dt)
         return np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)),
-                                     shape=(self.n * C.sizeof(so_hit),)).view(dt).copy()
+                                     shape=(self.n * C.sizeof(so_hit),)).view(dt)
+
+    def as_array(self):
+        return self.view().copy()
 
     def __del__(self):
         try:
