@@ -9,6 +9,9 @@ F = so.Fasta(p)
 S = so.Searcher(device=0, **bench.FLAGS)
 t = time.time(); S.set_targets(F); S.set_queries(F); info = S.build_index(); print('setup %.1f s, %d chunks' % (time.time() - t, len(info)), flush=True)
 t = time.time(); rows = S.search(0, nq); dt = time.time() - t
+print('cold: %.2f s' % dt, flush=True)
+S.stats(reset=True)
+t = time.time(); rows = S.search(nq, 2 * nq); dt = time.time() - t   # warm: buffers allocated
 a = rows.as_array()
 st = S.stats()
 print('search %d queries vs %d targets: %.2f s (%.0f q/s) rows %d' % (nq, n, dt, nq / dt, len(a)))
@@ -16,6 +19,7 @@ print(json.dumps({k: (round(v, 1) if isinstance(v, float) else v) for k, v in st
 # properties: rows grouped by ascending query, bit non-increasing within a query, every unmasked query hits itself first
 import numpy as np
 q = a['query']; assert np.all(np.diff(q) >= 0)
+assert q.min() >= nq
 same = np.diff(q) == 0
 assert np.all(np.diff(a['bit'])[same] <= 0)
 first = np.concatenate([[True], ~same])
