@@ -233,11 +233,13 @@ def test_search_baseline_flags_against_oracle(so, oracle, tmp_path):
 
 
 @pytest.mark.parametrize('env', [{'SO_CUB_SORT': '1'}, {'SO_GENERIC_UNGAP': '1'}, {'SO_NO_SINGLE': '1'},
-                                 {'SO_FORCE_PAIRS': '1'}, {'SO_XDROP_REFILL': '8'}])
+                                 {'SO_FORCE_PAIRS': '1'}, {'SO_XDROP_REFILL': '8'},
+                                 {'SO_QUERY_BLOCK': '64', 'SO_SUB_BLOCK0': '37'}])
 def test_alternative_code_paths_against_oracle(so, oracle, tmp_path, env):
     """Every fallback / alternative device path gives the oracle's file too: device-wide radix sort instead of the
     cell partition, the generic chained X-drop kernel instead of k_xdrop, hit ordinals carried through a pairs
-    sort, another refill threshold.  (The library reads these variables per call.)"""
+    sort, another refill threshold, odd query-block / sub-block sizes.  (The library reads these variables per
+    call.)"""
     p = _synth(tmp_path, 700, 8, 20261023)
     ref = str(tmp_path / 'oracle.sc')
     oracle.blastp(p, p, ref, {'-e': '1e-5', '-j': '1', '-M': '120000000', '-c': '400', '-s': '111111'})
