@@ -430,11 +430,16 @@ template <bool SCATTER>
 __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__ slot_off, BlockGeom g,
                                                     const uint64_t *__restrict__ qoff,
                                                     const uint32_t *__restrict__ slot_st, const uint32_t *__restrict__ slot_cnt,
-                                                    const uint2 *__restrict__ hdsst, uint32_t NB,
+                                                    const uint2 *__restrict__ hdsst, uint32_t NB, uint32_t nsplit,
                                                     uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ cell_base,
                                                     uint32_t *__restrict__ sub, uint32_t *__restrict__ max_cell,
                                                     uint32_t *__restrict__ next_query) {
-    extern __shared__ uint32_t s_cell[];  // [NB] per-target counters (count pass) or write cursors (scatter pass)
+    // a work item is (query, one of `nsplit` target ranges): with two ranges the counters of a CTA need half the
+    // shared memory, two CTAs (64 warps) fit an SM and hide the latency of this loop better; every CTA walks all
+    // bucket lists of its query and keeps the hits of its range (lists are in descending target order, so the
+    // upper ranges stop early)
+    extern __shared__ uint32_t s_cell[];  // [NB / nsplit] per-target counters (count pass) or write cursors (scatter pass)
+    const uint32_t NBh = (NB + nsplit - 1) / nsplit;
     __shared__ int s_qi;
     __shared__ uint32_t s_next_slot;
     const int lane = threadIdx.x & 31;
@@ -445,9 +450,11 @@ __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__
             s_next_slot = 0;
         }
         __syncthreads();
-        const int qi = s_qi;
-        if (qi >= g.nq) break;
-        for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cell[b] = SCATTER ? cell_base[(size_t)qi * NB + b] : 0u;
+        if ((uint32_t)s_qi >= (uint32_t)g.nq * nsplit) break;
+        const int qi = (int)((uint32_t)s_qi / nsplit);
+        const uint32_t lo = ((uint32_t)s_qi % nsplit) * NBh, span = min(NB, lo + NBh) - lo;  // targets [lo, lo + span)
+        for (uint32_t b = threadIdx.x; b < span; b += blockDim.x)
+            s_cell[b] = SCATTER ? cell_base[(size_t)qi * NB + lo + b] : 0u;
         __syncthreads();
         const uint32_t so0 = slot_off[qi], nsl = slot_off[qi + 1] - so0;
         const int L = (int)(qoff[g.qb0 + qi + 1] - qoff[g.qb0 + qi]);
@@ -460,34 +467,42 @@ __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__
             if (cnt == 0) continue;
             const uint32_t st = slot_st[so0 + sl];
             const int qst = (int)(sl % (uint32_t)L);
-            for (uint32_t k0 = lane; k0 < cnt; k0 += 32 * U) {
+            for (uint32_t kb = 0; kb < cnt; kb += 32 * U) {  // warp-uniform trip count (the loop votes)
+                const uint32_t k0 = kb + (uint32_t)lane;
                 uint2 e[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     const uint32_t k = k0 + 32u * u;
                     e[u] = k < cnt ? hdsst[st + k] : make_uint2(0u, 0u);
                 }
+                bool below = false;
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     if (e[u].x == 0) continue;  // past the end, or the reference's "sequence -1" (never scores): dropped
+                    const uint32_t b = e[u].x - lo;
+                    if (b >= span) {            // another range's target
+                        below |= e[u].x < lo;
+                        continue;
+                    }
                     if (!SCATTER)
-                        atomicAdd(&s_cell[e[u].x], 1u);
+                        atomicAdd(&s_cell[b], 1u);
                     else {
                         // only the cell-local part (diagonal | qst) is stored: 4 B per hit keep the partially
                         // written sectors of the queries in flight inside L2
-                        const uint32_t pos = atomicAdd(&s_cell[e[u].x], 1u);
+                        const uint32_t pos = atomicAdd(&s_cell[b], 1u);
                         const int diag = qst - (int)e[u].y + g.diag_bias;
                         sub[pos] = ((uint32_t)diag << g.qst_bits) | (uint32_t)qst;
                     }
                 }
+                if (__any_sync(0xffffffffu, below)) break;  // descending targets: nothing of this range is left
             }
         }
         __syncthreads();
         if (!SCATTER) {
             uint32_t mx = 0;
-            for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) {
+            for (uint32_t b = threadIdx.x; b < span; b += blockDim.x) {
                 const uint32_t v = s_cell[b];
-                cell_count[(size_t)qi * NB + b] = v;
+                cell_count[(size_t)qi * NB + lo + b] = v;
                 mx = max(mx, v);
             }
             mx = __reduce_max_sync(0xffffffffu, mx);
@@ -1334,11 +1349,14 @@ enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TM
 
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
 
-static int g_xdrop_refill = 24;  // idle lanes that trigger a refill in k_xdrop (SO_XDROP_REFILL: tuning hook)
+static int g_xdrop_refill = 24;
+static uint32_t g_cell_split = 0;  // target ranges per query in the cell passes; 0 = as few as fit shared memory (SO_CELL_SPLIT)  // idle lanes that trigger a refill in k_xdrop (SO_XDROP_REFILL: tuning hook)
 
 int upload_search_config(so_ctx *c) {
     const char *e = getenv("SO_XDROP_REFILL");
     g_xdrop_refill = e ? atoi(e) : 24;
+    g_cell_split = 0;
+    if (const char *cs = getenv("SO_CELL_SPLIT")) g_cell_split = (uint32_t)std::max(0, std::min(8, atoi(cs)));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
@@ -1491,7 +1509,10 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             // (SO_CUB_SORT=1 forces the device-wide sort)
             const uint32_t NB = (uint32_t)(M + 2);
             const int Lb = g.qst_bits + g.diag_bits;
-            bool cell_path = keys_only && !getenv("SO_CUB_SORT") && (size_t)NB * 4 <= 220 * 1024 && Lb <= 32 &&
+            // target ranges per query: as few as keep the per-CTA counters within shared memory (1 for -c 50000)
+            const uint32_t nsplit = g_cell_split ? g_cell_split : (uint32_t)(((size_t)NB * 4 + 220 * 1024 - 1) / (220 * 1024));
+            bool cell_path = keys_only && !getenv("SO_CUB_SORT") && nsplit <= 8 &&
+                             (size_t)((NB + nsplit - 1) / nsplit) * 4 <= 220 * 1024 && Lb <= 32 &&
                              (uint64_t)nq * NB < 0x7fffff00ull;
             if (cell_path) {
                 const uint32_t ncells = (uint32_t)nq * NB;
@@ -1502,9 +1523,10 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                 uint32_t *d_lcount = (uint32_t *)(d_counter + 7);  // two u32: warp-list / block-list lengths
                 uint32_t *d_nextq = (uint32_t *)(d_counter + 8);   // two u32: query counters of the two passes
                 SO_CUDA(cudaMemsetAsync(d_ccnt + ncells, 0, 4, st));
-                const int pblocks = std::min(nq, 148);
-                k_cell_pass<false><<<pblocks, 1024, NB * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, d_ccnt,
-                                                                nullptr, nullptr, d_maxcell, d_nextq);
+                const uint32_t NBh = (NB + nsplit - 1) / nsplit;
+                const int pblocks = std::min<int>(nq * (int)nsplit, 148 * (int)nsplit);
+                k_cell_pass<false><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit,
+                                                                 d_ccnt, nullptr, nullptr, d_maxcell, d_nextq);
                 tmp = 0;
                 cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_ccnt, d_cbase, (int)ncells + 1, st);
                 if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
@@ -1520,8 +1542,8 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                     cell_path = false;  // nothing valid / a cell too large for shared memory: device-wide sort
                 else {
                     SO_CUDA(cudaEventRecord(ev[1], st));
-                    k_cell_pass<true><<<pblocks, 1024, NB * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nullptr,
-                                                                   d_cbase, (uint32_t *)kb, nullptr, d_nextq + 1);
+                    k_cell_pass<true><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit,
+                                                                    nullptr, d_cbase, (uint32_t *)kb, nullptr, d_nextq + 1);
                     // queue of the warp-sorted cells = the (now free) count array; CTA-sorted cells: own small buffer
                     if ((rc = scratch[SC_MLIST].reserve(((size_t)h_cell[0] / kCellWarp + 2) * 4)) != SO_OK) return rc;
                     uint32_t *d_wlist = d_ccnt, *d_blist = (uint32_t *)scratch[SC_MLIST].p;

@@ -307,6 +307,22 @@ def test_full_size_config2_window_against_oracle(so, oracle, tmp_path):
     assert firsts > 0.95 * 1024
 
 
+def test_large_chunk_split_cells_against_oracle(so, oracle, tmp_path):
+    """-c 60000: the first chunk holds more targets than one CTA's shared-memory counters cover, so the cell passes
+    split the targets of a query into two ranges (two CTAs per query)."""
+    from swiftortho_b200 import synth
+    p = str(tmp_path / 'c2.fsa')
+    synth.write_config(p, 2, n=100000, taxa=20)
+    ref = str(tmp_path / 'oracle.sc')
+    oracle.blastp(p, p, ref, {'-e': '1e-5', '-j': '1', '-M': '120000000', '-c': '60000', '-s': '111111', '-l': '70000',
+                              '-u': '70012'})
+    out = str(tmp_path / 'gpu.sc')
+    so.blastp(p, p, out, expect=1e-5, step=1, ht=120000000, chk=60000, ssd='111111', st=70000, ed=70012)
+    exp = open(ref, 'rb').read()
+    assert exp.count(b'\n') >= 12
+    assert open(out, 'rb').read() == exp
+
+
 @pytest.mark.parametrize('cfg,n,taxa,ssd,ev,lo', [(5, 100000, 20, '111111', '1e-5', 2000),
                                                   (4, 100000, 20, '1110100111', '1e-3', 3000)])
 def test_full_size_configs_4_5_window_against_oracle(so, oracle, tmp_path, cfg, n, taxa, ssd, ev, lo):
