@@ -63,6 +63,10 @@ int so_seg(const uint8_t *seq, int64_t n, uint8_t *out);
  * ------------------------------------------------------------------------------------------- */
 int so_qsort_perm(const int64_t *keys, int64_t n, int32_t *perm);
 
+/* The same sort on the device (test hook of the H3 selection kernel, csrc/select.cu): perm[min(need, n)]
+ * receives the original indices at positions [0, need) of the reference quicksort of keys[n] (ascending,
+ * 32-bit keys).  Declared after so_ctx below. */
+
 /* ---------------------------------------------------------------------------------------------
  * F   score2bit / e-value text — lib/fsearch.py:1066-1071 `score2bit`, 1086 `bit2e`,
  * 43-61 `f2s`.  so_f2s writes a NUL-terminated string into out[cap].
@@ -167,6 +171,8 @@ typedef struct so_hit {
     double evalue;
 } so_hit;
 int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows, int64_t *n_rows);
+/* Q on the device — lib/fsearch.py:260-327 as run by the candidate selection of so_search (3051, 3059-3062) */
+int so_qsort_prefix_device(so_ctx *c, const uint32_t *keys, int64_t n, int64_t need, uint32_t *perm);
 
 /* F  format rows as the reference's 16-column text (lib/fsearch.py:3233-3243).  Headers come from
  * the two FASTA containers.  Appends to `path` when append != 0. */

@@ -73,6 +73,7 @@ SYMBOLS = {
     'so_fasta_header': (C.c_int, [C.c_void_p, C.c_int64, _P(C.c_char_p), _P(C.c_int64)]),
     'so_seg': (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p]),
     'so_qsort_perm': (C.c_int, [_P(C.c_int64), C.c_int64, _P(C.c_int32)]),
+    'so_qsort_prefix_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     'so_score2bit': (C.c_int64, [C.c_int64]),
     'so_bit2e': (C.c_double, [C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     'so_f2s': (C.c_int, [C.c_double, C.c_char_p, C.c_int]),

@@ -21,9 +21,19 @@ namespace so {
 
 template <class F>
 static void parallel_for(i64 n, F f) {
-    unsigned nt = std::thread::hardware_concurrency();
-    if (nt == 0) nt = 1;
-    if (nt > 32) nt = 32;
+    // host threads of one process: all cores by default, cores / WORLD_SIZE under a multi-rank launch (one process per
+    // GPU shares the host), SO_HOST_THREADS overrides
+    static const unsigned cap = []() {
+        unsigned nt = std::thread::hardware_concurrency();
+        if (nt == 0) nt = 1;
+        if (const char *w = getenv("LOCAL_WORLD_SIZE") ? getenv("LOCAL_WORLD_SIZE") : getenv("WORLD_SIZE")) {
+            const int ws = atoi(w);
+            if (ws > 1) nt = std::max(1u, nt / (unsigned)ws);
+        }
+        if (const char *e = getenv("SO_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+        return std::min(nt, 32u);
+    }();
+    unsigned nt = cap;
     if ((i64)nt > n) nt = (unsigned)std::max<i64>(n, 1);
     if (n < 4 || nt == 1) {
         for (i64 i = 0; i < n; i++) f(i);
@@ -126,6 +136,15 @@ int so_qsort_perm(const int64_t *keys, int64_t n, int32_t *perm) {
     return SO_OK;
 }
 
+int so_qsort_prefix_device(so_ctx *c, const uint32_t *keys, int64_t n, int64_t need, uint32_t *perm) {
+    if (!c || n < 0 || need < 0 || (n > 0 && (!keys || !perm))) {
+        set_error("so_qsort_prefix_device: bad argument");
+        return SO_EINVAL;
+    }
+    SO_CUDA(cudaSetDevice(c->device));
+    return so::qsort_prefix_device(c, keys, n, need, perm);
+}
+
 int64_t so_score2bit(int64_t raw) { return so::score2bit(raw); }
 double so_bit2e(int64_t D, int64_t ql, int64_t tl, int64_t bit) { return so::bit2e(D, ql, tl, bit); }
 int so_f2s(double e, char *out, int cap) {
@@ -192,6 +211,11 @@ void so_ctx_destroy(so_ctx *c) {
     if (c->d_tung) cudaFree(c->d_tung);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &pc : c->cand_pool) pc.release();
+    for (auto &b : c->bstore) b.release();
+    for (int k = 0; k < 4; k++) {
+        if (c->h_sel[k]) cudaFreeHost(c->h_sel[k]);
+        if (c->h_sel_n[k]) cudaFreeHost(c->h_sel_n[k]);
+    }
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
     for (auto &e : c->ev_aln)
@@ -451,7 +475,13 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     i64 QB = std::max<i64>(64, std::min<i64>(512, 4096 / (i64)std::max<size_t>(1, nch)));
     if (const char *e = getenv("SO_QUERY_BLOCK")) QB = std::max<i64>(16, atoll(e));  // tuning hook
     const int kSlots = 4;
-    if (c->cand_pool.size() < (size_t)kSlots * nch) c->cand_pool.resize((size_t)kSlots * nch);
+    // at most one candidate per (query, target): fixed per-query capacity of the device lists
+    i64 capq = 0;
+    for (const auto &ix : c->chunks) capq += ix.c1 - ix.c0;
+    capq = std::max<i64>(capq, 1);
+    // keep one lane's lists within ~3 GB
+    QB = std::max<i64>(16, std::min<i64>(QB, (i64)(3000000000ll / (capq * 8))));
+    if (c->cand_pool.size() < 2) c->cand_pool.resize(2);
     {
         int rc = so::upload_search_config(c);
         if (rc != SO_OK) return rc;
@@ -481,50 +511,31 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     std::vector<QueryState> pending;
     const size_t kAlignBatch = 2048;
 
+    const i64 selcap = std::max<i64>(1, std::min<i64>(vmax, capq));
     auto order_block = [&](i64 b0, i64 b1, int slot, const std::function<void()> &release_slot) -> int {
         const i64 nq = b1 - b0;
         std::vector<QueryState> qs((size_t)nq);
-        // candidate `idx` of query k in the chunk-major concatenation (fsearch.py:3043-3049)
-        auto cand_at = [&](i64 k, uint32_t idx) -> uint64_t {
-            for (size_t ch = 0; ch < nch; ch++) {
-                const so::PackedCands &pc = c->cand_pool[(size_t)slot * nch + ch];
-                const uint64_t lo = pc.offsets[(size_t)k], hi = pc.offsets[(size_t)k + 1];
-                if (idx < hi - lo) return pc.vals[lo + idx];
-                idx -= (uint32_t)(hi - lo);
-            }
-            return 0;
-        };
-        // PASS 2 (fsearch.py:3051-3059): qsort by -score, mmiss, vmax
+        // PASS 2 head (fsearch.py:3039-3059): the merge, the quicksort by -score and the [:vmax] cut ran on the
+        // device (select.cu); h_sel holds the selected candidates of every query in sorted order
         Timer th;
+        const uint64_t *hs = c->h_sel[slot];
+        const uint32_t *hn = c->h_sel_n[slot];
         so::parallel_for(nq, [&](i64 k) {
             QueryState &s = qs[(size_t)k];
             s.qord = b0 + k;
-            i64 n = 0;
-            for (size_t ch = 0; ch < nch; ch++) n += (i64)(c->cand_pool[(size_t)slot * nch + ch].offsets[(size_t)k + 1] - c->cand_pool[(size_t)slot * nch + ch].offsets[(size_t)k]);
-            s.order.resize((size_t)n);
-            i64 w = 0;
-            for (size_t ch = 0; ch < nch; ch++) {
-                const so::PackedCands &pc = c->cand_pool[(size_t)slot * nch + ch];
-                for (uint64_t p = pc.offsets[(size_t)k]; p < pc.offsets[(size_t)k + 1]; p++, w++) {
-                    const uint32_t score = (uint32_t)((pc.vals[p] >> 20) & 0xfffffu);
-                    s.order[(size_t)w] = ((uint64_t)(0xffffffffu - score) << 32) | (uint32_t)w;
-                }
-            }
+            const i64 n = (i64)hn[k];
             s.limit = std::min<i64>(vmax, n);
-            so::qsort_prefix(s.order, s.limit);
             double mm = (double)n * max_miss + 1;
             mm = std::max(mm, 100. / mm);
             mm = std::min(std::max(mm, 10.), 120.);
             s.mmiss = mm;
             s.done = s.limit == 0;
-            // only the prefix is ever consumed: resolve it to candidates and drop the rest
             s.sel.resize((size_t)s.limit);
-            for (i64 i = 0; i < s.limit; i++) s.sel[(size_t)i] = so::unpack_cand(cand_at(k, (uint32_t)s.order[(size_t)i]));
-            std::vector<uint64_t>().swap(s.order);
+            for (i64 i = 0; i < s.limit; i++) s.sel[(size_t)i] = so::unpack_cand(hs[(size_t)k * (size_t)selcap + (size_t)i]);
         });
         wstats.ms_host += th.ms();
         c->prof.order_ms += th.ms();
-        release_slot();  // the packed candidates of this block are no longer needed
+        release_slot();  // the pinned selection of this block is no longer needed
         for (auto &q : qs) pending.push_back(std::move(q));
         return SO_OK;
     };
@@ -723,10 +734,49 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 if (worker_rc != SO_OK || abort_all) break;
                 slot_busy[slot] = true;
             }
-            // PASS 1 (fsearch.py:2990-3016): candidates of every chunk (packed, pinned, reference order)
+            // PASS 1 (fsearch.py:2990-3016): candidates of every chunk, appended on the device to the block's
+            // per-query lists in chunk order; then the device selection and the copy of the selected candidates
             Timer tc;
+            cudaStream_t st = pid ? c->stream1 : c->stream;
+            so::BlockStore &bs = c->bstore[pid];
+            const i64 nqb = b1 - b0;
+            rc = bs.prepare(c, nqb, (size_t)capq, (int)selcap, st);
             for (size_t ch = 0; ch < nch && rc == SO_OK; ch++)
-                rc = so::chunk_candidates(c, c->chunks[ch], b0, b1, c->cand_pool[(size_t)slot * nch + ch], pid);
+                rc = so::chunk_candidates(c, c->chunks[ch], b0, b1, c->cand_pool[(size_t)pid], pid, &bs, 0);
+            if (rc == SO_OK) rc = bs.select(st);
+            if (rc == SO_OK) {
+                const size_t need_sel = (size_t)nqb * (size_t)selcap;
+                if (need_sel > c->h_sel_cap[slot]) {
+                    if (c->h_sel[slot]) cudaFreeHost(c->h_sel[slot]);
+                    if (c->h_sel_n[slot]) cudaFreeHost(c->h_sel_n[slot]);
+                    c->h_sel[slot] = nullptr, c->h_sel_n[slot] = nullptr, c->h_sel_cap[slot] = 0;
+                    const size_t cap = (size_t)std::max<i64>(QB, nqb) * (size_t)selcap;
+                    if (cudaMallocHost((void **)&c->h_sel[slot], cap * 8) != cudaSuccess ||
+                        cudaMallocHost((void **)&c->h_sel_n[slot], ((size_t)std::max<i64>(QB, nqb) + 8) * 4) != cudaSuccess) {
+                        so::set_error("cudaMallocHost of the selection buffers failed");
+                        rc = SO_ENOMEM;
+                    } else
+                        c->h_sel_cap[slot] = cap;
+                }
+            }
+            if (rc == SO_OK) {
+                Timer td;
+                uint32_t flags[2] = {0, 0};
+                cudaMemcpyAsync(c->h_sel[slot], bs.sel.p, (size_t)nqb * (size_t)selcap * 8, cudaMemcpyDeviceToHost, st);
+                cudaMemcpyAsync(c->h_sel_n[slot], bs.sel_n.p, (size_t)nqb * 4, cudaMemcpyDeviceToHost, st);
+                cudaMemcpyAsync(flags, bs.count.p + nqb, 8, cudaMemcpyDeviceToHost, st);
+                cudaError_t e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) {
+                    so::set_error("CUDA error in the candidate selection: %s", cudaGetErrorString(e));
+                    rc = SO_ENODEV;
+                } else if (flags[1]) {
+                    so::set_error("device candidate selection failed (flag %u)", flags[1]);
+                    rc = SO_ELIMIT;
+                }
+                c->stats_lane[pid].d2h_bytes += (i64)nqb * selcap * 8 + nqb * 4 + 8;
+                c->stats_lane[pid].kernel_launches += 1;
+                c->d2h_ms_lane[pid] += td.ms();
+            }
             std::lock_guard<std::mutex> lk(mu);
             c->prof.cand_ms += tc.ms();
             if (rc == SO_OK)

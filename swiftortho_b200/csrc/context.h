@@ -99,6 +99,24 @@ static inline so_cand unpack_cand(uint64_t v) {
     return cd;
 }
 
+// Candidates of one query block on the device (H3, select.cu): per-query lists with a fixed capacity (one entry per
+// target at most), filled chunk by chunk in the reference's concatenation order, then sorted / cut by k_h3_select.
+struct BlockStore {
+    DBuf<uint64_t> vals;    // [nq][capq] packed candidates (target << 40 | score << 20 | diagonal + bias)
+    DBuf<uint32_t> count;   // [nq] candidates per query, [nq] work counter, [nq + 1] error flag
+    DBuf<uint64_t> keys;    // per resident CTA: (0xffffffff - score) << 32 | index
+    DBuf<uint32_t> la, lb;  // per resident CTA: stopper lists of the partition in flight
+    DBuf<uint64_t> sel;     // [nq][vmax] the first min(vmax, n) candidates in the reference's sorted order
+    DBuf<uint32_t> sel_n;   // [nq] n = len(hits)
+    i64 nq = 0;
+    size_t capq = 0;
+    int vmax = 0, grid = 0;
+    int prepare(so_ctx *c, i64 nq, size_t capq, int vmax, cudaStream_t st);
+    int append(const uint64_t *d_cv, const uint32_t *d_bounds, int n, int q0, cudaStream_t st);
+    int select(cudaStream_t st);
+    void release();
+};
+
 struct HostProfile {  // wall-clock breakdown of the host side (SO_PROFILE=1 prints it)
     double cand_ms = 0, d2h_ms = 0, order_ms = 0, rounds_ms = 0, align_ms = 0, replay_ms = 0, final_ms = 0, total_ms = 0;
 };
@@ -158,6 +176,10 @@ struct so_ctx {
     so_stats stats_aln = {};                  // written by the alignment side only; merged by merge_align_stats
     so::HostProfile prof;
     std::vector<so::PackedCands> cand_pool;   // one pinned buffer per chunk, reused across query blocks
+    so::BlockStore bstore[2];                 // per production lane
+    uint64_t *h_sel[4] = {};                  // pinned, per pipeline slot: selected candidates of a block
+    uint32_t *h_sel_n[4] = {};
+    size_t h_sel_cap[4] = {};
 };
 
 namespace so {
@@ -166,7 +188,11 @@ int upload_tables();
 int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out);
 int build_chunk_index(so_ctx *c, ChunkIndex &ix);
 void free_chunk_index(ChunkIndex &ix);
-int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out, int lane = 0);
+// candidates of queries [q_begin, q_end) against one chunk: copied to `out` (pinned host memory) or, when `bs` is
+// given, appended on the device to the block's per-query lists (query q_begin = list bs_q0)
+int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out, int lane = 0,
+                     BlockStore *bs = nullptr, int bs_q0 = 0);
+int qsort_prefix_device(so_ctx *c, const uint32_t *keys, i64 n, i64 need, uint32_t *perm_out);
 int upload_search_config(so_ctx *c);
 void merge_lane_stats(so_ctx *c);
 int ensure_pinned(so_ctx *c, size_t bytes);

@@ -1384,7 +1384,8 @@ void merge_lane_stats(so_ctx *c) {
 }
 
 // The caller uploads the search configuration (upload_search_config) once before the first call.
-int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out, int lane) {
+int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out, int lane, BlockStore *bs,
+                     int bs_q0) {
     so::DBuf<uint8_t> *scratch = lane ? c->scratch1 : c->scratch;
     cudaEvent_t *ev = lane ? c->ev1 : c->ev;
     so_stats &stats = c->stats_lane[lane];
@@ -1713,21 +1714,31 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                 if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
                 SO_CUDA(cub::DeviceRadixSort::SortPairs(scratch[SC_TMP].p, tmp, ck, cv, (int)ncand, 0, rank_bits + q_bits, st));
                 k_query_bounds<<<(nq + 1 + 127) / 128, 128, 0, st>>>(ck.Current(), (uint32_t)ncand, nq, rank_bits, d_bounds);
-                SO_CUDA(cudaEventRecord(ev[4], st));
-                Timer td;
-                if ((rc = out.reserve(base_c + (size_t)ncand)) != SO_OK) return rc;
-                SO_CUDA(cudaMemcpyAsync(out.vals + base_c, cv.Current(), (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
-                SO_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds, ((size_t)nq + 1) * 4, cudaMemcpyDeviceToHost, st));
-                SO_CUDA(cudaStreamSynchronize(st));
-                SO_CUDA(cudaGetLastError());
-                out.n = base_c + (size_t)ncand;
-                stats.kernel_launches += 1;
-                stats.lib_launches += 1;
-                stats.d2h_bytes += (i64)ncand * 8 + ((i64)nq + 1) * 4;
+                if (bs) {
+                    // H3 runs on the device: the candidates join the block's per-query lists (select.cu)
+                    if ((rc = bs->append(cv.Current(), d_bounds, nq, bs_q0 + (int)(b0 - q_begin), st)) != SO_OK) return rc;
+                    SO_CUDA(cudaEventRecord(ev[4], st));
+                    SO_CUDA(cudaEventSynchronize(ev[4]));
+                    out.n = base_c + (size_t)ncand;  // count only
+                    stats.kernel_launches += 2;
+                    stats.lib_launches += 1;
+                } else {
+                    SO_CUDA(cudaEventRecord(ev[4], st));
+                    Timer td;
+                    if ((rc = out.reserve(base_c + (size_t)ncand)) != SO_OK) return rc;
+                    SO_CUDA(cudaMemcpyAsync(out.vals + base_c, cv.Current(), (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
+                    SO_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds, ((size_t)nq + 1) * 4, cudaMemcpyDeviceToHost, st));
+                    SO_CUDA(cudaStreamSynchronize(st));
+                    SO_CUDA(cudaGetLastError());
+                    out.n = base_c + (size_t)ncand;
+                    stats.kernel_launches += 1;
+                    stats.lib_launches += 1;
+                    stats.d2h_bytes += (i64)ncand * 8 + ((i64)nq + 1) * 4;
+                    c->d2h_ms_lane[lane] += td.ms();
+                }
                 float ms = 0;
                 cudaEventElapsedTime(&ms, ev[3], ev[4]);
                 stats.ms_select += ms;
-                c->d2h_ms_lane[lane] += td.ms();
             }
             float ms = 0;
             cudaEventElapsedTime(&ms, ev[0], ev[1]);

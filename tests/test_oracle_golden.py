@@ -107,3 +107,58 @@ def test_readme_known_answer(oracle, tmp_path):
     exp = open(os.path.join(GOLDEN, 'qry450.sc'), 'rb').read().split(b'\t')
     assert exp[2:10] == [b'100.00', b'450', b'0', b'0', b'1', b'450', b'1', b'450']
     assert exp[11:14] == [b'897', b'450', b'450']
+
+
+def test_parallel_hoare_formula():
+    """The data-parallel statement of the reference's Hoare partition (lib/fsearch.py:281-297) used by the
+    device-side candidate sort (csrc/select.cu): with a_k the k-th position from the left whose key is >= pivot
+    and b_k the k-th from the right whose key is <= pivot (both on the array before the partition), the loop
+    swaps exactly (a_k, b_k) for k <= K = #{k: a_k <= b_k} and ends at j = max(b_{K+1}, a_K') with K' = K if
+    a_K < b_K else K - 1.  Checked against the sequential loop on random ranges with heavy ties."""
+    import random
+
+    def seq_partition(x, l, r):
+        pv = x[l][0]
+        i, j = l, r + 1
+        while True:
+            i += 1
+            while i <= r and x[i][0] < pv:
+                i += 1
+            j -= 1
+            while x[j][0] > pv:
+                j -= 1
+            if i > j:
+                break
+            x[i], x[j] = x[j], x[i]
+        x[l], x[j] = x[j], x[l]
+        return j
+
+    def par_partition(x, l, r):
+        pv = x[l][0]
+        A = [p for p in range(l + 1, r + 1) if x[p][0] >= pv]
+        B = [p for p in range(l, r + 1) if x[p][0] <= pv]
+        nA, nB = len(A), len(B)
+        ok = [A[k] <= B[nB - 1 - k] for k in range(min(nA, nB))]
+        K = sum(ok)
+        assert ok == [True] * K + [False] * (len(ok) - K)      # monotone
+        for k in range(K):
+            a, b = A[k], B[nB - 1 - k]
+            x[a], x[b] = x[b], x[a]
+        if K == 0:
+            j = B[nB - 1]
+        else:
+            assert K < nB                                      # position l is a j-stopper that never pairs
+            Kp = K if A[K - 1] < B[nB - K] else K - 1
+            j = max(B[nB - 1 - K], A[Kp - 1] if Kp >= 1 else -1)
+        x[l], x[j] = x[j], x[l]
+        return j
+
+    rnd = random.Random(7)
+    for _ in range(20000):
+        n = rnd.randint(2, 48)
+        kr = rnd.choice([0, 1, 2, 3, 5, 10, 100])
+        x = [(rnd.randint(0, kr), i) for i in range(n)]
+        l = rnd.randint(0, n - 2)
+        r = rnd.randint(l + 1, n - 1)
+        x1, x2 = list(x), list(x)
+        assert seq_partition(x1, l, r) == par_partition(x2, l, r) and x1 == x2
