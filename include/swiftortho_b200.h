@@ -189,6 +189,7 @@ typedef struct so_stats {
     int64_t h2d_bytes, d2h_bytes;
     double ms_ungap_kernel;  /* X-drop kernels alone (k_single_ungap + k_group_ungap), inside ms_ungap */
     int64_t multi_groups;    /* diagonal groups holding more than one seed (chained path)            */
+    int64_t redo_blocks;     /* query blocks the sync-free path handed back to the general path      */
 } so_stats;
 int so_stats_get(const so_ctx *c, so_stats *s);
 /* tuning hooks (no reference counterpart): queries per seeding sub-block (0 = adaptive), and the number

@@ -397,6 +397,41 @@ int so_candidates(so_ctx *c, int64_t chunk, int64_t q_begin, int64_t q_end, uint
     SO_CUDA(cudaSetDevice(c->device));
     so::PackedCands bc;
     int rc = so::upload_search_config(c);
+    // the sync-free cell path when the configuration allows it (the path so_search takes), else the general path
+    const so::ChunkIndex &cix = c->chunks[(size_t)chunk];
+    const i64 nqc = q_end - q_begin;
+    const size_t capc = (size_t)std::max<i64>(cix.c1 - cix.c0, 1);
+    if (rc == SO_OK && nqc > 0 && (double)nqc * (double)capc * 8. < 3e9) {
+        so::BlockStore &bs = c->bstore[0];
+        bool fast = false, redo = false;
+        rc = bs.prepare(c, nqc, capc, 1, c->stream);
+        if (rc == SO_OK) rc = so::block_candidates_fast(c, q_begin, q_end, 0, bs, fast, (int)chunk);
+        if (rc == SO_OK && fast) rc = so::finish_fast_block(c, 0, redo);
+        if (rc == SO_OK && fast && !redo) {
+            std::vector<uint32_t> cnt((size_t)nqc);
+            SO_CUDA(cudaMemcpy(cnt.data(), bs.count.p, (size_t)nqc * 4, cudaMemcpyDeviceToHost));
+            uint64_t tot = 0;
+            for (uint32_t v : cnt) tot += v;
+            *cand_offsets = (uint64_t *)malloc(((size_t)nqc + 1) * 8);
+            *cands = (so_cand *)malloc(std::max<size_t>(1, (size_t)tot) * sizeof(so_cand));
+            if (!*cand_offsets || !*cands) {
+                set_error("out of host memory");
+                return SO_ENOMEM;
+            }
+            std::vector<uint64_t> tmp;
+            uint64_t w = 0;
+            (*cand_offsets)[0] = 0;
+            for (i64 k = 0; k < nqc; k++) {
+                tmp.resize(cnt[(size_t)k]);
+                if (!tmp.empty())
+                    SO_CUDA(cudaMemcpy(tmp.data(), bs.vals.p + (size_t)k * bs.capq, tmp.size() * 8, cudaMemcpyDeviceToHost));
+                for (uint64_t v : tmp) (*cands)[w++] = so::unpack_cand(v);
+                (*cand_offsets)[k + 1] = w;
+            }
+            so::merge_lane_stats(c);
+            return SO_OK;
+        }
+    }
     if (rc == SO_OK) rc = so::chunk_candidates(c, c->chunks[(size_t)chunk], q_begin, q_end, bc);
     so::merge_lane_stats(c);
     if (rc != SO_OK) {
@@ -741,8 +776,13 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             so::BlockStore &bs = c->bstore[pid];
             const i64 nqb = b1 - b0;
             rc = bs.prepare(c, nqb, (size_t)capq, (int)selcap, st);
-            for (size_t ch = 0; ch < nch && rc == SO_OK; ch++)
-                rc = so::chunk_candidates(c, c->chunks[ch], b0, b1, c->cand_pool[(size_t)pid], pid, &bs, 0);
+            bool fast = false;
+            if (rc == SO_OK) rc = so::block_candidates_fast(c, b0, b1, pid, bs, fast);
+            auto general_path = [&]() {
+                for (size_t ch = 0; ch < nch && rc == SO_OK; ch++)
+                    rc = so::chunk_candidates(c, c->chunks[ch], b0, b1, c->cand_pool[(size_t)pid], pid, &bs, 0);
+            };
+            if (!fast) general_path();
             if (rc == SO_OK) rc = bs.select(st);
             if (rc == SO_OK) {
                 const size_t need_sel = (size_t)nqb * (size_t)selcap;
@@ -776,6 +816,31 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 c->stats_lane[pid].d2h_bytes += (i64)nqb * selcap * 8 + nqb * 4 + 8;
                 c->stats_lane[pid].kernel_launches += 1;
                 c->d2h_ms_lane[pid] += td.ms();
+                if (rc == SO_OK && fast) {
+                    bool redo = false;
+                    rc = so::finish_fast_block(c, pid, redo);
+                    if (rc == SO_OK && redo) {
+                        // a cell too large for the shared-memory sort: the whole block goes through the general path
+                        fast = false;
+                        rc = bs.prepare(c, nqb, (size_t)capq, (int)selcap, st);
+                        general_path();
+                        if (rc == SO_OK) rc = bs.select(st);
+                        if (rc == SO_OK) {
+                            cudaMemcpyAsync(c->h_sel[slot], bs.sel.p, (size_t)nqb * (size_t)selcap * 8, cudaMemcpyDeviceToHost, st);
+                            cudaMemcpyAsync(c->h_sel_n[slot], bs.sel_n.p, (size_t)nqb * 4, cudaMemcpyDeviceToHost, st);
+                            cudaMemcpyAsync(flags, bs.count.p + nqb, 8, cudaMemcpyDeviceToHost, st);
+                            e = cudaStreamSynchronize(st);
+                            if (e != cudaSuccess) {
+                                so::set_error("CUDA error in the candidate selection: %s", cudaGetErrorString(e));
+                                rc = SO_ENODEV;
+                            } else if (flags[1]) {
+                                so::set_error("device candidate selection failed (flag %u)", flags[1]);
+                                rc = SO_ELIMIT;
+                            }
+                            c->stats_lane[pid].redo_blocks += 1;
+                        }
+                    }
+                }
             }
             std::lock_guard<std::mutex> lk(mu);
             c->prof.cand_ms += tc.ms();

@@ -52,6 +52,7 @@ struct ChunkIndex {
     i64 n_used = 0;              // non-empty buckets
     i64 threshold = 0;
     uint32_t max_tlen = 0;
+    uint32_t max_bucket = 0;     // largest bucket (bounds the seed hits of a query: threshold * len + max_bucket)
     uint32_t *d_start = nullptr; // [NC + 1] start[b] = #entries with bucket < b
     uint32_t *d_locus = nullptr; // [n_seeds] reverse insertion order inside a bucket
     uint32_t *d_soas = nullptr;  // [M + 1] residue offsets inside the chunk
@@ -159,12 +160,14 @@ struct so_ctx {
     std::vector<so::ChunkIndex> chunks;
 
     // scratch (grown on demand, reused)
-    so::DBuf<uint8_t> scratch[40];
+    so::DBuf<uint8_t> scratch[64];
     // second candidate-production lane (so_search runs two producer threads on alternating query blocks so
     // that one lane's host synchronisations and D2H copies overlap the other lane's kernels)
-    so::DBuf<uint8_t> scratch1[40];
+    so::DBuf<uint8_t> scratch1[64];
     cudaStream_t stream1 = nullptr;
     cudaEvent_t ev1[8] = {};
+    std::vector<cudaEvent_t> ev_pool[2];
+    size_t ev_used[2] = {0, 0};      // per lane: stage events of the sync-free path, read at the end of a block
     so_stats stats_lane[2] = {};
     int n_lanes = 2;
     double d2h_ms_lane[2] = {0, 0};
@@ -194,6 +197,11 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                      BlockStore *bs = nullptr, int bs_q0 = 0);
 int qsort_prefix_device(so_ctx *c, const uint32_t *keys, i64 n, i64 need, uint32_t *perm_out);
 int upload_search_config(so_ctx *c);
+// sync-free candidate production of a whole query block (one pattern, one alphabet, sequences < 8192): every chunk's
+// candidates are appended to `bs` with no host synchronisation; `eligible` = false when the block needs the general
+// path (nothing was launched); finish_fast_block reads the flags / counters after the block's stream sync
+int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, bool &eligible, int only_chunk = -1);
+int finish_fast_block(so_ctx *c, int lane, bool &redo);
 void merge_lane_stats(so_ctx *c);
 int ensure_pinned(so_ctx *c, size_t bytes);
 void merge_align_stats(so_ctx *c);

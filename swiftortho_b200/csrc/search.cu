@@ -282,6 +282,7 @@ int build_chunk_index(so_ctx *c, ChunkIndex &ix) {
             uint32_t q = p + 1;
             while (q < ix.n_seeds && h_keys[q] == h_keys[p]) q++;
             counts.push_back(q - p);
+            ix.max_bucket = std::max<uint32_t>(ix.max_bucket, q - p);
             p = q;
         }
         for (uint32_t v : counts) mu += (double)v, N += 1;
@@ -426,14 +427,22 @@ __global__ void __launch_bounds__(256) k_expand(const uint32_t *__restrict__ slo
 // ---------------------------------------------------------------------------------------------
 enum { kCellSmall = 8, kCellWarp = 192, kCellMax = 16384 };
 
+// Count pass (SCATTER = false): per work item (query, target range) the per-target counters are scanned inside the
+// CTA; cell_local[query][target] receives the exclusive prefix inside the item and utot[item] its total, so no
+// device-wide scan over the cells is needed (k_unit_scan turns the <= 16 K item totals into item bases).  A cell
+// above `cell_max` hits raises flags[0] (the block is then redone through the device-wide sort).
+// Scatter pass (SCATTER = true): cursors start at ubase[item] + cell_local[..].
 template <bool SCATTER>
 __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__ slot_off, BlockGeom g,
                                                     const uint64_t *__restrict__ qoff,
                                                     const uint32_t *__restrict__ slot_st, const uint32_t *__restrict__ slot_cnt,
                                                     const uint2 *__restrict__ hdsst, uint32_t NB, uint32_t nsplit,
-                                                    uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ cell_base,
-                                                    uint32_t *__restrict__ sub, uint32_t *__restrict__ max_cell,
+                                                    uint32_t *__restrict__ cell_local, uint32_t *__restrict__ utot,
+                                                    const uint32_t *__restrict__ ubase, uint32_t *__restrict__ sub,
+                                                    uint32_t cell_max, uint32_t *__restrict__ flags,
                                                     uint32_t *__restrict__ next_query) {
+    if (SCATTER && flags[0]) return;
+    __shared__ uint32_t s_part[32];
     // a work item is (query, one of `nsplit` target ranges): with two ranges the counters of a CTA need half the
     // shared memory, two CTAs (64 warps) fit an SM and hide the latency of this loop better; every CTA walks all
     // bucket lists of its query and keeps the hits of its range (lists are in descending target order, so the
@@ -453,8 +462,11 @@ __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__
         if ((uint32_t)s_qi >= (uint32_t)g.nq * nsplit) break;
         const int qi = (int)((uint32_t)s_qi / nsplit);
         const uint32_t lo = ((uint32_t)s_qi % nsplit) * NBh, span = min(NB, lo + NBh) - lo;  // targets [lo, lo + span)
-        for (uint32_t b = threadIdx.x; b < span; b += blockDim.x)
-            s_cell[b] = SCATTER ? cell_base[(size_t)qi * NB + lo + b] : 0u;
+        {
+            const uint32_t ub = SCATTER ? ubase[s_qi] : 0u;
+            for (uint32_t b = threadIdx.x; b < span; b += blockDim.x)
+                s_cell[b] = SCATTER ? ub + cell_local[(size_t)qi * NB + lo + b] : 0u;
+        }
         __syncthreads();
         const uint32_t so0 = slot_off[qi], nsl = slot_off[qi + 1] - so0;
         const int L = (int)(qoff[g.qb0 + qi + 1] - qoff[g.qb0 + qi]);
@@ -499,14 +511,46 @@ __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__
         }
         __syncthreads();
         if (!SCATTER) {
-            uint32_t mx = 0;
-            for (uint32_t b = threadIdx.x; b < span; b += blockDim.x) {
+            // exclusive scan of the item's counters in shared memory: every thread owns `per` consecutive counters
+            // (per is odd: no bank conflicts), block scan over the per-thread sums
+            const uint32_t per = ((span + blockDim.x - 1) / blockDim.x) | 1u;
+            const uint32_t b0 = threadIdx.x * per, b1 = min(span, b0 + per);
+            uint32_t sum = 0, mx = 0;
+            for (uint32_t b = b0; b < b1; b++) {
                 const uint32_t v = s_cell[b];
-                cell_count[(size_t)qi * NB + lo + b] = v;
+                sum += v;
                 mx = max(mx, v);
             }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) s_part[threadIdx.x >> 5] = inc;
             mx = __reduce_max_sync(0xffffffffu, mx);
-            if (lane == 0 && mx > (uint32_t)kCellSmall) atomicMax(max_cell, mx);
+            if (lane == 0 && mx > cell_max) atomicExch(flags, 1u);
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                const uint32_t v = s_part[threadIdx.x];
+                uint32_t w = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                    if (lane >= o) w += u;
+                }
+                s_part[threadIdx.x] = w - v;
+                if (threadIdx.x == 31) utot[s_qi] = w;
+            }
+            __syncthreads();
+            uint32_t run = s_part[threadIdx.x >> 5] + inc - sum;
+            for (uint32_t b = b0; b < b1; b++) {
+                const uint32_t v = s_cell[b];
+                s_cell[b] = run;
+                run += v;
+            }
+            __syncthreads();
+            for (uint32_t b = threadIdx.x; b < span; b += blockDim.x) cell_local[(size_t)qi * NB + lo + b] = s_cell[b];
             __syncthreads();
         }
     }
@@ -517,20 +561,113 @@ __device__ __forceinline__ void cex(uint32_t &a, uint32_t &b) {
     a = lo, b = hi;
 }
 
-__device__ __forceinline__ uint64_t cell_upper(uint32_t c, uint32_t NB, const BlockGeom &g) {
-    const uint32_t qi = c / NB, hd1 = c - qi * NB;
-    return ((uint64_t)qi << (g.hd_bits + g.diag_bits + g.qst_bits)) | ((uint64_t)hd1 << (g.diag_bits + g.qst_bits));
+// X-drop descriptor flags (uint2.y: query residue index inside the sub-block's view in the low 24 bits)
+static const uint32_t kDescSingle = 1u << 24, kDescNoLeft = 1u << 25;
+// chained group of exactly two seeds whose qst differ by 1..32 (the usual chain: two overlapping k-mers):
+// bit 26 + (delta - 1) in bits 27..31, so k_xdrop never has to read the hits of such a group
+static const uint32_t kDescPair = 1u << 26;
+static const uint32_t kDescSkipX = 0xffffffffu;  // uint2.x of a hit that is not the head of its diagonal group
+static const uint32_t kHeadBit = 0x80000000u;    // sorted cell-local key: first hit of a (query, target, diagonal) group
+
+// item bases from the item totals (<= 16 K items): one CTA; also publishes the number of valid hits
+__global__ void __launch_bounds__(1024) k_unit_scan(const uint32_t *__restrict__ utot, uint32_t U, uint32_t *__restrict__ ubase,
+                                                    unsigned long long *__restrict__ counters, const uint32_t *__restrict__ flags) {
+    __shared__ uint32_t s_part[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (uint32_t i0 = 0; i0 < U; i0 += 1024) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint32_t v = i < U ? utot[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_part[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t t = s_part[threadIdx.x];
+            uint32_t w = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            s_part[threadIdx.x] = w - t;
+        }
+        __syncthreads();
+        const uint32_t ex = s_carry + s_part[threadIdx.x >> 5] + inc - v;
+        if (i < U) ubase[i] = ex;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = ex + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        ubase[U] = s_carry;
+        counters[0] = flags[0] ? 0ull : (unsigned long long)s_carry;  // hits to score (none when the block is to be redone)
+        counters[2] = 0ull;                                            // group pool of k_xdrop
+        counters[6] += (unsigned long long)s_carry;                    // statistic: seed hits
+        uint32_t *t = reinterpret_cast<uint32_t *>(counters + 8);      // transient: list lengths, work counters
+        t[0] = t[1] = t[2] = t[3] = 0u;
+    }
 }
 
-// one thread per cell: cells of 1..8 hits are sorted in registers on their cell-local 32 bits (diagonal | qst) and
-// written out as full 64-bit keys; larger cells are queued for k_cell_warp / k_cell_block
-__global__ void __launch_bounds__(256) k_cell_small(const uint32_t *__restrict__ cell_base, uint32_t ncells, uint32_t NB,
-                                                    BlockGeom g, const uint32_t *__restrict__ sub, uint64_t *__restrict__ keys,
-                                                    uint32_t *__restrict__ wlist, uint32_t *__restrict__ blist,
-                                                    uint32_t *__restrict__ lcount) {
+// extent of cell c = (query qi, target t) in the hit arrays
+__device__ __forceinline__ void cell_extent(uint32_t c, uint32_t NB, uint32_t NBh, uint32_t nsplit,
+                                            const uint32_t *__restrict__ cell_local, const uint32_t *__restrict__ ubase,
+                                            uint32_t &qi, uint32_t &t, uint32_t &off, uint32_t &n) {
+    qi = c / NB;
+    t = c - qi * NB;
+    const uint32_t r = t / NBh, unit = qi * nsplit + r;
+    const uint32_t ub = ubase[unit];
+    off = ub + cell_local[c];
+    const bool last = (t + 1 == NB) || ((t + 1) % NBh == 0);
+    const uint32_t end = last ? ubase[unit + 1] : ub + cell_local[c + 1];
+    n = end - off;
+}
+
+// sorted hit i of a cell: key + head bit, and the X-drop descriptor when it is the head of its diagonal group
+// (kp / k1 / k2 = previous / next / second next sorted keys; has* = they exist inside the cell)
+__device__ __forceinline__ void cell_emit(uint32_t p, uint32_t k, bool hasp, uint32_t kp, bool has1, uint32_t k1, bool has2,
+                                          uint32_t k2, uint32_t tbase, uint32_t qrel, const BlockGeom &g,
+                                          uint32_t *__restrict__ ssub, uint2 *__restrict__ desc) {
+    const uint32_t qmask = (1u << g.qst_bits) - 1u;
+    const uint32_t dg = k >> g.qst_bits;
+    const bool head = !hasp || (kp >> g.qst_bits) != dg;
+    ssub[p] = k | (head ? kHeadBit : 0u);
+    if (!head) {
+        desc[p] = make_uint2(kDescSkipX, 0u);
+        return;
+    }
+    const int qst = (int)(k & qmask);
+    const int diag = (int)dg - g.diag_bias;
+    const int sst = qst - diag;
+    const bool multi = has1 && (k1 >> g.qst_bits) == dg;
+    uint32_t flags = (multi ? 0u : kDescSingle) | ((qst == 0 || sst == 0) ? kDescNoLeft : 0u);
+    if (multi && !(has2 && (k2 >> g.qst_bits) == dg)) {
+        const uint32_t delta = (k1 & qmask) - (uint32_t)qst;
+        if (delta >= 1 && delta <= 32) flags |= kDescPair | ((delta - 1) << 27);
+    }
+    desc[p] = make_uint2(tbase + (uint32_t)sst, (qrel + (uint32_t)qst) | flags);
+}
+
+// one thread per cell: cells of 1..8 hits are sorted in registers on their cell-local bits (diagonal | qst) and
+// written out as sorted keys + descriptors; larger cells are queued for k_cell_warp / k_cell_block
+__global__ void __launch_bounds__(256) k_cell_small(const uint32_t *__restrict__ cell_local, const uint32_t *__restrict__ ubase,
+                                                    uint32_t ncells, uint32_t NB, uint32_t NBh, uint32_t nsplit, BlockGeom g,
+                                                    const uint64_t *__restrict__ qoff, const uint64_t *__restrict__ toff, uint64_t qa,
+                                                    const uint32_t *__restrict__ sub, uint32_t *__restrict__ ssub,
+                                                    uint2 *__restrict__ desc, uint32_t *__restrict__ wlist,
+                                                    uint32_t *__restrict__ blist, uint32_t *__restrict__ lcount,
+                                                    const uint32_t *__restrict__ flags) {
+    if (flags[0]) return;
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
-    const uint32_t off = cell_base[c], n = cell_base[c + 1] - off;
+    uint32_t qi, t, off, n;
+    cell_extent(c, NB, NBh, nsplit, cell_local, ubase, qi, t, off, n);
     if (n == 0) return;
     if (n > (uint32_t)kCellSmall) {
         if (n <= (uint32_t)kCellWarp)
@@ -539,7 +676,6 @@ __global__ void __launch_bounds__(256) k_cell_small(const uint32_t *__restrict__
             blist[atomicAdd(lcount + 1, 1u)] = c;
         return;
     }
-    const uint64_t upper = cell_upper(c, NB, g);
     uint32_t k[kCellSmall];
 #pragma unroll
     for (int i = 0; i < kCellSmall; i++) k[i] = (uint32_t)i < n ? sub[off + i] : 0xffffffffu;
@@ -554,73 +690,56 @@ __global__ void __launch_bounds__(256) k_cell_small(const uint32_t *__restrict__
     } else if (n > 1) {  // 5-comparator network on 4
         cex(k[0], k[1]), cex(k[2], k[3]), cex(k[0], k[2]), cex(k[1], k[3]), cex(k[1], k[2]);
     }
+    const uint32_t tbase = (uint32_t)toff[g.c0 + (int)t - 1];
+    const uint32_t qrel = (uint32_t)(qoff[g.qb0 + (int)qi] - qa);
 #pragma unroll
     for (int i = 0; i < kCellSmall; i++)
-        if ((uint32_t)i < n) keys[off + i] = upper | (uint64_t)k[i];
+        if ((uint32_t)i < n)
+            cell_emit(off + i, k[i], i > 0, i > 0 ? k[i - 1] : 0u, (uint32_t)(i + 1) < n, i + 1 < kCellSmall ? k[i + 1] : 0u,
+                      (uint32_t)(i + 2) < n, i + 2 < kCellSmall ? k[i + 2] : 0u, tbase, qrel, g, ssub, desc);
 }
 
 // one warp per queued cell (9..kCellWarp hits): rank sort out of shared memory (keys of a cell are distinct)
-__global__ void __launch_bounds__(256) k_cell_warp(const uint32_t *__restrict__ cell_base, const uint32_t *__restrict__ wlist,
-                                                   const uint32_t *__restrict__ lcount, uint32_t NB, BlockGeom g,
-                                                   const uint32_t *__restrict__ sub, uint64_t *__restrict__ keys) {
-    __shared__ uint32_t s_keys[8][kCellWarp];
+__global__ void __launch_bounds__(256) k_cell_warp(const uint32_t *__restrict__ cell_local, const uint32_t *__restrict__ ubase,
+                                                   const uint32_t *__restrict__ wlist, const uint32_t *__restrict__ lcount,
+                                                   uint32_t NB, uint32_t NBh, uint32_t nsplit, BlockGeom g,
+                                                   const uint64_t *__restrict__ qoff, const uint64_t *__restrict__ toff, uint64_t qa,
+                                                   const uint32_t *__restrict__ sub, uint32_t *__restrict__ ssub,
+                                                   uint2 *__restrict__ desc, const uint32_t *__restrict__ flags) {
+    if (flags[0]) return;
+    __shared__ uint32_t s_in[8][kCellWarp];
+    __shared__ uint32_t s_out[8][kCellWarp + 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nlist = lcount[0];
-    uint32_t *sk = s_keys[warp];
-    for (uint32_t w0 = (blockIdx.x * 8 + warp) * 32; w0 < nlist; w0 += gridDim.x * 8 * 32) {
-        // 32 queued cells per warp at a time: their list entries and bounds are fetched by the lanes in parallel
-        uint32_t my_c = 0, my_off = 0, my_n = 0;
-        if (w0 + lane < nlist) {
-            my_c = wlist[w0 + lane];
-            my_off = cell_base[my_c];
-            my_n = cell_base[my_c + 1] - my_off;
-        }
-        const int cells = (int)min(32u, nlist - w0);
-        // cells of up to 32 hits (most of them): one key per lane, ranks by shuffles, the next cell's key is in
-        // flight while the current one is ranked; larger cells go through shared memory
-        uint32_t nx = 0;
-        {
-            const uint32_t off0 = __shfl_sync(0xffffffffu, my_off, 0), n0 = __shfl_sync(0xffffffffu, my_n, 0);
-            if ((uint32_t)lane < n0 && n0 <= 32u) nx = sub[off0 + lane];
-        }
-        for (int t = 0; t < cells; t++) {
-            const uint32_t c = __shfl_sync(0xffffffffu, my_c, t), off = __shfl_sync(0xffffffffu, my_off, t);
-            const uint32_t n = __shfl_sync(0xffffffffu, my_n, t);
-            const uint64_t upper = cell_upper(c, NB, g);
-            const uint32_t x1 = nx;
-            if (t + 1 < cells) {
-                const uint32_t off1 = __shfl_sync(0xffffffffu, my_off, t + 1), n1 = __shfl_sync(0xffffffffu, my_n, t + 1);
-                if ((uint32_t)lane < n1 && n1 <= 32u) nx = sub[off1 + lane];
+    uint32_t *si = s_in[warp], *so_ = s_out[warp];
+    for (uint32_t w = blockIdx.x * 8 + warp; w < nlist; w += gridDim.x * 8) {
+        const uint32_t c = wlist[w];
+        uint32_t qi, t, off, n;
+        cell_extent(c, NB, NBh, nsplit, cell_local, ubase, qi, t, off, n);
+        for (uint32_t i = lane; i < n; i += 32) si[i] = sub[off + i];
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t x = si[i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n; j++) {
+                const uint32_t y = si[j];
+                rank += (y < x || (y == x && j < i)) ? 1u : 0u;
             }
-            if (n <= 32u) {
-                uint32_t rank = 0;
-                for (uint32_t j = 0; j < n; j++) {
-                    const uint32_t y = __shfl_sync(0xffffffffu, x1, (int)j);
-                    rank += (y < x1 || (y == x1 && j < (uint32_t)lane)) ? 1u : 0u;
-                }
-                if ((uint32_t)lane < n) keys[off + rank] = upper | (uint64_t)x1;
-                continue;
-            }
-            for (uint32_t i = lane; i < n; i += 32) sk[i] = sub[off + i];
-            __syncwarp();
-            for (uint32_t i = lane; i < n; i += 32) {
-                const uint32_t x = sk[i];
-                uint32_t rank = 0;
-                for (uint32_t j = 0; j < n; j++) {
-                    const uint32_t y = sk[j];
-                    rank += (y < x || (y == x && j < i)) ? 1u : 0u;
-                }
-                keys[off + rank] = upper | (uint64_t)x;
-            }
-            __syncwarp();
+            so_[rank] = x;
         }
+        __syncwarp();
+        const uint32_t tbase = (uint32_t)toff[g.c0 + (int)t - 1];
+        const uint32_t qrel = (uint32_t)(qoff[g.qb0 + (int)qi] - qa);
+        for (uint32_t i = lane; i < n; i += 32)
+            cell_emit(off + i, so_[i], i > 0, i > 0 ? so_[i - 1] : 0u, i + 1 < n, i + 1 < n ? so_[i + 1] : 0u, i + 2 < n,
+                      i + 2 < n ? so_[i + 2] : 0u, tbase, qrel, g, ssub, desc);
+        __syncwarp();
     }
 }
 
 // one CTA per queued cell (kCellWarp < hits <= kCellMax): shared-memory radix sort of the cell-local bits
 template <int THREADS, int ITEMS>
-__device__ __forceinline__ void cell_sort_tile(const uint32_t *__restrict__ sub, uint64_t *__restrict__ keys, uint64_t upper,
-                                               uint32_t off, uint32_t n, int Lb, void *smem) {
+__device__ __forceinline__ void cell_sort_tile(const uint32_t *__restrict__ sub, uint32_t off, uint32_t n, int Lb, void *smem) {
     typedef cub::BlockRadixSort<uint32_t, THREADS, ITEMS> Sort;
     typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem);
     uint32_t k[ITEMS];
@@ -630,36 +749,54 @@ __device__ __forceinline__ void cell_sort_tile(const uint32_t *__restrict__ sub,
         k[i] = idx < n ? sub[off + idx] : 0xffffffffu;
     }
     Sort(tmp).SortBlockedToStriped(k, 0, Lb);
+    __syncthreads();
+    uint32_t *sorted = reinterpret_cast<uint32_t *>(smem);  // the sort's scratch becomes the sorted cell
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const uint32_t idx = (uint32_t)i * THREADS + threadIdx.x;
-        if (idx < n) keys[off + idx] = upper | (uint64_t)k[i];
+        if (idx < n) sorted[idx] = k[i];
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(512) k_cell_block(const uint32_t *__restrict__ cell_base, const uint32_t *__restrict__ blist,
-                                                    const uint32_t *__restrict__ lcount, uint32_t NB, BlockGeom g,
-                                                    const uint32_t *__restrict__ sub, uint64_t *__restrict__ keys) {
-    extern __shared__ __align__(16) unsigned char smem[];  // sizeof(BlockRadixSort<uint32_t, 512, 32>::TempStorage)
+union CellBlockSmem {
+    cub::BlockRadixSort<uint32_t, 512, 32>::TempStorage sort;
+    uint32_t sorted[kCellMax + 8];
+};
+
+__global__ void __launch_bounds__(512) k_cell_block(const uint32_t *__restrict__ cell_local, const uint32_t *__restrict__ ubase,
+                                                    const uint32_t *__restrict__ blist, const uint32_t *__restrict__ lcount,
+                                                    uint32_t NB, uint32_t NBh, uint32_t nsplit, BlockGeom g,
+                                                    const uint64_t *__restrict__ qoff, const uint64_t *__restrict__ toff, uint64_t qa,
+                                                    const uint32_t *__restrict__ sub, uint32_t *__restrict__ ssub,
+                                                    uint2 *__restrict__ desc, const uint32_t *__restrict__ flags) {
+    if (flags[0]) return;
+    extern __shared__ __align__(16) unsigned char smem[];  // CellBlockSmem
     const uint32_t nlist = lcount[1];
     const int Lb = g.qst_bits + g.diag_bits;
+    const uint32_t *sorted = reinterpret_cast<const uint32_t *>(smem);
     for (uint32_t w = blockIdx.x; w < nlist; w += gridDim.x) {
         const uint32_t c = blist[w];
-        const uint32_t off = cell_base[c], n = cell_base[c + 1] - off;
-        const uint64_t upper = cell_upper(c, NB, g);
+        uint32_t qi, t, off, n;
+        cell_extent(c, NB, NBh, nsplit, cell_local, ubase, qi, t, off, n);
         if (n <= 512u * 1)
-            cell_sort_tile<512, 1>(sub, keys, upper, off, n, Lb, smem);
+            cell_sort_tile<512, 1>(sub, off, n, Lb, smem);
         else if (n <= 512u * 2)
-            cell_sort_tile<512, 2>(sub, keys, upper, off, n, Lb, smem);
+            cell_sort_tile<512, 2>(sub, off, n, Lb, smem);
         else if (n <= 512u * 4)
-            cell_sort_tile<512, 4>(sub, keys, upper, off, n, Lb, smem);
+            cell_sort_tile<512, 4>(sub, off, n, Lb, smem);
         else if (n <= 512u * 8)
-            cell_sort_tile<512, 8>(sub, keys, upper, off, n, Lb, smem);
+            cell_sort_tile<512, 8>(sub, off, n, Lb, smem);
         else if (n <= 512u * 16)
-            cell_sort_tile<512, 16>(sub, keys, upper, off, n, Lb, smem);
+            cell_sort_tile<512, 16>(sub, off, n, Lb, smem);
         else
-            cell_sort_tile<512, 32>(sub, keys, upper, off, n, Lb, smem);
+            cell_sort_tile<512, 32>(sub, off, n, Lb, smem);
+        const uint32_t tbase = (uint32_t)toff[g.c0 + (int)t - 1];
+        const uint32_t qrel = (uint32_t)(qoff[g.qb0 + (int)qi] - qa);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            cell_emit(off + i, sorted[i], i > 0, i > 0 ? sorted[i - 1] : 0u, i + 1 < n, i + 1 < n ? sorted[i + 1] : 0u, i + 2 < n,
+                      i + 2 < n ? sorted[i + 2] : 0u, tbase, qrel, g, ssub, desc);
+        __syncthreads();
     }
 }
 
@@ -858,11 +995,6 @@ __global__ void __launch_bounds__(256) k_group_ungap_generic(const uint64_t *__r
 // loads) runs only when kRefill or more lanes are idle.  Requires sequences < 8192 residues.
 // ---------------------------------------------------------------------------------------------
 enum { kUngPad = 64, kUngStop = 24, kUngSkip = 25, kUngRows = 26, kUngTabBytes = kUngRows * 32 * 32 * 4 };
-static const uint32_t kDescSingle = 1u << 24, kDescNoLeft = 1u << 25;
-// chained group of exactly two seeds whose qst differ by 1..32 (the usual chain: two overlapping k-mers):
-// bit 26 + (delta - 1) in bits 27..31, so k_xdrop never has to read the hits of such a group
-static const uint32_t kDescPair = 1u << 26;
-
 __global__ void __launch_bounds__(256) k_ung_fill(const uint8_t *__restrict__ cls, uint32_t n, uint8_t *__restrict__ dst,
                                                   uint32_t offF, uint32_t offR, uint32_t total, int shift) {
     const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1025,8 +1157,12 @@ __device__ __forceinline__ void ung_steps16(int &v, int &d, int &alive, int one,
 }
 #undef SO_XS
 
-template <int kRefill>
-__global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc, uint32_t G,
+// FAST = the sync-free cell path: descriptors are indexed by HIT position (one per sorted hit; hits that are not the
+// head of their diagonal group carry kDescSkipX and are skipped), the number of hits comes from device memory
+// (counters[0], written by k_unit_scan) and chains walk the sorted cell-local keys `ssub` up to the next head bit.
+template <int kRefill, bool FAST>
+__global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc, uint32_t G_,
+                                                  const uint32_t *__restrict__ ssub,
                                                   const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                   uint32_t nhits, const uint32_t *__restrict__ gheads, int qst_bits,
                                                   const uint4 *__restrict__ T4, uint32_t toffF, uint32_t toffR, uint32_t R,
@@ -1034,6 +1170,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                                                   uint32_t *__restrict__ gscore, uint32_t *__restrict__ grank,
                                                   unsigned long long *__restrict__ counters, int one) {
     extern __shared__ int s_tab[];  // [(ct << 5 | cq)][lane]
+    const uint32_t G = FAST ? (uint32_t)counters[0] : G_;
     for (int k = threadIdx.x; k < kUngRows * 32 * 32; k += blockDim.x) {
         const int e = k >> 5, ct = e >> 5, cq = e & 31;
         int val = 1 << 29;
@@ -1057,9 +1194,10 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
     uint32_t gi = 0, xt = 0, uq = 0, tci = 0, qci = 0, bs8 = 0, e = 0;
     uint4 tc = make_uint4(0, 0, 0, 0), carry = make_uint4(0, 0, 0, 0);
     uint32_t W[4] = {0, 0, 0, 0};
-    unsigned int steps = 0, nmulti = 0;
+    unsigned int steps = 0, nmulti = 0, ngroups = 0;
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform
     bool exhausted = false;                // warp-uniform
+    if (FAST && G == 0) return;
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !alive);
         if (__popc(idle) >= kRefill) {
@@ -1094,11 +1232,18 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                         // next seed of the chain: seeds at or below max_qed extend nothing and leave it unchanged
                         for (;;) {
                             e++;
-                            if (e >= nhits) break;
-                            const uint64_t k2 = keys[e];
-                            if (((k2 ^ keys[e - 1]) >> qst_bits) != 0) break;
-                            if (vals) grank[gi] = min(grank[gi], vals[e]);
-                            const int qst = (int)((uint32_t)k2 & qmask);
+                            if (e >= (FAST ? G : nhits)) break;
+                            uint32_t k2lo;
+                            if (FAST) {
+                                k2lo = ssub[e];
+                                if (k2lo & kHeadBit) break;
+                            } else {
+                                const uint64_t k2 = keys[e];
+                                if (((k2 ^ keys[e - 1]) >> qst_bits) != 0) break;
+                                if (vals) grank[gi] = min(grank[gi], vals[e]);
+                                k2lo = (uint32_t)k2;
+                            }
+                            const int qst = (int)(k2lo & qmask);
                             if (qst <= lo) continue;
                             const uint32_t delta = (uint32_t)(qst - qcur);
                             xt += delta, uq += delta;
@@ -1116,8 +1261,8 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                     }
                 }
             }
-            const unsigned need = __ballot_sync(0xffffffffu, !has && !fin);
-            if (need) {
+            unsigned need = __ballot_sync(0xffffffffu, !has && !fin);
+            for (int tries = 0; need != 0u && tries < (FAST ? 3 : 1); tries++, need = __ballot_sync(0xffffffffu, !has && !fin)) {
                 if (pool_next == pool_end && !exhausted) {
                     unsigned long long base = 0;
                     if (lane == 0) base = atomicAdd(counters + 2, kBatch);
@@ -1136,23 +1281,26 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                     const uint32_t mine = pool_next + __popc(need & ((1u << lane) - 1));
                     if (mine < pool_end) {
                         const uint2 ds = desc[mine];
-                        gi = mine;
-                        xt = ds.x;
-                        uq = ds.y & 0xffffffu;
-                        noleft = (ds.y & kDescNoLeft) != 0;
-                        multi = (ds.y & kDescSingle) == 0;
-                        qcur = 0;  // chains only use qst differences: the first seed of a described pair counts from 0
-                        pairm = multi && (ds.y & kDescPair) != 0 && vals == nullptr;
-                        if (multi) nmulti++;
-                        if (pairm)
-                            e = (ds.y >> 27) + 1u;
-                        else if (multi) {
-                            e = gheads[mine];
-                            qcur = (int)((uint32_t)keys[e] & qmask);
+                        if (!FAST || ds.x != kDescSkipX) {
+                            gi = mine;
+                            xt = ds.x;
+                            uq = ds.y & 0xffffffu;
+                            noleft = (ds.y & kDescNoLeft) != 0;
+                            multi = (ds.y & kDescSingle) == 0;
+                            qcur = 0;  // chains only use qst differences: the first seed of a described pair counts from 0
+                            pairm = multi && (ds.y & kDescPair) != 0 && vals == nullptr;
+                            if (multi) nmulti++;
+                            if (pairm)
+                                e = (ds.y >> 27) + 1u;
+                            else if (multi) {
+                                e = FAST ? mine : gheads[mine];
+                                qcur = FAST ? (int)(ssub[e] & qmask) : (int)((uint32_t)keys[e] & qmask);
+                            }
+                            phase = 0, acc = 0, chained = false, lim = kNoLimit;
+                            has = true;
+                            setup = true;
+                            if (FAST) ngroups++;
                         }
-                        phase = 0, acc = 0, chained = false, lim = kNoLimit;
-                        has = true;
-                        setup = true;
                     } else if (exhausted)
                         fin = true;  // otherwise the pool is refilled at the next service
                 }
@@ -1209,6 +1357,10 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
     if (lane == 0 && st64) atomicAdd(counters + 1, st64);
     nmulti = __reduce_add_sync(0xffffffffu, nmulti);
     if (lane == 0 && nmulti) atomicAdd(counters + 3, (unsigned long long)nmulti);  // statistic
+    if (FAST) {
+        ngroups = __reduce_add_sync(0xffffffffu, ngroups);
+        if (lane == 0 && ngroups) atomicAdd(counters + 4, (unsigned long long)ngroups);  // statistic: diagonal groups
+    }
 }
 
 // Pair selection over the PASSING groups only (score >= 25, self.min: fsearch.py:2224, 2707): `plist` holds
@@ -1297,6 +1449,218 @@ __global__ void __launch_bounds__(256) k_pair_select(const uint32_t *__restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pair fold of the cell path (fsearch.py:2696-2719): the passing diagonals (score >= 25, self.min) of one
+// (query, target) cell give one candidate: the best diagonal (the first one in the reference's dict order wins
+// ties) and, as the candidate's place in the reference's list, the rank of the FIRST passing diagonal.  With one
+// pattern and one alphabet the dict order of the groups of a query is (qst of the group's first seed ascending,
+// then target descending, then sst descending = diagonal ascending), so inside a cell it is (qst, diagonal).
+// A candidate is ONE 64-bit word, rank on top:
+//   [ qst of the first passing group | hdmask - (target + 1) | score (20 bits) | best diagonal + bias ]
+// so ordering the words of a query orders its candidates like the reference.  Candidates are appended to a
+// fixed-capacity region per query (at most one per target) through a warp-aggregated atomic.
+// ---------------------------------------------------------------------------------------------
+struct FoldAcc {
+    uint32_t first;  // smallest (qst << diag_bits | diagonal) among the passing groups
+    uint32_t best;   // score of the best
+    uint32_t brk;    // its (qst << diag_bits | diagonal)
+};
+__device__ __forceinline__ void fold_add(FoldAcc &a, uint32_t key, uint32_t score, const BlockGeom &g) {
+    const uint32_t qmask = (1u << g.qst_bits) - 1u;
+    const uint32_t rk = ((key & qmask) << g.diag_bits) | ((key & ~kHeadBit) >> g.qst_bits);
+    a.first = min(a.first, rk);
+    if (score > a.best || (score == a.best && rk < a.brk)) a.best = score, a.brk = rk;
+}
+__device__ __forceinline__ uint64_t fold_word(const FoldAcc &a, uint32_t t, const BlockGeom &g) {
+    const uint32_t dmask = (1u << g.diag_bits) - 1u, hdmask = (1u << g.hd_bits) - 1u;
+    const uint64_t rank = ((uint64_t)(a.first >> g.diag_bits) << g.hd_bits) | (uint64_t)(hdmask - t);
+    return (rank << (20 + g.diag_bits)) | ((uint64_t)a.best << g.diag_bits) | (uint64_t)(a.brk & dmask);
+}
+// lanes with a candidate append it to their query's region
+__device__ __forceinline__ void fold_append(bool has, uint32_t qi, uint64_t word, uint64_t *__restrict__ creg, size_t ccap,
+                                            uint32_t *__restrict__ qcount) {
+    const unsigned act = __ballot_sync(0xffffffffu, has);
+    if (!has) return;
+    const unsigned peers = __match_any_sync(act, qi);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&qcount[qi], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    if (pos < ccap) creg[(size_t)qi * ccap + pos] = word;
+}
+
+// one thread per cell of at most kCellSmall hits
+__global__ void __launch_bounds__(256) k_cell_fold(const uint32_t *__restrict__ cell_local, const uint32_t *__restrict__ ubase,
+                                                   uint32_t ncells, uint32_t NB, uint32_t NBh, uint32_t nsplit, BlockGeom g,
+                                                   const uint32_t *__restrict__ ssub, const uint32_t *__restrict__ gscore,
+                                                   uint64_t *__restrict__ creg, size_t ccap, uint32_t *__restrict__ qcount,
+                                                   const uint32_t *__restrict__ flags) {
+    if (flags[0]) return;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    bool has = false;
+    uint32_t qi = 0, t = 0;
+    FoldAcc a = {0xffffffffu, 0u, 0xffffffffu};
+    if (c < ncells) {
+        uint32_t off, n;
+        cell_extent(c, NB, NBh, nsplit, cell_local, ubase, qi, t, off, n);
+        if (n <= (uint32_t)kCellSmall)
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t k = ssub[off + i];
+                if (!(k & kHeadBit)) continue;
+                const uint32_t sc = gscore[off + i];
+                if (sc >= 25u) fold_add(a, k, sc, g), has = true;
+            }
+    }
+    fold_append(has, qi, has ? fold_word(a, t, g) : 0ull, creg, ccap, qcount);
+}
+
+// one warp per queued cell (more than kCellSmall hits): both lists
+__global__ void __launch_bounds__(256) k_cell_fold_list(const uint32_t *__restrict__ cell_local, const uint32_t *__restrict__ ubase,
+                                                        const uint32_t *__restrict__ wlist, const uint32_t *__restrict__ blist,
+                                                        const uint32_t *__restrict__ lcount, uint32_t NB, uint32_t NBh,
+                                                        uint32_t nsplit, BlockGeom g, const uint32_t *__restrict__ ssub,
+                                                        const uint32_t *__restrict__ gscore, uint64_t *__restrict__ creg,
+                                                        size_t ccap, uint32_t *__restrict__ qcount,
+                                                        const uint32_t *__restrict__ flags) {
+    if (flags[0]) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nw = lcount[0], ntot = nw + lcount[1];
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < ntot; w += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t c = w < nw ? wlist[w] : blist[w - nw];
+        uint32_t qi, t, off, n;
+        cell_extent(c, NB, NBh, nsplit, cell_local, ubase, qi, t, off, n);
+        FoldAcc a = {0xffffffffu, 0u, 0xffffffffu};
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t k = ssub[off + i];
+            if (!(k & kHeadBit)) continue;
+            const uint32_t sc = gscore[off + i];
+            if (sc >= 25u) fold_add(a, k, sc, g);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            FoldAcc b;
+            b.first = __shfl_xor_sync(0xffffffffu, a.first, o);
+            b.best = __shfl_xor_sync(0xffffffffu, a.best, o);
+            b.brk = __shfl_xor_sync(0xffffffffu, a.brk, o);
+            a.first = min(a.first, b.first);
+            if (b.best > a.best || (b.best == a.best && b.brk < a.brk)) a.best = b.best, a.brk = b.brk;
+        }
+        if (lane == 0 && a.best >= 25u) {
+            const uint32_t pos = atomicAdd(&qcount[qi], 1u);
+            if (pos < ccap) creg[(size_t)qi * ccap + pos] = fold_word(a, t, g);
+        }
+    }
+}
+
+// Candidate order of one (query, chunk): the words of the query's region are sorted ascending (= the reference's
+// candidate list order, fsearch.py:2715-2719) and appended, converted to the block format
+// (target << 40 | score << 20 | diagonal + kCandDiagBias), to the query's list of the block (select.cu).
+// Counting sort on the top bits of the rank into kCandBins bins (shared-memory histogram, scan, scatter), then every
+// bin (about one candidate on average) is put in order by one thread.  The scattered words live in shared memory
+// when the query has at most kCandSmem candidates, else in a per-CTA global buffer (same code, generic pointer).
+enum { kCandBins = 8192, kCandSmem = 9216, kCandThreads = 512 };
+__global__ void __launch_bounds__(kCandThreads) k_cand_sort(const uint64_t *__restrict__ creg, size_t ccap,
+                                                           const uint32_t *__restrict__ qcount, int nq, BlockGeom g,
+                                                           uint64_t *__restrict__ gbuf, uint64_t *__restrict__ bvals,
+                                                           size_t bcap, uint32_t *__restrict__ bcount, int bq0,
+                                                           uint32_t *__restrict__ next, uint32_t *__restrict__ flags,
+                                                           unsigned long long *__restrict__ counters) {
+    if (flags[0]) return;
+    extern __shared__ __align__(16) unsigned char cs_raw[];
+    uint64_t *s_f = reinterpret_cast<uint64_t *>(cs_raw);                       // [kCandSmem]
+    uint32_t *s_bin = reinterpret_cast<uint32_t *>(cs_raw + (size_t)kCandSmem * 8);  // [kCandBins]
+    __shared__ uint32_t s_part[kCandThreads / 32];
+    __shared__ int s_q;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int esh = 20 + g.diag_bits, rank_bits = g.qst_bits + g.hd_bits;
+    const int bsh = esh + max(0, rank_bits - 13);
+    const uint32_t dmask = (1u << g.diag_bits) - 1u, hdmask = (1u << g.hd_bits) - 1u;
+    for (;;) {
+        if (tid == 0) s_q = (int)atomicAdd(next, 1u);
+        __syncthreads();
+        const int q = s_q;
+        __syncthreads();
+        if (q >= nq) break;
+        uint32_t n = qcount[q];
+        if (n == 0) continue;
+        if ((size_t)n > ccap) {  // cannot happen (one candidate per target at most): refuse rather than overrun
+            if (tid == 0) atomicExch(flags + 1, 3u);
+            continue;
+        }
+        const uint64_t *src = creg + (size_t)q * ccap;
+        uint64_t *F = n <= (uint32_t)kCandSmem ? s_f : gbuf + (size_t)blockIdx.x * ccap;
+        for (int b = tid; b < kCandBins; b += kCandThreads) s_bin[b] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += kCandThreads) atomicAdd(&s_bin[(uint32_t)(src[i] >> bsh)], 1u);
+        __syncthreads();
+        {  // exclusive scan over the bins: kCandBins / kCandThreads consecutive bins per thread
+            constexpr int per = kCandBins / kCandThreads;
+            uint32_t v[per], sum = 0;
+#pragma unroll
+            for (int k = 0; k < per; k++) v[k] = s_bin[tid * per + k], sum += v[k];
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            if (lane == 31) s_part[warp] = inc;
+            __syncthreads();
+            if (tid < 32) {
+                const uint32_t t0 = tid < kCandThreads / 32 ? s_part[tid] : 0u;
+                uint32_t w = t0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                    if (lane >= o) w += u;
+                }
+                if (tid < kCandThreads / 32) s_part[tid] = w - t0;
+            }
+            __syncthreads();
+            uint32_t run = s_part[warp] + inc - sum;
+#pragma unroll
+            for (int k = 0; k < per; k++) s_bin[tid * per + k] = run, run += v[k];
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += kCandThreads) {
+            const uint64_t e = src[i];
+            F[atomicAdd(&s_bin[(uint32_t)(e >> bsh)], 1u)] = e;
+        }
+        __syncthreads();
+        // s_bin[b] is now the END of bin b: insertion sort inside every bin
+        for (int b = tid; b < kCandBins; b += kCandThreads) {
+            const uint32_t lo = b ? s_bin[b - 1] : 0u, hi = s_bin[b];
+            for (uint32_t i = lo + 1; i < hi; i++) {
+                const uint64_t x = F[i];
+                uint32_t j = i;
+                while (j > lo && F[j - 1] > x) F[j] = F[j - 1], j--;
+                F[j] = x;
+            }
+        }
+        __syncthreads();
+        const uint32_t base = bcount[bq0 + q];
+        if ((size_t)base + n > bcap) {
+            if (tid == 0) atomicExch(flags + 1, 2u);
+            continue;
+        }
+        uint64_t *dst = bvals + (size_t)(bq0 + q) * bcap + base;
+        for (uint32_t i = tid; i < n; i += kCandThreads) {
+            const uint64_t e = F[i];
+            const uint32_t t = hdmask - (uint32_t)((e >> esh) & hdmask);      // target + 1 inside the chunk
+            const uint32_t score = (uint32_t)((e >> g.diag_bits) & 0xfffffu);
+            const int diag = (int)((uint32_t)e & dmask) - g.diag_bias;
+            dst[i] = ((uint64_t)(uint32_t)(g.c0 + (int)t - 1) << 40) | ((uint64_t)score << 20) | (uint64_t)(uint32_t)(diag + kCandDiagBias);
+        }
+        if (tid == 0) {
+            bcount[bq0 + q] = base + n;
+            atomicAdd(counters + 5, (unsigned long long)n);  // statistic: candidates
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) k_classify(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = c_code2[in[i]];
@@ -1345,11 +1709,14 @@ static int bits_for(uint64_t maxval) {  // bits needed to hold values 0..maxval
 }
 
 enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TMP, SC_CKA, SC_CKB, SC_CVA, SC_CVB, SC_MISC,
-       SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK, SC_QUNG, SC_DESC, SC_MLIST, SC_GKEY, SC_PLIST, SC_CELLCNT, SC_CELLBASE };
+       SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK, SC_QUNG, SC_DESC, SC_MLIST, SC_GKEY, SC_PLIST, SC_CELLLOC, SC_UNIT, SC_SUB, SC_SSUB,
+       SC_WLIST, SC_CREG, SC_QCOUNT, SC_GBUF, SC_CTL, SC_COUNT_ };
+static_assert(SC_COUNT_ <= 64, "scratch slots");
 
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
 
 static int g_xdrop_refill = 24;
+static uint32_t g_cell_max = kCellMax;  // cells above this many hits send the block to the general path (SO_CELL_MAX: test hook)
 static uint32_t g_cell_split = 0;  // target ranges per query in the cell passes; 0 = as few as fit shared memory (SO_CELL_SPLIT)  // idle lanes that trigger a refill in k_xdrop (SO_XDROP_REFILL: tuning hook)
 
 int upload_search_config(so_ctx *c) {
@@ -1357,15 +1724,22 @@ int upload_search_config(so_ctx *c) {
     g_xdrop_refill = e ? atoi(e) : 24;
     g_cell_split = 0;
     if (const char *cs = getenv("SO_CELL_SPLIT")) g_cell_split = (uint32_t)std::max(0, std::min(8, atoi(cs)));
-    SO_CUDA(cudaFuncSetAttribute(k_xdrop<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-    SO_CUDA(cudaFuncSetAttribute(k_xdrop<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-    SO_CUDA(cudaFuncSetAttribute(k_xdrop<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-    SO_CUDA(cudaFuncSetAttribute(k_xdrop<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-    SO_CUDA(cudaFuncSetAttribute(k_xdrop<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-    SO_CUDA(cudaFuncSetAttribute(k_cell_block, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(cub::BlockRadixSort<uint32_t, 512, 32>::TempStorage)));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_cell_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CellBlockSmem)));
     SO_CUDA(cudaFuncSetAttribute(k_cell_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     SO_CUDA(cudaFuncSetAttribute(k_cell_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SO_CUDA(cudaFuncSetAttribute(k_cand_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, kCandSmem * 8 + kCandBins * 4));
+    g_cell_max = kCellMax;
+    if (const char *cm = getenv("SO_CELL_MAX")) g_cell_max = (uint32_t)std::max(1, std::min((int)kCellMax, atoi(cm)));  // test hook
     return upload_cfg(c->P);
 }
 
@@ -1375,7 +1749,7 @@ void merge_lane_stats(so_ctx *c) {
         d.seed_hits += a.seed_hits, d.groups += a.groups, d.candidates += a.candidates, d.ungap_steps += a.ungap_steps;
         d.kernel_launches += a.kernel_launches, d.lib_launches += a.lib_launches;
         d.ms_seed += a.ms_seed, d.ms_sort += a.ms_sort, d.ms_ungap += a.ms_ungap, d.ms_select += a.ms_select;
-        d.ms_ungap_kernel += a.ms_ungap_kernel, d.multi_groups += a.multi_groups;
+        d.ms_ungap_kernel += a.ms_ungap_kernel, d.multi_groups += a.multi_groups, d.redo_blocks += a.redo_blocks;
         d.h2d_bytes += a.h2d_bytes, d.d2h_bytes += a.d2h_bytes;
         c->prof.d2h_ms += c->d2h_ms_lane[l];
         memset(&a, 0, sizeof a);
@@ -1506,64 +1880,8 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             cub::DoubleBuffer<uint32_t> dv(va, vb);
             unsigned long long *d_counter = (unsigned long long *)(scratch[SC_MISC].p);
             SO_CUDA(cudaMemsetAsync(d_counter, 0, 128, st));
-            // ---- grouping: (query, target) cell partition + in-cell sort (keys-only), else the device-wide radix sort
-            // (SO_CUB_SORT=1 forces the device-wide sort)
-            const uint32_t NB = (uint32_t)(M + 2);
-            const int Lb = g.qst_bits + g.diag_bits;
-            // target ranges per query: as few as keep the per-CTA counters within shared memory (1 for -c 50000)
-            const uint32_t nsplit = g_cell_split ? g_cell_split : (uint32_t)(((size_t)NB * 4 + 220 * 1024 - 1) / (220 * 1024));
-            bool cell_path = keys_only && !getenv("SO_CUB_SORT") && nsplit <= 8 &&
-                             (size_t)((NB + nsplit - 1) / nsplit) * 4 <= 220 * 1024 && Lb <= 32 &&
-                             (uint64_t)nq * NB < 0x7fffff00ull;
-            if (cell_path) {
-                const uint32_t ncells = (uint32_t)nq * NB;
-                if ((rc = scratch[SC_CELLCNT].reserve(((size_t)ncells + 1) * 4)) != SO_OK) return rc;
-                if ((rc = scratch[SC_CELLBASE].reserve(((size_t)ncells + 1) * 4)) != SO_OK) return rc;
-                uint32_t *d_ccnt = (uint32_t *)scratch[SC_CELLCNT].p, *d_cbase = (uint32_t *)scratch[SC_CELLBASE].p;
-                uint32_t *d_maxcell = (uint32_t *)(d_counter + 6);
-                uint32_t *d_lcount = (uint32_t *)(d_counter + 7);  // two u32: warp-list / block-list lengths
-                uint32_t *d_nextq = (uint32_t *)(d_counter + 8);   // two u32: query counters of the two passes
-                SO_CUDA(cudaMemsetAsync(d_ccnt + ncells, 0, 4, st));
-                const uint32_t NBh = (NB + nsplit - 1) / nsplit;
-                const int pblocks = std::min<int>(nq * (int)nsplit, 148 * (int)nsplit);
-                k_cell_pass<false><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit,
-                                                                 d_ccnt, nullptr, nullptr, d_maxcell, d_nextq);
-                tmp = 0;
-                cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_ccnt, d_cbase, (int)ncells + 1, st);
-                if ((rc = scratch[SC_TMP].reserve(tmp)) != SO_OK) return rc;
-                SO_CUDA(cub::DeviceScan::ExclusiveSum(scratch[SC_TMP].p, tmp, d_ccnt, d_cbase, (int)ncells + 1, st));
-                uint32_t h_cell[2] = {0, 0};  // valid hits, largest cell (0 when none exceeds kCellSmall)
-                SO_CUDA(cudaMemcpyAsync(&h_cell[0], d_cbase + ncells, 4, cudaMemcpyDeviceToHost, st));
-                SO_CUDA(cudaMemcpyAsync(&h_cell[1], d_maxcell, 4, cudaMemcpyDeviceToHost, st));
-                SO_CUDA(cudaStreamSynchronize(st));
-                SO_CUDA(cudaGetLastError());
-                stats.kernel_launches += 1;
-                stats.lib_launches += 1;
-                if (h_cell[0] == 0 || h_cell[1] > (uint32_t)kCellMax)
-                    cell_path = false;  // nothing valid / a cell too large for shared memory: device-wide sort
-                else {
-                    SO_CUDA(cudaEventRecord(ev[1], st));
-                    k_cell_pass<true><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit,
-                                                                    nullptr, d_cbase, (uint32_t *)kb, nullptr, d_nextq + 1);
-                    // queue of the warp-sorted cells = the (now free) count array; CTA-sorted cells: own small buffer
-                    if ((rc = scratch[SC_MLIST].reserve(((size_t)h_cell[0] / kCellWarp + 2) * 4)) != SO_OK) return rc;
-                    uint32_t *d_wlist = d_ccnt, *d_blist = (uint32_t *)scratch[SC_MLIST].p;
-                    k_cell_small<<<(ncells + 255) / 256, 256, 0, st>>>(d_cbase, ncells, NB, g, (const uint32_t *)kb, ka, d_wlist,
-                                                                      d_blist, d_lcount);
-                    stats.kernel_launches += 2;
-                    if (h_cell[1] > (uint32_t)kCellSmall) {
-                        k_cell_warp<<<148 * 4, 256, 0, st>>>(d_cbase, d_wlist, d_lcount, NB, g, (const uint32_t *)kb, ka);
-                        stats.kernel_launches += 1;
-                    }
-                    if (h_cell[1] > (uint32_t)kCellWarp) {
-                        k_cell_block<<<148 * 2, 512, sizeof(cub::BlockRadixSort<uint32_t, 512, 32>::TempStorage), st>>>(
-                            d_cbase, d_blist, d_lcount, NB, g, (const uint32_t *)kb, ka);
-                        stats.kernel_launches += 1;
-                    }
-                    H = h_cell[0];  // the hits of "sequence -1" are gone
-                }
-            }
-            if (!cell_path) {
+            // ---- grouping: device-wide radix sort (the cell partition lives in block_candidates_fast)
+            {
                 const int ewarps = 148 * 64;
                 k_expand<<<ewarps * 32 / 256, 256, 0, st>>>(d_slot_off, g, nslots, c->d_qoff, d_st, d_cnt, d_out, ix.d_hdsst, ka,
                                                             va);
@@ -1650,9 +1968,9 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                                                                              d_counter);
                     SO_CUDA(cudaEventRecord(ev[5], st));
                     const int refill = g_xdrop_refill;
-                    auto kx = refill <= 8 ? k_xdrop<8> : refill <= 12 ? k_xdrop<12> : refill <= 16 ? k_xdrop<16>
-                              : refill <= 20 ? k_xdrop<20> : k_xdrop<24>;
-                    kx<<<148 * 2, 512, kUngTabBytes, st>>>(d_desc, G, dk.Current(), d_vals, (uint32_t)H, d_gheads, g.qst_bits,
+                    auto kx = refill <= 8 ? k_xdrop<8, false> : refill <= 12 ? k_xdrop<12, false> : refill <= 16 ? k_xdrop<16, false>
+                              : refill <= 20 ? k_xdrop<20, false> : k_xdrop<24, false>;
+                    kx<<<148 * 2, 512, kUngTabBytes, st>>>(d_desc, G, nullptr, dk.Current(), d_vals, (uint32_t)H, d_gheads, g.qst_bits,
                                                           (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
                                                           (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
                                                           qoff2[1], (uint32_t)Lq64, d_gscore, d_grank, d_counter, 1);
@@ -1769,6 +2087,260 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
         b0 = b1;
     }
     stats.candidates += (i64)out.n;
+    return SO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sync-free candidate production of one query block (the BASELINE configurations: one pattern, one alphabet,
+// sequences below 8192 residues).  Per (sub-block, chunk): k_query_seeds, k_filter, k_cell_pass<false> (cell counts
+// + in-CTA scan), k_unit_scan, k_cell_pass<true>, k_cell_small / k_cell_warp / k_cell_block (sorted cell keys +
+// X-drop descriptors), k_xdrop<FAST>, k_cell_fold / k_cell_fold_list (pair fold -> one word per candidate),
+// k_cand_sort (reference order, appended to the block's per-query lists).  Every launch is sized on the host from
+// upper bounds (a query keeps at most threshold * len + max_bucket seed hits, fsearch.py:2667-2677), every
+// data-dependent size stays in device memory, so the host never waits inside a block.
+// ---------------------------------------------------------------------------------------------
+struct FastPlan {
+    int nsplit;
+    uint32_t NB, NBh;
+    BlockGeom g;
+};
+
+static bool fast_plan(const so_ctx *c, const ChunkIndex &ix, uint32_t maxql, int nq, i64 b0, FastPlan &pl) {
+    const Params &P = c->P;
+    const i64 M = ix.c1 - ix.c0;
+    BlockGeom &g = pl.g;
+    g.nq = nq;
+    g.qb0 = (int)b0;
+    g.qst_bits = bits_for(maxql);
+    g.diag_bias = (int)ix.max_tlen + 1;
+    g.diag_bits = bits_for((uint64_t)maxql + ix.max_tlen + 2);
+    g.hd_bits = bits_for((uint64_t)M + 1);
+    g.L = ix.n_seeds ? ix.n_seeds - 1 : 0;
+    g.nc = P.nc;
+    g.thr_mul = ix.threshold;
+    g.mink = P.mink;
+    g.c0 = (int)ix.c0;
+    pl.NB = (uint32_t)(M + 2);
+    pl.nsplit = g_cell_split ? (int)g_cell_split : (int)(((size_t)pl.NB * 4 + 220 * 1024 - 1) / (220 * 1024));
+    pl.NBh = (pl.NB + (uint32_t)pl.nsplit - 1) / (uint32_t)pl.nsplit;
+    if (pl.nsplit > 8 || (size_t)pl.NBh * 4 > 220 * 1024) return false;
+    if (g.qst_bits + g.diag_bits > 31) return false;                           // cell-local key + head bit
+    if (g.qst_bits + g.hd_bits + 20 + g.diag_bits > 64) return false;          // candidate word
+    if ((uint64_t)nq * pl.NB >= 0x7fffff00ull || (uint64_t)nq * (uint64_t)pl.nsplit > 16384) return false;
+    if (maxql >= 8192 || ix.max_tlen >= 8192) return false;                    // packed X-drop state
+    return true;
+}
+
+int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, bool &eligible, int only_chunk) {
+    eligible = false;
+    const Params &P = c->P;
+    const int AS = (int)(P.alphabets.size() * P.patterns.size());
+    if (AS != 1 || getenv("SO_FORCE_PAIRS") || getenv("SO_CUB_SORT") || getenv("SO_GENERIC_UNGAP") || getenv("SO_NO_SINGLE") ||
+        getenv("SO_NO_FAST"))
+        return SO_OK;
+    if (!c->d_tung || c->q_off[(size_t)c->n_q] >= 0xfff00000ull || c->t_off[(size_t)c->n_t] >= 0xfff00000ull) return SO_OK;
+    so::DBuf<uint8_t> *scratch = lane ? c->scratch1 : c->scratch;
+    so_stats &stats = c->stats_lane[lane];
+    cudaStream_t st = lane ? c->stream1 : c->stream;
+    const size_t nch = c->chunks.size();
+    // ---- sub-blocks: bounded seed hits (all chunks), query view below 2^24 bytes
+    uint64_t thr_max = 0, maxb = 0;
+    for (const auto &ix : c->chunks) {
+        thr_max = std::max<uint64_t>(thr_max, (uint64_t)std::max<i64>(ix.threshold, 0));
+        maxb = std::max<uint64_t>(maxb, ix.max_bucket);
+    }
+    struct Sub {
+        i64 s0, s1;
+        uint32_t maxql;
+        uint64_t hit_cap;
+    };
+    std::vector<Sub> subs;
+    i64 sub_max = c->sub_block > 0 ? c->sub_block : 2047;
+    if (const char *e = getenv("SO_SUB_BLOCK0")) sub_max = std::max<i64>(1, std::min<i64>(2047, atoll(e)));  // test hook
+    {
+        i64 s0 = b0;
+        uint64_t hits = 0, res = 0;
+        uint32_t mq = 1;
+        for (i64 q = b0; q <= b1; q++) {
+            uint64_t L = 0, ub = 0;
+            if (q < b1) {
+                L = c->q_off[(size_t)q + 1] - c->q_off[(size_t)q];
+                ub = L >= (uint64_t)P.mink ? thr_max * L + maxb : 0;
+                if (ub > kHitCap) return SO_OK;  // a single query may exceed the hit buffers: general path
+            }
+            const bool full = q == b1 || hits + ub > kHitCap || res + L + 2 * kUngPad + 64 >= (1ull << 24) ||
+                              q - s0 >= sub_max;
+            if (full && q > s0) {
+                subs.push_back(Sub{s0, q, mq, hits});
+                s0 = q, hits = 0, res = 0, mq = 1;
+            }
+            if (q < b1) {
+                hits += ub, res += L;
+                if (L >= (uint64_t)P.mink) mq = std::max<uint32_t>(mq, (uint32_t)L);
+            }
+        }
+    }
+    // ---- every (sub-block, chunk) must fit the packed layouts, else nothing is launched
+    std::vector<FastPlan> plans(subs.size() * nch);
+    for (size_t si = 0; si < subs.size(); si++)
+        for (size_t ch = 0; ch < nch; ch++)
+            if (!fast_plan(c, c->chunks[ch], subs[si].maxql, (int)(subs[si].s1 - subs[si].s0), subs[si].s0, plans[si * nch + ch]))
+                return SO_OK;
+    eligible = true;
+    int rc;
+    // ---- control block: [0..7] u64 counters (0 hits of the launch, 1 X-drop steps, 2 group pool, 3 chained groups,
+    //      4 groups, 5 candidates, 6 seed hits), [8..9] transient u32 (list lengths, work counters), [10] flags
+    if ((rc = scratch[SC_CTL].reserve(256)) != SO_OK) return rc;
+    unsigned long long *d_ctl = (unsigned long long *)scratch[SC_CTL].p;
+    uint32_t *d_lcount = (uint32_t *)(d_ctl + 8);  // [0] warp list, [1] block list, [2] scatter-pass work counter, [3] cand-sort work counter
+    uint32_t *d_flags = (uint32_t *)(d_ctl + 10);  // [0] redo through the general path, [1] hard error
+    SO_CUDA(cudaMemsetAsync(d_ctl, 0, 128, st));
+    std::vector<cudaEvent_t> &evp = c->ev_pool[lane];
+    size_t ev_used = 0;
+    auto stamp = [&]() {
+        if (ev_used >= 640) return;
+        if (ev_used >= evp.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            evp.push_back(e);
+        }
+        cudaEventRecord(evp[ev_used++], st);
+    };
+    const int refill = g_xdrop_refill;
+    auto kx = refill <= 8 ? k_xdrop<8, true> : refill <= 12 ? k_xdrop<12, true> : refill <= 16 ? k_xdrop<16, true>
+              : refill <= 20 ? k_xdrop<20, true> : k_xdrop<24, true>;
+    for (size_t si = 0; si < subs.size(); si++) {
+        const Sub &sb = subs[si];
+        const int nq = (int)(sb.s1 - sb.s0);
+        std::vector<uint32_t> slot_off((size_t)nq + 1, 0);
+        uint64_t tot = 0;
+        for (int k = 0; k < nq; k++) {
+            const uint64_t L = c->q_off[(size_t)(sb.s0 + k + 1)] - c->q_off[(size_t)(sb.s0 + k)];
+            tot += L >= (uint64_t)P.mink ? L : 0;
+            slot_off[(size_t)k + 1] = (uint32_t)tot;
+        }
+        const uint32_t nslots = (uint32_t)tot;
+        if (nslots == 0) continue;
+        const uint64_t Hcap = std::max<uint64_t>(sb.hit_cap, 1);
+        const uint64_t qa = c->q_off[(size_t)sb.s0], Lq64 = c->q_off[(size_t)sb.s1] - qa;
+        uint32_t qoff2[2], qtotal;
+        ung_layout((uint32_t)Lq64, qoff2, qtotal);
+        if ((rc = scratch[SC_SLOTOFF].reserve(((size_t)nq + 1) * 4)) != SO_OK) return rc;
+        if ((rc = scratch[SC_ST].reserve((size_t)nslots * 4)) != SO_OK) return rc;
+        if ((rc = scratch[SC_CNT].reserve(((size_t)nslots + 1) * 4)) != SO_OK) return rc;
+        if ((rc = scratch[SC_QUNG].reserve(qtotal)) != SO_OK) return rc;
+        if ((rc = scratch[SC_SUB].reserve((size_t)Hcap * 4)) != SO_OK) return rc;
+        if ((rc = scratch[SC_SSUB].reserve((size_t)Hcap * 4)) != SO_OK) return rc;
+        if ((rc = scratch[SC_DESC].reserve((size_t)Hcap * 8)) != SO_OK) return rc;
+        if ((rc = scratch[SC_GSCORE].reserve((size_t)Hcap * 4)) != SO_OK) return rc;
+        if ((rc = scratch[SC_WLIST].reserve(((size_t)Hcap / kCellSmall + 16) * 4 * 2)) != SO_OK) return rc;
+        uint32_t *d_slot_off = (uint32_t *)scratch[SC_SLOTOFF].p;
+        uint32_t *d_st = (uint32_t *)scratch[SC_ST].p, *d_cnt = (uint32_t *)scratch[SC_CNT].p;
+        uint8_t *d_qung = scratch[SC_QUNG].p;
+        uint32_t *d_sub = (uint32_t *)scratch[SC_SUB].p, *d_ssub = (uint32_t *)scratch[SC_SSUB].p;
+        uint2 *d_desc = (uint2 *)scratch[SC_DESC].p;
+        uint32_t *d_gscore = (uint32_t *)scratch[SC_GSCORE].p;
+        uint32_t *d_wlist = (uint32_t *)scratch[SC_WLIST].p, *d_blist = d_wlist + ((size_t)Hcap / kCellSmall + 16);
+        SO_CUDA(cudaMemcpyAsync(d_slot_off, slot_off.data(), ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, st));
+        stats.h2d_bytes += ((i64)nq + 1) * 4;
+        // X-drop view of the sub-block's queries: (class << 3), forward + reversed (shared by all chunks)
+        if ((rc = ung_build(st, stats, c->d_qcls + qa, c->d_qoff + sb.s0, (uint32_t)nq, qa, (uint32_t)Lq64, d_qung, qoff2, qtotal,
+                            3)) != SO_OK)
+            return rc;
+        for (size_t ch = 0; ch < nch; ch++) {
+            const ChunkIndex &ix = c->chunks[ch];
+            if (ix.n_seeds == 0 || (only_chunk >= 0 && (size_t)only_chunk != ch)) continue;
+            const FastPlan &pl = plans[si * nch + ch];
+            const BlockGeom &g = pl.g;
+            const i64 M = ix.c1 - ix.c0;
+            const uint32_t NB = pl.NB, NBh = pl.NBh, nsplit = (uint32_t)pl.nsplit;
+            const uint32_t ncells = (uint32_t)nq * NB, U = (uint32_t)nq * nsplit;
+            const size_t ccap = (size_t)M + 1;
+            if ((rc = scratch[SC_CELLLOC].reserve(((size_t)ncells + 1) * 4)) != SO_OK) return rc;
+            if ((rc = scratch[SC_UNIT].reserve(((size_t)U * 2 + 8) * 4)) != SO_OK) return rc;
+            if ((rc = scratch[SC_CREG].reserve((size_t)nq * ccap * 8)) != SO_OK) return rc;
+            if ((rc = scratch[SC_QCOUNT].reserve(((size_t)nq + 8) * 4)) != SO_OK) return rc;
+            const int sgrid = std::min(nq, 148 * 2);
+            if ((rc = scratch[SC_GBUF].reserve((size_t)sgrid * ccap * 8)) != SO_OK) return rc;
+            uint32_t *d_cloc = (uint32_t *)scratch[SC_CELLLOC].p;
+            uint32_t *d_utot = (uint32_t *)scratch[SC_UNIT].p, *d_ubase = d_utot + U + 4;
+            uint64_t *d_creg = (uint64_t *)scratch[SC_CREG].p;
+            uint32_t *d_qcount = (uint32_t *)scratch[SC_QCOUNT].p;  // [nq] candidates per query, [nq] count-pass work counter
+            SO_CUDA(cudaMemsetAsync(d_qcount, 0, ((size_t)nq + 8) * 4, st));
+            stamp();
+            k_query_seeds<<<(nslots + 255) / 256, 256, 0, st>>>(c->d_qres, c->d_qoff, d_slot_off, g, ix.d_start, nslots, d_st, d_cnt);
+            k_filter<<<(nq * 32 + 255) / 256, 256, 0, st>>>(c->d_qoff, d_slot_off, c->d_perm, g, d_cnt);
+            stamp();
+            const int pblocks = std::min<int>(nq * (int)nsplit, 148 * (int)nsplit);
+            k_cell_pass<false><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit, d_cloc,
+                                                             d_utot, nullptr, nullptr, g_cell_max, d_flags, d_qcount + nq);
+            k_unit_scan<<<1, 1024, 0, st>>>(d_utot, U, d_ubase, d_ctl, d_flags);
+            k_cell_pass<true><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit, d_cloc,
+                                                            nullptr, d_ubase, d_sub, g_cell_max, d_flags, d_lcount + 2);
+            k_cell_small<<<(ncells + 255) / 256, 256, 0, st>>>(d_cloc, d_ubase, ncells, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa,
+                                                              d_sub, d_ssub, d_desc, d_wlist, d_blist, d_lcount, d_flags);
+            k_cell_warp<<<148 * 4, 256, 0, st>>>(d_cloc, d_ubase, d_wlist, d_lcount, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa, d_sub,
+                                                d_ssub, d_desc, d_flags);
+            k_cell_block<<<148 * 2, 512, sizeof(CellBlockSmem), st>>>(d_cloc, d_ubase, d_blist, d_lcount, NB, NBh, nsplit, g, c->d_qoff,
+                                                                     c->d_toff, qa, d_sub, d_ssub, d_desc, d_flags);
+            stamp();
+            kx<<<148 * 2, 512, kUngTabBytes, st>>>(d_desc, 0u, d_ssub, nullptr, nullptr, 0u, nullptr, g.qst_bits,
+                                                  (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
+                                                  (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0], qoff2[1],
+                                                  (uint32_t)Lq64, d_gscore, nullptr, d_ctl, 1);
+            stamp();
+            k_cell_fold<<<(ncells + 255) / 256, 256, 0, st>>>(d_cloc, d_ubase, ncells, NB, NBh, nsplit, g, d_ssub, d_gscore, d_creg, ccap,
+                                                             d_qcount, d_flags);
+            k_cell_fold_list<<<148 * 4, 256, 0, st>>>(d_cloc, d_ubase, d_wlist, d_blist, d_lcount, NB, NBh, nsplit, g, d_ssub, d_gscore,
+                                                     d_creg, ccap, d_qcount, d_flags);
+            k_cand_sort<<<sgrid, kCandThreads, kCandSmem * 8 + kCandBins * 4, st>>>(d_creg, ccap, d_qcount, nq, g,
+                                                                                   (uint64_t *)scratch[SC_GBUF].p, bs.vals.p, bs.capq,
+                                                                                   bs.count.p, (int)(sb.s0 - b0), d_lcount + 3, d_flags,
+                                                                                   d_ctl);
+            stamp();
+            SO_CUDA(cudaGetLastError());
+            stats.kernel_launches += 12;
+        }
+    }
+    c->ev_used[lane] = ev_used;
+    return SO_OK;
+}
+
+// after the block's stream synchronisation: flags, counters and stage times of block_candidates_fast
+int finish_fast_block(so_ctx *c, int lane, bool &redo) {
+    so::DBuf<uint8_t> *scratch = lane ? c->scratch1 : c->scratch;
+    so_stats &stats = c->stats_lane[lane];
+    cudaStream_t st = lane ? c->stream1 : c->stream;
+    redo = false;
+    unsigned long long h[11] = {};
+    SO_CUDA(cudaMemcpyAsync(h, scratch[SC_CTL].p, sizeof h, cudaMemcpyDeviceToHost, st));
+    SO_CUDA(cudaStreamSynchronize(st));
+    const uint32_t f0 = (uint32_t)h[10], f1 = (uint32_t)(h[10] >> 32);
+    if (f1) {
+        set_error("candidate production failed on the device (flag %u)", f1);
+        return SO_ELIMIT;
+    }
+    const std::vector<cudaEvent_t> &evp = c->ev_pool[lane];
+    const size_t n = c->ev_used[lane] / 5;
+    for (size_t k = 0; k < n; k++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, evp[k * 5], evp[k * 5 + 1]);
+        stats.ms_seed += ms;
+        cudaEventElapsedTime(&ms, evp[k * 5 + 1], evp[k * 5 + 2]);
+        stats.ms_sort += ms;
+        cudaEventElapsedTime(&ms, evp[k * 5 + 2], evp[k * 5 + 3]);
+        stats.ms_ungap += ms, stats.ms_ungap_kernel += ms;
+        cudaEventElapsedTime(&ms, evp[k * 5 + 3], evp[k * 5 + 4]);
+        stats.ms_select += ms;
+    }
+    c->ev_used[lane] = 0;
+    if (f0) {
+        redo = true;  // a (query, target) cell above the shared-memory sort: the general path redoes the block
+        return SO_OK;
+    }
+    stats.ungap_steps += (i64)h[1], stats.multi_groups += (i64)h[3], stats.groups += (i64)h[4];
+    stats.candidates += (i64)h[5], stats.seed_hits += (i64)h[6];
+    stats.d2h_bytes += (i64)sizeof h;
     return SO_OK;
 }
 
