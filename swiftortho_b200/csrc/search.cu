@@ -632,8 +632,8 @@ __device__ __forceinline__ void cell_extent(uint32_t c, uint32_t NB, uint32_t NB
 // sorted hit i of a cell: key + head bit, and the X-drop descriptor when it is the head of its diagonal group
 // (kp / k1 / k2 = previous / next / second next sorted keys; has* = they exist inside the cell)
 __device__ __forceinline__ void cell_emit(uint32_t p, uint32_t k, bool hasp, uint32_t kp, bool has1, uint32_t k1, bool has2,
-                                          uint32_t k2, uint32_t tbase, uint32_t qrel, const BlockGeom &g,
-                                          uint32_t *__restrict__ ssub, uint2 *__restrict__ desc) {
+                                          uint32_t k2, uint32_t tbase, uint32_t qrel, uint32_t cid, const BlockGeom &g,
+                                          uint32_t *__restrict__ ssub, uint2 *__restrict__ desc, uint32_t *__restrict__ cellid) {
     const uint32_t qmask = (1u << g.qst_bits) - 1u;
     const uint32_t dg = k >> g.qst_bits;
     const bool head = !hasp || (kp >> g.qst_bits) != dg;
@@ -642,6 +642,7 @@ __device__ __forceinline__ void cell_emit(uint32_t p, uint32_t k, bool hasp, uin
         desc[p] = make_uint2(kDescSkipX, 0u);
         return;
     }
+    cellid[p] = cid;  // (query << 16 | target + 1): read back by k_xdrop for the groups that pass
     const int qst = (int)(k & qmask);
     const int diag = (int)dg - g.diag_bias;
     const int sst = qst - diag;
@@ -660,22 +661,32 @@ __global__ void __launch_bounds__(256) k_cell_small(const uint32_t *__restrict__
                                                     uint32_t ncells, uint32_t NB, uint32_t NBh, uint32_t nsplit, BlockGeom g,
                                                     const uint64_t *__restrict__ qoff, const uint64_t *__restrict__ toff, uint64_t qa,
                                                     const uint32_t *__restrict__ sub, uint32_t *__restrict__ ssub,
-                                                    uint2 *__restrict__ desc, uint32_t *__restrict__ wlist,
+                                                    uint2 *__restrict__ desc, uint32_t *__restrict__ cellid,
+                                                    uint32_t *__restrict__ wlist,
                                                     uint32_t *__restrict__ blist, uint32_t *__restrict__ lcount,
                                                     const uint32_t *__restrict__ flags) {
     if (flags[0]) return;
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncells) return;
-    uint32_t qi, t, off, n;
-    cell_extent(c, NB, NBh, nsplit, cell_local, ubase, qi, t, off, n);
-    if (n == 0) return;
-    if (n > (uint32_t)kCellSmall) {
-        if (n <= (uint32_t)kCellWarp)
-            wlist[atomicAdd(lcount, 1u)] = c;
-        else
-            blist[atomicAdd(lcount + 1, 1u)] = c;
-        return;
+    uint32_t qi = 0, t = 0, off = 0, n = 0;
+    if (c < ncells) cell_extent(c, NB, NBh, nsplit, cell_local, ubase, qi, t, off, n);
+    {   // larger cells are queued: one atomic per warp and list
+        const int lane = threadIdx.x & 31;
+        const bool qw = n > (uint32_t)kCellSmall && n <= (uint32_t)kCellWarp, qb = n > (uint32_t)kCellWarp;
+        const unsigned mw = __ballot_sync(0xffffffffu, qw), mb = __ballot_sync(0xffffffffu, qb);
+        if (mw) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(lcount, (uint32_t)__popc(mw));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (qw) wlist[base + __popc(mw & ((1u << lane) - 1u))] = c;
+        }
+        if (mb) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(lcount + 1, (uint32_t)__popc(mb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (qb) blist[base + __popc(mb & ((1u << lane) - 1u))] = c;
+        }
     }
+    if (n == 0 || n > (uint32_t)kCellSmall) return;
     uint32_t k[kCellSmall];
 #pragma unroll
     for (int i = 0; i < kCellSmall; i++) k[i] = (uint32_t)i < n ? sub[off + i] : 0xffffffffu;
@@ -696,7 +707,7 @@ __global__ void __launch_bounds__(256) k_cell_small(const uint32_t *__restrict__
     for (int i = 0; i < kCellSmall; i++)
         if ((uint32_t)i < n)
             cell_emit(off + i, k[i], i > 0, i > 0 ? k[i - 1] : 0u, (uint32_t)(i + 1) < n, i + 1 < kCellSmall ? k[i + 1] : 0u,
-                      (uint32_t)(i + 2) < n, i + 2 < kCellSmall ? k[i + 2] : 0u, tbase, qrel, g, ssub, desc);
+                      (uint32_t)(i + 2) < n, i + 2 < kCellSmall ? k[i + 2] : 0u, tbase, qrel, (qi << 16) | t, g, ssub, desc, cellid);
 }
 
 // one warp per queued cell (9..kCellWarp hits): rank sort out of shared memory (keys of a cell are distinct)
@@ -705,35 +716,66 @@ __global__ void __launch_bounds__(256) k_cell_warp(const uint32_t *__restrict__ 
                                                    uint32_t NB, uint32_t NBh, uint32_t nsplit, BlockGeom g,
                                                    const uint64_t *__restrict__ qoff, const uint64_t *__restrict__ toff, uint64_t qa,
                                                    const uint32_t *__restrict__ sub, uint32_t *__restrict__ ssub,
-                                                   uint2 *__restrict__ desc, const uint32_t *__restrict__ flags) {
+                                                   uint2 *__restrict__ desc, uint32_t *__restrict__ cellid,
+                                                   const uint32_t *__restrict__ flags) {
     if (flags[0]) return;
     __shared__ uint32_t s_in[8][kCellWarp];
     __shared__ uint32_t s_out[8][kCellWarp + 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nlist = lcount[0];
     uint32_t *si = s_in[warp], *so_ = s_out[warp];
-    for (uint32_t w = blockIdx.x * 8 + warp; w < nlist; w += gridDim.x * 8) {
-        const uint32_t c = wlist[w];
-        uint32_t qi, t, off, n;
-        cell_extent(c, NB, NBh, nsplit, cell_local, ubase, qi, t, off, n);
-        for (uint32_t i = lane; i < n; i += 32) si[i] = sub[off + i];
-        __syncwarp();
-        for (uint32_t i = lane; i < n; i += 32) {
-            const uint32_t x = si[i];
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < n; j++) {
-                const uint32_t y = si[j];
-                rank += (y < x || (y == x && j < i)) ? 1u : 0u;
-            }
-            so_[rank] = x;
+    for (uint32_t w0 = (blockIdx.x * 8 + warp) * 32; w0 < nlist; w0 += gridDim.x * 8 * 32) {
+        // 32 queued cells per warp at a time: list entries, extents and sequence bases are fetched by the lanes in parallel
+        uint32_t my_c = 0, my_qi = 0, my_t = 0, my_off = 0, my_n = 0, my_tb = 0, my_qr = 0;
+        if (w0 + lane < nlist) {
+            my_c = wlist[w0 + lane];
+            cell_extent(my_c, NB, NBh, nsplit, cell_local, ubase, my_qi, my_t, my_off, my_n);
+            my_tb = (uint32_t)toff[g.c0 + (int)my_t - 1];
+            my_qr = (uint32_t)(qoff[g.qb0 + (int)my_qi] - qa);
         }
-        __syncwarp();
-        const uint32_t tbase = (uint32_t)toff[g.c0 + (int)t - 1];
-        const uint32_t qrel = (uint32_t)(qoff[g.qb0 + (int)qi] - qa);
-        for (uint32_t i = lane; i < n; i += 32)
-            cell_emit(off + i, so_[i], i > 0, i > 0 ? so_[i - 1] : 0u, i + 1 < n, i + 1 < n ? so_[i + 1] : 0u, i + 2 < n,
-                      i + 2 < n ? so_[i + 2] : 0u, tbase, qrel, g, ssub, desc);
-        __syncwarp();
+        const int cells = (int)min(32u, nlist - w0);
+        // cells of up to 32 hits (most of them): one key per lane, ranks by shuffles, the next cell's key is in
+        // flight while the current one is ranked; larger cells go through shared memory
+        uint32_t nx = 0;
+        {
+            const uint32_t off0 = __shfl_sync(0xffffffffu, my_off, 0), n0 = __shfl_sync(0xffffffffu, my_n, 0);
+            if ((uint32_t)lane < n0 && n0 <= 32u) nx = sub[off0 + lane];
+        }
+        for (int t = 0; t < cells; t++) {
+            const uint32_t off = __shfl_sync(0xffffffffu, my_off, t), n = __shfl_sync(0xffffffffu, my_n, t);
+            const uint32_t tbase = __shfl_sync(0xffffffffu, my_tb, t), qrel = __shfl_sync(0xffffffffu, my_qr, t);
+            const uint32_t cid = (__shfl_sync(0xffffffffu, my_qi, t) << 16) | __shfl_sync(0xffffffffu, my_t, t);
+            const uint32_t x1 = nx;
+            if (t + 1 < cells) {
+                const uint32_t off1 = __shfl_sync(0xffffffffu, my_off, t + 1), n1 = __shfl_sync(0xffffffffu, my_n, t + 1);
+                if ((uint32_t)lane < n1 && n1 <= 32u) nx = sub[off1 + lane];
+            }
+            if (n <= 32u) {
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < n; j++) {
+                    const uint32_t y = __shfl_sync(0xffffffffu, x1, (int)j);
+                    rank += (y < x1 || (y == x1 && j < (uint32_t)lane)) ? 1u : 0u;
+                }
+                if ((uint32_t)lane < n) so_[rank] = x1;
+            } else {
+                for (uint32_t i = lane; i < n; i += 32) si[i] = sub[off + i];
+                __syncwarp();
+                for (uint32_t i = lane; i < n; i += 32) {
+                    const uint32_t x = si[i];
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < n; j++) {
+                        const uint32_t y = si[j];
+                        rank += (y < x || (y == x && j < i)) ? 1u : 0u;
+                    }
+                    so_[rank] = x;
+                }
+            }
+            __syncwarp();
+            for (uint32_t i = lane; i < n; i += 32)
+                cell_emit(off + i, so_[i], i > 0, i > 0 ? so_[i - 1] : 0u, i + 1 < n, i + 1 < n ? so_[i + 1] : 0u, i + 2 < n,
+                          i + 2 < n ? so_[i + 2] : 0u, tbase, qrel, cid, g, ssub, desc, cellid);
+            __syncwarp();
+        }
     }
 }
 
@@ -769,7 +811,8 @@ __global__ void __launch_bounds__(512) k_cell_block(const uint32_t *__restrict__
                                                     uint32_t NB, uint32_t NBh, uint32_t nsplit, BlockGeom g,
                                                     const uint64_t *__restrict__ qoff, const uint64_t *__restrict__ toff, uint64_t qa,
                                                     const uint32_t *__restrict__ sub, uint32_t *__restrict__ ssub,
-                                                    uint2 *__restrict__ desc, const uint32_t *__restrict__ flags) {
+                                                    uint2 *__restrict__ desc, uint32_t *__restrict__ cellid,
+                                                    const uint32_t *__restrict__ flags) {
     if (flags[0]) return;
     extern __shared__ __align__(16) unsigned char smem[];  // CellBlockSmem
     const uint32_t nlist = lcount[1];
@@ -795,7 +838,7 @@ __global__ void __launch_bounds__(512) k_cell_block(const uint32_t *__restrict__
         const uint32_t qrel = (uint32_t)(qoff[g.qb0 + (int)qi] - qa);
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
             cell_emit(off + i, sorted[i], i > 0, i > 0 ? sorted[i - 1] : 0u, i + 1 < n, i + 1 < n ? sorted[i + 1] : 0u, i + 2 < n,
-                      i + 2 < n ? sorted[i + 2] : 0u, tbase, qrel, g, ssub, desc);
+                      i + 2 < n ? sorted[i + 2] : 0u, tbase, qrel, (qi << 16) | t, g, ssub, desc, cellid);
         __syncthreads();
     }
 }
@@ -1157,6 +1200,33 @@ __device__ __forceinline__ void ung_steps16(int &v, int &d, int &alive, int one,
 }
 #undef SO_XS
 
+enum { kXdBuf = 48, kXdBufBytes = 16 * kXdBuf * (8 + 2) };  // per-warp record buffer of k_xdrop<FAST> (16 warps per CTA)
+// warp-collective: the staged records go to their queries' regions, one global atomic per query present
+__device__ __forceinline__ void xd_flush(const uint64_t *wrec, const uint16_t *wqi, int cnt, uint64_t *__restrict__ creg,
+                                         size_t ccap, uint32_t *__restrict__ qcount, uint32_t *__restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+        const int i = i0 + lane;
+        const bool v = i < cnt;
+        const unsigned act = __ballot_sync(0xffffffffu, v);
+        if (v) {
+            const uint64_t r = wrec[i];
+            const uint32_t q = wqi[i];
+            const unsigned peers = __match_any_sync(act, q);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&qcount[q], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            if (pos < ccap)
+                creg[(size_t)q * ccap + pos] = r;
+            else
+                atomicExch(flags, 1u);  // more passing diagonals than the region holds: the general path redoes the block
+        }
+    }
+    __syncwarp();
+}
+
 // FAST = the sync-free cell path: descriptors are indexed by HIT position (one per sorted hit; hits that are not the
 // head of their diagonal group carry kDescSkipX and are skipped), the number of hits comes from device memory
 // (counters[0], written by k_unit_scan) and chains walk the sorted cell-local keys `ssub` up to the next head bit.
@@ -1168,9 +1238,21 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                                                   const uint4 *__restrict__ T4, uint32_t toffF, uint32_t toffR, uint32_t R,
                                                   const uint4 *__restrict__ Q4, uint32_t qoffF, uint32_t qoffR, uint32_t Lq,
                                                   uint32_t *__restrict__ gscore, uint32_t *__restrict__ grank,
-                                                  unsigned long long *__restrict__ counters, int one) {
-    extern __shared__ int s_tab[];  // [(ct << 5 | cq)][lane]
+                                                  unsigned long long *__restrict__ counters, int one,
+                                                  const uint32_t *__restrict__ cellid, int diag_bits,
+                                                  uint64_t *__restrict__ creg, size_t ccap, uint32_t *__restrict__ qcount,
+                                                  uint32_t *__restrict__ flags) {
+    extern __shared__ int s_tab[];  // [(ct << 5 | cq)][lane]; FAST: + per-warp record buffers
     const uint32_t G = FAST ? (uint32_t)counters[0] : G_;
+    // FAST: groups that pass (score >= 25, self.min: fsearch.py:2224, 2707) leave one record
+    //   [ target + 1 | qst | diagonal + bias | score (20 bits) ]
+    // in their query's region; records are staged per warp in shared memory and flushed kXdBuf / 3 at a time, so
+    // a warp issues one global atomic per ~30 records instead of one per passing group (consecutive groups belong
+    // to the same query: per-group atomics would serialise on one address)
+    uint64_t *wrec = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_tab) + kUngTabBytes) + (threadIdx.x >> 5) * kXdBuf;
+    uint16_t *wqi = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(s_tab) + kUngTabBytes + (blockDim.x >> 5) * kXdBuf * 8) +
+                    (threadIdx.x >> 5) * kXdBuf;
+    int wcount = 0;  // warp-uniform
     for (int k = threadIdx.x; k < kUngRows * 32 * 32; k += blockDim.x) {
         const int e = k >> 5, ct = e >> 5, cq = e & 31;
         int val = 1 << 29;
@@ -1202,7 +1284,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
         const unsigned idle = __ballot_sync(0xffffffffu, !alive);
         if (__popc(idle) >= kRefill) {
             // ---- service: finished phases, next seeds / groups, first loads of the next phase
-            bool setup = false;
+            bool setup = false, pass = false;
             if (!alive && has) {
                 const int nst = (-v) & 8191;
                 acc += (v + d + 8191) >> 13;
@@ -1256,8 +1338,29 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                         phase = 0, noleft = false, chained = true, lim = kNoLimit;
                         setup = true;
                     } else {
-                        gscore[gi] = (uint32_t)acc;
+                        if (FAST)
+                            pass = acc >= 25;
+                        else
+                            gscore[gi] = (uint32_t)acc;
                         has = false;
+                    }
+                }
+            }
+            if (FAST) {
+                const unsigned pm = __ballot_sync(0xffffffffu, pass);
+                if (pm) {
+                    if (pass) {
+                        const uint32_t cid = cellid[gi], key = ssub[gi];
+                        const uint32_t rk = ((key & qmask) << diag_bits) | ((key & ~kHeadBit) >> qst_bits);
+                        const int slot = wcount + __popc(pm & ((1u << lane) - 1u));
+                        wrec[slot] = ((uint64_t)(cid & 0xffffu) << (qst_bits + diag_bits + 20)) | ((uint64_t)rk << 20) | (uint64_t)(uint32_t)acc;
+                        wqi[slot] = (uint16_t)(cid >> 16);
+                    }
+                    wcount += __popc(pm);
+                    __syncwarp();
+                    if (wcount > kXdBuf - 32) {
+                        xd_flush(wrec, wqi, wcount, creg, ccap, qcount, flags);
+                        wcount = 0;
                     }
                 }
             }
@@ -1358,6 +1461,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
     nmulti = __reduce_add_sync(0xffffffffu, nmulti);
     if (lane == 0 && nmulti) atomicAdd(counters + 3, (unsigned long long)nmulti);  // statistic
     if (FAST) {
+        if (wcount) xd_flush(wrec, wqi, wcount, creg, ccap, qcount, flags);
         ngroups = __reduce_add_sync(0xffffffffu, ngroups);
         if (lane == 0 && ngroups) atomicAdd(counters + 4, (unsigned long long)ngroups);  // statistic: diagonal groups
     }
@@ -1450,212 +1554,235 @@ __global__ void __launch_bounds__(256) k_pair_select(const uint32_t *__restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pair fold of the cell path (fsearch.py:2696-2719): the passing diagonals (score >= 25, self.min) of one
-// (query, target) cell give one candidate: the best diagonal (the first one in the reference's dict order wins
-// ties) and, as the candidate's place in the reference's list, the rank of the FIRST passing diagonal.  With one
-// pattern and one alphabet the dict order of the groups of a query is (qst of the group's first seed ascending,
-// then target descending, then sst descending = diagonal ascending), so inside a cell it is (qst, diagonal).
-// A candidate is ONE 64-bit word, rank on top:
-//   [ qst of the first passing group | hdmask - (target + 1) | score (20 bits) | best diagonal + bias ]
-// so ordering the words of a query orders its candidates like the reference.  Candidates are appended to a
-// fixed-capacity region per query (at most one per target) through a warp-aggregated atomic.
+// Pair fold + candidate order of the cell path (fsearch.py:2696-2719), one CTA per query at a time.
+// k_xdrop<FAST> left one record per PASSING diagonal group (score >= 25) in the query's region:
+//   [ target + 1 | qst of the group's first seed | diagonal + bias | score (20 bits) ]
+// With one pattern and one alphabet the reference's dict order of a query's groups is (qst ascending, then target
+// descending, then sst descending = diagonal ascending), so inside one (query, target) pair it is (qst, diagonal).
+//   1. the records are ordered by (target, qst, diagonal): counting sort on the top bits (about 8 targets per bin),
+//      then every bin (a few records) is put in order by one thread;
+//   2. the records of one target fold into one candidate: best score, the FIRST diagonal in dict order wins ties,
+//      and the candidate's place in the reference's list is the dict rank of the target's first passing group.
+//      A candidate is one 64-bit word, rank on top:
+//        [ qst of the first passing group | hdmask - (target + 1) | score (20 bits) | best diagonal + bias ]
+//   3. the words are ordered (= the reference's candidate list order, fsearch.py:2715-2719): counting sort on the
+//      top bits of the rank, position inside a bin by counting the smaller words (bins are skewed here: ranks start
+//      with qst), and written, converted to the block format (target << 40 | score << 20 | diagonal +
+//      kCandDiagBias), behind the query's candidates of the earlier chunks (select.cu).
+// Both sorts run in passes over bin ranges that fit the shared-memory buffer (one pass for a typical query).
 // ---------------------------------------------------------------------------------------------
-struct FoldAcc {
-    uint32_t first;  // smallest (qst << diag_bits | diagonal) among the passing groups
-    uint32_t best;   // score of the best
-    uint32_t brk;    // its (qst << diag_bits | diagonal)
-};
-__device__ __forceinline__ void fold_add(FoldAcc &a, uint32_t key, uint32_t score, const BlockGeom &g) {
-    const uint32_t qmask = (1u << g.qst_bits) - 1u;
-    const uint32_t rk = ((key & qmask) << g.diag_bits) | ((key & ~kHeadBit) >> g.qst_bits);
-    a.first = min(a.first, rk);
-    if (score > a.best || (score == a.best && rk < a.brk)) a.best = score, a.brk = rk;
-}
-__device__ __forceinline__ uint64_t fold_word(const FoldAcc &a, uint32_t t, const BlockGeom &g) {
-    const uint32_t dmask = (1u << g.diag_bits) - 1u, hdmask = (1u << g.hd_bits) - 1u;
-    const uint64_t rank = ((uint64_t)(a.first >> g.diag_bits) << g.hd_bits) | (uint64_t)(hdmask - t);
-    return (rank << (20 + g.diag_bits)) | ((uint64_t)a.best << g.diag_bits) | (uint64_t)(a.brk & dmask);
-}
-// lanes with a candidate append it to their query's region
-__device__ __forceinline__ void fold_append(bool has, uint32_t qi, uint64_t word, uint64_t *__restrict__ creg, size_t ccap,
-                                            uint32_t *__restrict__ qcount) {
-    const unsigned act = __ballot_sync(0xffffffffu, has);
-    if (!has) return;
-    const unsigned peers = __match_any_sync(act, qi);
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(&qcount[qi], (uint32_t)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-    if (pos < ccap) creg[(size_t)qi * ccap + pos] = word;
-}
-
-// one thread per cell of at most kCellSmall hits
-__global__ void __launch_bounds__(256) k_cell_fold(const uint32_t *__restrict__ cell_local, const uint32_t *__restrict__ ubase,
-                                                   uint32_t ncells, uint32_t NB, uint32_t NBh, uint32_t nsplit, BlockGeom g,
-                                                   const uint32_t *__restrict__ ssub, const uint32_t *__restrict__ gscore,
-                                                   uint64_t *__restrict__ creg, size_t ccap, uint32_t *__restrict__ qcount,
-                                                   const uint32_t *__restrict__ flags) {
-    if (flags[0]) return;
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    bool has = false;
-    uint32_t qi = 0, t = 0;
-    FoldAcc a = {0xffffffffu, 0u, 0xffffffffu};
-    if (c < ncells) {
-        uint32_t off, n;
-        cell_extent(c, NB, NBh, nsplit, cell_local, ubase, qi, t, off, n);
-        if (n <= (uint32_t)kCellSmall)
-            for (uint32_t i = 0; i < n; i++) {
-                const uint32_t k = ssub[off + i];
-                if (!(k & kHeadBit)) continue;
-                const uint32_t sc = gscore[off + i];
-                if (sc >= 25u) fold_add(a, k, sc, g), has = true;
-            }
-    }
-    fold_append(has, qi, has ? fold_word(a, t, g) : 0ull, creg, ccap, qcount);
-}
-
-// one warp per queued cell (more than kCellSmall hits): both lists
-__global__ void __launch_bounds__(256) k_cell_fold_list(const uint32_t *__restrict__ cell_local, const uint32_t *__restrict__ ubase,
-                                                        const uint32_t *__restrict__ wlist, const uint32_t *__restrict__ blist,
-                                                        const uint32_t *__restrict__ lcount, uint32_t NB, uint32_t NBh,
-                                                        uint32_t nsplit, BlockGeom g, const uint32_t *__restrict__ ssub,
-                                                        const uint32_t *__restrict__ gscore, uint64_t *__restrict__ creg,
-                                                        size_t ccap, uint32_t *__restrict__ qcount,
-                                                        const uint32_t *__restrict__ flags) {
-    if (flags[0]) return;
-    const int lane = threadIdx.x & 31;
-    const uint32_t nw = lcount[0], ntot = nw + lcount[1];
-    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < ntot; w += (gridDim.x * blockDim.x) >> 5) {
-        const uint32_t c = w < nw ? wlist[w] : blist[w - nw];
-        uint32_t qi, t, off, n;
-        cell_extent(c, NB, NBh, nsplit, cell_local, ubase, qi, t, off, n);
-        FoldAcc a = {0xffffffffu, 0u, 0xffffffffu};
-        for (uint32_t i = lane; i < n; i += 32) {
-            const uint32_t k = ssub[off + i];
-            if (!(k & kHeadBit)) continue;
-            const uint32_t sc = gscore[off + i];
-            if (sc >= 25u) fold_add(a, k, sc, g);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            FoldAcc b;
-            b.first = __shfl_xor_sync(0xffffffffu, a.first, o);
-            b.best = __shfl_xor_sync(0xffffffffu, a.best, o);
-            b.brk = __shfl_xor_sync(0xffffffffu, a.brk, o);
-            a.first = min(a.first, b.first);
-            if (b.best > a.best || (b.best == a.best && b.brk < a.brk)) a.best = b.best, a.brk = b.brk;
-        }
-        if (lane == 0 && a.best >= 25u) {
-            const uint32_t pos = atomicAdd(&qcount[qi], 1u);
-            if (pos < ccap) creg[(size_t)qi * ccap + pos] = fold_word(a, t, g);
-        }
-    }
-}
-
-// Candidate order of one (query, chunk): the words of the query's region are sorted ascending (= the reference's
-// candidate list order, fsearch.py:2715-2719) and appended, converted to the block format
-// (target << 40 | score << 20 | diagonal + kCandDiagBias), to the query's list of the block (select.cu).
-// Counting sort on the top bits of the rank into kCandBins bins (shared-memory histogram, scan, scatter), then every
-// bin (about one candidate on average) is put in order by one thread.  The scattered words live in shared memory
-// when the query has at most kCandSmem candidates, else in a per-CTA global buffer (same code, generic pointer).
 enum { kCandBins = 8192, kCandSmem = 9216, kCandThreads = 512 };
+
+struct CandSmem {
+    uint64_t f[kCandSmem];
+    uint32_t bin[kCandBins + 1];
+    uint32_t part[kCandThreads / 32];
+    int q;
+    uint32_t b1, nc, flag;
+};
+
+// exclusive scan of s.bin[0..kCandBins) in place (kCandBins / kCandThreads consecutive bins per thread)
+__device__ __forceinline__ void cand_scan_bins(CandSmem &s) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int per = kCandBins / kCandThreads;
+    uint32_t v[per], sum = 0;
+#pragma unroll
+    for (int k = 0; k < per; k++) v[k] = s.bin[tid * per + k], sum += v[k];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) s.part[warp] = inc;
+    __syncthreads();
+    if (tid < 32) {
+        const uint32_t t0 = tid < kCandThreads / 32 ? s.part[tid] : 0u;
+        uint32_t w = t0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        if (tid < kCandThreads / 32) s.part[tid] = w - t0;
+    }
+    __syncthreads();
+    uint32_t run = s.part[warp] + inc - sum;
+#pragma unroll
+    for (int k = 0; k < per; k++) s.bin[tid * per + k] = run, run += v[k];
+    __syncthreads();
+}
+
+// histogram of src[0..n) on (word >> sh) and its exclusive scan: s.bin[b] = first position of bin b, s.bin[kCandBins] = n
+__device__ __forceinline__ void cand_histogram(CandSmem &s, const uint64_t *__restrict__ src, uint32_t n, int sh) {
+    for (int b = threadIdx.x; b <= kCandBins; b += kCandThreads) s.bin[b] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += kCandThreads) atomicAdd(&s.bin[(uint32_t)(src[i] >> sh)], 1u);
+    __syncthreads();
+    cand_scan_bins(s);
+    if (threadIdx.x == 0) s.bin[kCandBins] = n;
+    __syncthreads();
+}
+
+// next pass: bins [b0, b1) whose elements fit the buffer (b1 > b0; a single bin above the buffer gives b1 = b0)
+__device__ __forceinline__ uint32_t cand_plan(CandSmem &s, uint32_t b0) {
+    if (threadIdx.x == 0) {
+        const uint32_t base = s.bin[b0];
+        uint32_t lo = b0, hi = kCandBins;  // largest b1 in (b0, kCandBins] with bin[b1] - base <= kCandSmem
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (s.bin[mid] - base <= (uint32_t)kCandSmem)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        s.b1 = lo;
+    }
+    __syncthreads();
+    return s.b1;
+}
+
 __global__ void __launch_bounds__(kCandThreads) k_cand_sort(const uint64_t *__restrict__ creg, size_t ccap,
                                                            const uint32_t *__restrict__ qcount, int nq, BlockGeom g,
                                                            uint64_t *__restrict__ gbuf, uint64_t *__restrict__ bvals,
                                                            size_t bcap, uint32_t *__restrict__ bcount, int bq0,
                                                            uint32_t *__restrict__ next, uint32_t *__restrict__ flags,
                                                            unsigned long long *__restrict__ counters) {
-    if (flags[0]) return;
     extern __shared__ __align__(16) unsigned char cs_raw[];
-    uint64_t *s_f = reinterpret_cast<uint64_t *>(cs_raw);                       // [kCandSmem]
-    uint32_t *s_bin = reinterpret_cast<uint32_t *>(cs_raw + (size_t)kCandSmem * 8);  // [kCandBins]
-    __shared__ uint32_t s_part[kCandThreads / 32];
-    __shared__ int s_q;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int esh = 20 + g.diag_bits, rank_bits = g.qst_bits + g.hd_bits;
-    const int bsh = esh + max(0, rank_bits - 13);
+    CandSmem &s = *reinterpret_cast<CandSmem *>(cs_raw);
+    const int tid = threadIdx.x;
+    // (other CTAs of this kernel may raise the flag at any time: it is read by one thread and broadcast)
+    if (tid == 0) s.flag = flags[0];
+    __syncthreads();
+    if (s.flag) return;
+    const int Lb = g.qst_bits + g.diag_bits, esh = 20 + g.diag_bits, rank_bits = g.qst_bits + g.hd_bits;
+    const int sh1 = 20 + Lb + max(0, g.hd_bits - 13);  // records: bin = top 13 bits of (target + 1)
+    const int sh2 = esh + max(0, rank_bits - 13);      // words:   bin = top 13 bits of the rank
     const uint32_t dmask = (1u << g.diag_bits) - 1u, hdmask = (1u << g.hd_bits) - 1u;
+    uint64_t *C = gbuf + (size_t)blockIdx.x * ccap;    // this CTA's candidate words
+    constexpr int per = kCandBins / kCandThreads;
     for (;;) {
-        if (tid == 0) s_q = (int)atomicAdd(next, 1u);
+        if (tid == 0) s.q = (int)atomicAdd(next, 1u);
         __syncthreads();
-        const int q = s_q;
+        const int q = s.q;
         __syncthreads();
         if (q >= nq) break;
-        uint32_t n = qcount[q];
+        const uint32_t n = qcount[q];
         if (n == 0) continue;
-        if ((size_t)n > ccap) {  // cannot happen (one candidate per target at most): refuse rather than overrun
-            if (tid == 0) atomicExch(flags + 1, 3u);
-            continue;
-        }
+        if ((size_t)n > ccap) continue;  // region overflow: k_xdrop raised the redo flag
         const uint64_t *src = creg + (size_t)q * ccap;
-        uint64_t *F = n <= (uint32_t)kCandSmem ? s_f : gbuf + (size_t)blockIdx.x * ccap;
-        for (int b = tid; b < kCandBins; b += kCandThreads) s_bin[b] = 0;
-        __syncthreads();
-        for (uint32_t i = tid; i < n; i += kCandThreads) atomicAdd(&s_bin[(uint32_t)(src[i] >> bsh)], 1u);
-        __syncthreads();
-        {  // exclusive scan over the bins: kCandBins / kCandThreads consecutive bins per thread
-            constexpr int per = kCandBins / kCandThreads;
-            uint32_t v[per], sum = 0;
-#pragma unroll
-            for (int k = 0; k < per; k++) v[k] = s_bin[tid * per + k], sum += v[k];
-            uint32_t inc = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += u;
+        // ---- 1 + 2: records by (target, qst, diagonal), fold per target -> candidate words in C
+        cand_histogram(s, src, n, sh1);
+        if (tid == 0) s.nc = 0;
+        for (uint32_t b0 = 0; b0 < (uint32_t)kCandBins;) {
+            const uint32_t b1 = cand_plan(s, b0);
+            if (b1 == b0) {  // one bin above the buffer (thousands of passing diagonals on 8 targets): general path
+                if (tid == 0) atomicExch(flags, 1u);
+                break;
             }
-            if (lane == 31) s_part[warp] = inc;
+            const uint32_t base = s.bin[b0];
             __syncthreads();
-            if (tid < 32) {
-                const uint32_t t0 = tid < kCandThreads / 32 ? s_part[tid] : 0u;
-                uint32_t w = t0;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
-                    if (lane >= o) w += u;
+            for (uint32_t i = tid; i < n; i += kCandThreads) {
+                const uint64_t e = src[i];
+                const uint32_t b = (uint32_t)(e >> sh1);
+                if (b >= b0 && b < b1) s.f[atomicAdd(&s.bin[b], 1u) - base] = e;
+            }
+            __syncthreads();
+            // bins of the pass, `per` consecutive ones per thread: s.bin[b] is now the END of bin b
+            uint64_t words[4];
+            uint32_t nw = 0, wbase = 0;
+            for (int pass = 0; pass < 2; pass++) {  // pass 0 counts the candidates, pass 1 writes them
+                uint32_t cnt = 0;
+                for (uint32_t b = b0 + (uint32_t)tid * per; b < min(b1, b0 + (uint32_t)(tid + 1) * per); b++) {
+                    const uint32_t lo = (b == b0 ? base : s.bin[b - 1]) - base, hi = s.bin[b] - base;
+                    if (pass == 0)
+                        for (uint32_t i = lo + 1; i < hi; i++) {  // insertion sort of the bin
+                            const uint64_t x = s.f[i];
+                            uint32_t j = i;
+                            while (j > lo && s.f[j - 1] > x) s.f[j] = s.f[j - 1], j--;
+                            s.f[j] = x;
+                        }
+                    for (uint32_t i = lo; i < hi;) {
+                        const uint64_t e0 = s.f[i];
+                        const uint32_t t = (uint32_t)(e0 >> (20 + Lb));
+                        const uint32_t first = (uint32_t)(e0 >> 20) & ((1u << Lb) - 1u);
+                        uint32_t best = (uint32_t)e0 & 0xfffffu, brk = first;
+                        uint32_t k = i + 1;
+                        for (; k < hi; k++) {
+                            const uint64_t e = s.f[k];
+                            if ((uint32_t)(e >> (20 + Lb)) != t) break;
+                            const uint32_t sc = (uint32_t)e & 0xfffffu;
+                            if (sc > best) best = sc, brk = (uint32_t)(e >> 20) & ((1u << Lb) - 1u);
+                        }
+                        i = k;
+                        if (pass == 1) {
+                            const uint64_t rank = ((uint64_t)(first >> g.diag_bits) << g.hd_bits) | (uint64_t)(hdmask - t);
+                            const uint64_t w = (rank << esh) | ((uint64_t)best << g.diag_bits) | (uint64_t)(brk & dmask);
+                            if (nw < 4)
+                                words[nw] = w;  // the usual handful goes out together below
+                            else
+                                C[wbase + nw] = w;
+                            nw++;
+                        } else
+                            cnt++;
+                    }
                 }
-                if (tid < kCandThreads / 32) s_part[tid] = w - t0;
+                if (pass == 0) {
+                    wbase = cnt ? atomicAdd(&s.nc, cnt) : 0u;  // order inside C is irrelevant (sorted next)
+                } else {
+                    for (uint32_t k = 0; k < min(nw, 4u); k++) C[wbase + k] = words[k];
+                }
             }
             __syncthreads();
-            uint32_t run = s_part[warp] + inc - sum;
-#pragma unroll
-            for (int k = 0; k < per; k++) s_bin[tid * per + k] = run, run += v[k];
+            b0 = b1;
         }
+        if (tid == 0) s.flag = flags[0];
         __syncthreads();
-        for (uint32_t i = tid; i < n; i += kCandThreads) {
-            const uint64_t e = src[i];
-            F[atomicAdd(&s_bin[(uint32_t)(e >> bsh)], 1u)] = e;
-        }
+        const uint32_t nc = s.nc;
+        const uint32_t stop = s.flag;
         __syncthreads();
-        // s_bin[b] is now the END of bin b: insertion sort inside every bin
-        for (int b = tid; b < kCandBins; b += kCandThreads) {
-            const uint32_t lo = b ? s_bin[b - 1] : 0u, hi = s_bin[b];
-            for (uint32_t i = lo + 1; i < hi; i++) {
-                const uint64_t x = F[i];
-                uint32_t j = i;
-                while (j > lo && F[j - 1] > x) F[j] = F[j - 1], j--;
-                F[j] = x;
-            }
-        }
-        __syncthreads();
-        const uint32_t base = bcount[bq0 + q];
-        if ((size_t)base + n > bcap) {
+        if (stop) continue;
+        // ---- 3: words by rank -> the block's list of the query
+        const uint32_t cbase = bcount[bq0 + q];
+        if ((size_t)cbase + nc > bcap) {
             if (tid == 0) atomicExch(flags + 1, 2u);
             continue;
         }
-        uint64_t *dst = bvals + (size_t)(bq0 + q) * bcap + base;
-        for (uint32_t i = tid; i < n; i += kCandThreads) {
-            const uint64_t e = F[i];
-            const uint32_t t = hdmask - (uint32_t)((e >> esh) & hdmask);      // target + 1 inside the chunk
-            const uint32_t score = (uint32_t)((e >> g.diag_bits) & 0xfffffu);
-            const int diag = (int)((uint32_t)e & dmask) - g.diag_bias;
-            dst[i] = ((uint64_t)(uint32_t)(g.c0 + (int)t - 1) << 40) | ((uint64_t)score << 20) | (uint64_t)(uint32_t)(diag + kCandDiagBias);
+        uint64_t *dst = bvals + (size_t)(bq0 + q) * bcap + cbase;
+        cand_histogram(s, C, nc, sh2);
+        for (uint32_t b0 = 0; b0 < (uint32_t)kCandBins;) {
+            const uint32_t b1 = cand_plan(s, b0);
+            if (b1 == b0) {
+                if (tid == 0) atomicExch(flags, 1u);
+                break;
+            }
+            const uint32_t base = s.bin[b0];
+            __syncthreads();
+            for (uint32_t i = tid; i < nc; i += kCandThreads) {
+                const uint64_t e = C[i];
+                const uint32_t b = (uint32_t)(e >> sh2);
+                if (b >= b0 && b < b1) s.f[atomicAdd(&s.bin[b], 1u) - base] = e;
+            }
+            __syncthreads();
+            const uint32_t m = s.bin[b1 - 1] - base;  // elements of the pass
+            for (uint32_t i = tid; i < m; i += kCandThreads) {
+                const uint64_t e = s.f[i];
+                const uint32_t b = (uint32_t)(e >> sh2);
+                const uint32_t lo = (b == b0 ? base : s.bin[b - 1]) - base, hi = s.bin[b] - base;
+                uint32_t r = 0;
+                for (uint32_t j = lo; j < hi; j++) r += s.f[j] < e ? 1u : 0u;
+                const uint32_t t = hdmask - (uint32_t)((e >> esh) & hdmask);  // target + 1 inside the chunk
+                const uint32_t score = (uint32_t)((e >> g.diag_bits) & 0xfffffu);
+                const int diag = (int)((uint32_t)e & dmask) - g.diag_bias;
+                dst[base + lo + r] = ((uint64_t)(uint32_t)(g.c0 + (int)t - 1) << 40) | ((uint64_t)score << 20) |
+                                     (uint64_t)(uint32_t)(diag + kCandDiagBias);
+            }
+            __syncthreads();
+            b0 = b1;
         }
         if (tid == 0) {
-            bcount[bq0 + q] = base + n;
-            atomicAdd(counters + 5, (unsigned long long)n);  // statistic: candidates
+            bcount[bq0 + q] = cbase + nc;
+            atomicAdd(counters + 5, (unsigned long long)nc);  // statistic: candidates
         }
         __syncthreads();
     }
@@ -1729,15 +1856,15 @@ int upload_search_config(so_ctx *c) {
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-    SO_CUDA(cudaFuncSetAttribute(k_xdrop<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-    SO_CUDA(cudaFuncSetAttribute(k_xdrop<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-    SO_CUDA(cudaFuncSetAttribute(k_xdrop<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-    SO_CUDA(cudaFuncSetAttribute(k_xdrop<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
-    SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + kXdBufBytes));
     SO_CUDA(cudaFuncSetAttribute(k_cell_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CellBlockSmem)));
     SO_CUDA(cudaFuncSetAttribute(k_cell_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     SO_CUDA(cudaFuncSetAttribute(k_cell_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    SO_CUDA(cudaFuncSetAttribute(k_cand_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, kCandSmem * 8 + kCandBins * 4));
+    SO_CUDA(cudaFuncSetAttribute(k_cand_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CandSmem)));
     g_cell_max = kCellMax;
     if (const char *cm = getenv("SO_CELL_MAX")) g_cell_max = (uint32_t)std::max(1, std::min((int)kCellMax, atoi(cm)));  // test hook
     return upload_cfg(c->P);
@@ -1973,7 +2100,8 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                     kx<<<148 * 2, 512, kUngTabBytes, st>>>(d_desc, G, nullptr, dk.Current(), d_vals, (uint32_t)H, d_gheads, g.qst_bits,
                                                           (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
                                                           (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
-                                                          qoff2[1], (uint32_t)Lq64, d_gscore, d_grank, d_counter, 1);
+                                                          qoff2[1], (uint32_t)Lq64, d_gscore, d_grank, d_counter, 1, nullptr, 0, nullptr, 0,
+                                                          nullptr, nullptr);
                     d_gkey = (const uint64_t *)scratch[SC_GKEY].p;
                     stats.kernel_launches += 2;
                 } else {
@@ -2094,8 +2222,8 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
 // Sync-free candidate production of one query block (the BASELINE configurations: one pattern, one alphabet,
 // sequences below 8192 residues).  Per (sub-block, chunk): k_query_seeds, k_filter, k_cell_pass<false> (cell counts
 // + in-CTA scan), k_unit_scan, k_cell_pass<true>, k_cell_small / k_cell_warp / k_cell_block (sorted cell keys +
-// X-drop descriptors), k_xdrop<FAST>, k_cell_fold / k_cell_fold_list (pair fold -> one word per candidate),
-// k_cand_sort (reference order, appended to the block's per-query lists).  Every launch is sized on the host from
+// X-drop descriptors), k_xdrop<FAST> (passing groups leave a record in their query's region), k_cand_sort (pair fold, reference order,
+// appended to the block's per-query lists).  Every launch is sized on the host from
 // upper bounds (a query keeps at most threshold * len + max_bucket seed hits, fsearch.py:2667-2677), every
 // data-dependent size stays in device memory, so the host never waits inside a block.
 // ---------------------------------------------------------------------------------------------
@@ -2125,7 +2253,8 @@ static bool fast_plan(const so_ctx *c, const ChunkIndex &ix, uint32_t maxql, int
     pl.NBh = (pl.NB + (uint32_t)pl.nsplit - 1) / (uint32_t)pl.nsplit;
     if (pl.nsplit > 8 || (size_t)pl.NBh * 4 > 220 * 1024) return false;
     if (g.qst_bits + g.diag_bits > 31) return false;                           // cell-local key + head bit
-    if (g.qst_bits + g.hd_bits + 20 + g.diag_bits > 64) return false;          // candidate word
+    if (g.qst_bits + g.hd_bits + 20 + g.diag_bits > 64) return false;          // candidate word / passing-group record
+    if (g.hd_bits > 16 || nq >= 65536) return false;                           // (query << 16 | target + 1), 16-bit query in the record buffers
     if ((uint64_t)nq * pl.NB >= 0x7fffff00ull || (uint64_t)nq * (uint64_t)pl.nsplit > 16384) return false;
     if (maxql >= 8192 || ix.max_tlen >= 8192) return false;                    // packed X-drop state
     return true;
@@ -2239,7 +2368,7 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
         uint8_t *d_qung = scratch[SC_QUNG].p;
         uint32_t *d_sub = (uint32_t *)scratch[SC_SUB].p, *d_ssub = (uint32_t *)scratch[SC_SSUB].p;
         uint2 *d_desc = (uint2 *)scratch[SC_DESC].p;
-        uint32_t *d_gscore = (uint32_t *)scratch[SC_GSCORE].p;
+        uint32_t *d_cellid = (uint32_t *)scratch[SC_GSCORE].p;  // (query << 16 | target + 1) of every group head
         uint32_t *d_wlist = (uint32_t *)scratch[SC_WLIST].p, *d_blist = d_wlist + ((size_t)Hcap / kCellSmall + 16);
         SO_CUDA(cudaMemcpyAsync(d_slot_off, slot_off.data(), ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, st));
         stats.h2d_bytes += ((i64)nq + 1) * 4;
@@ -2255,7 +2384,7 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
             const i64 M = ix.c1 - ix.c0;
             const uint32_t NB = pl.NB, NBh = pl.NBh, nsplit = (uint32_t)pl.nsplit;
             const uint32_t ncells = (uint32_t)nq * NB, U = (uint32_t)nq * nsplit;
-            const size_t ccap = (size_t)M + 1;
+            const size_t ccap = 2 * ((size_t)M + 1);  // passing diagonal groups per query (overflow raises the redo flag)
             if ((rc = scratch[SC_CELLLOC].reserve(((size_t)ncells + 1) * 4)) != SO_OK) return rc;
             if ((rc = scratch[SC_UNIT].reserve(((size_t)U * 2 + 8) * 4)) != SO_OK) return rc;
             if ((rc = scratch[SC_CREG].reserve((size_t)nq * ccap * 8)) != SO_OK) return rc;
@@ -2278,28 +2407,24 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
             k_cell_pass<true><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit, d_cloc,
                                                             nullptr, d_ubase, d_sub, g_cell_max, d_flags, d_lcount + 2);
             k_cell_small<<<(ncells + 255) / 256, 256, 0, st>>>(d_cloc, d_ubase, ncells, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa,
-                                                              d_sub, d_ssub, d_desc, d_wlist, d_blist, d_lcount, d_flags);
+                                                              d_sub, d_ssub, d_desc, d_cellid, d_wlist, d_blist, d_lcount, d_flags);
             k_cell_warp<<<148 * 4, 256, 0, st>>>(d_cloc, d_ubase, d_wlist, d_lcount, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa, d_sub,
-                                                d_ssub, d_desc, d_flags);
+                                                d_ssub, d_desc, d_cellid, d_flags);
             k_cell_block<<<148 * 2, 512, sizeof(CellBlockSmem), st>>>(d_cloc, d_ubase, d_blist, d_lcount, NB, NBh, nsplit, g, c->d_qoff,
-                                                                     c->d_toff, qa, d_sub, d_ssub, d_desc, d_flags);
+                                                                     c->d_toff, qa, d_sub, d_ssub, d_desc, d_cellid, d_flags);
             stamp();
-            kx<<<148 * 2, 512, kUngTabBytes, st>>>(d_desc, 0u, d_ssub, nullptr, nullptr, 0u, nullptr, g.qst_bits,
-                                                  (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
-                                                  (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0], qoff2[1],
-                                                  (uint32_t)Lq64, d_gscore, nullptr, d_ctl, 1);
+            kx<<<148 * 2, 512, kUngTabBytes + kXdBufBytes, st>>>(d_desc, 0u, d_ssub, nullptr, nullptr, 0u, nullptr, g.qst_bits,
+                                                                (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
+                                                                (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
+                                                                qoff2[1], (uint32_t)Lq64, nullptr, nullptr, d_ctl, 1, d_cellid,
+                                                                g.diag_bits, d_creg, ccap, d_qcount, d_flags);
             stamp();
-            k_cell_fold<<<(ncells + 255) / 256, 256, 0, st>>>(d_cloc, d_ubase, ncells, NB, NBh, nsplit, g, d_ssub, d_gscore, d_creg, ccap,
-                                                             d_qcount, d_flags);
-            k_cell_fold_list<<<148 * 4, 256, 0, st>>>(d_cloc, d_ubase, d_wlist, d_blist, d_lcount, NB, NBh, nsplit, g, d_ssub, d_gscore,
-                                                     d_creg, ccap, d_qcount, d_flags);
-            k_cand_sort<<<sgrid, kCandThreads, kCandSmem * 8 + kCandBins * 4, st>>>(d_creg, ccap, d_qcount, nq, g,
-                                                                                   (uint64_t *)scratch[SC_GBUF].p, bs.vals.p, bs.capq,
-                                                                                   bs.count.p, (int)(sb.s0 - b0), d_lcount + 3, d_flags,
-                                                                                   d_ctl);
+            k_cand_sort<<<sgrid, kCandThreads, sizeof(CandSmem), st>>>(d_creg, ccap, d_qcount, nq, g, (uint64_t *)scratch[SC_GBUF].p,
+                                                                      bs.vals.p, bs.capq, bs.count.p, (int)(sb.s0 - b0), d_lcount + 3,
+                                                                      d_flags, d_ctl);
             stamp();
             SO_CUDA(cudaGetLastError());
-            stats.kernel_launches += 12;
+            stats.kernel_launches += 10;
         }
     }
     c->ev_used[lane] = ev_used;
