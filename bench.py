@@ -28,17 +28,35 @@ sys.path.insert(0, ROOT)
 AA9 = 'AST,CFILMVY,DN,EQ,G,H,KR,P,W'
 FLAGS = dict(ssd='111111', nr=AA9, ht=120000000, step=1, expect=1e-5, v=500, max_miss=1e-3, thr=-1, flt='T', chk=50000)
 CACHE = os.environ.get('SWIFTORTHO_BENCH_CACHE', '/tmp/swiftortho_b200_bench')
+# BASELINE.json configs: id -> (proteins, taxa, seed pattern, e-value, description)
+CONFIGS = {
+    2: (100000, 20, '111111', 1e-5, 'synthetic 100k proteins (~350 aa mean, 20 taxa), seed 111111'),
+    3: (1000000, 200, '111111', 1e-5, 'synthetic 1M proteins (200 taxa), seed 111111'),
+    4: (250000, 50, '1110100111', 1e-3, 'synthetic 250k proteins (50 taxa), spaced seed 1110100111, -e 1e-3'),
+    5: (100000, 20, '111111', 1e-5, 'synthetic 100k proteins, long-tailed lengths 50-5000 aa, seed 111111'),
+}
 METRIC = 'all-vs-all proteins/sec (find_hit blastp, config 2: 100k synthetic proteins, seed 111111)'
 
 
-def dataset(n, taxa, rank=0, wait=True):
-    """config-2 FASTA (generated once per box, deterministic)."""
+def flags_of(args):
+    n, taxa, ssd, ev, _ = CONFIGS[args.config]
+    return dict(FLAGS, ssd=ssd, expect=ev)
+
+
+def metric_of(args):
+    if args.config == 2:
+        return METRIC
+    return 'all-vs-all proteins/sec (find_hit blastp, config %d: %s)' % (args.config, CONFIGS[args.config][4])
+
+
+def dataset(n, taxa, rank=0, wait=True, config=2):
+    """FASTA of a BASELINE config (generated once per box, deterministic)."""
     os.makedirs(CACHE, exist_ok=True)
-    path = os.path.join(CACHE, 'c2_%d_%d.fsa' % (n, taxa))
+    path = os.path.join(CACHE, 'c%d_%d_%d.fsa' % (config, n, taxa))
     done = path + '.done'
     if rank == 0 and not os.path.exists(done):
         from swiftortho_b200 import synth
-        synth.write_config(path + '.tmp', 2, n=n, taxa=taxa)
+        synth.write_config(path + '.tmp', config, n=n, taxa=taxa)
         os.replace(path + '.tmp', path)
         open(done, 'w').close()
     while wait and not os.path.exists(done):
@@ -109,20 +127,20 @@ _SESSION = None
 def _cpu_worker(job):
     import ctypes as C
     L, h = _SESSION
-    q0, q1 = job
+    q0, q1, out = job
     st = (C.c_longlong * 7)()
-    t = L.orc_session_search(h, q0, q1, b'', st)
+    t = L.orc_session_search(h, q0, q1, out.encode(), st)
     return t, list(st)
 
 
-def cpu_arm(fasta, n_total, steps, warmup, per_worker, first_query=0):
+def cpu_arm(fasta, n_total, steps, warmup, per_worker, first_query=0, flags=None, parity_out=None):
     """The oracle port (oracle/fsearch_oracle.cpp = CPU restatement of lib/fsearch.py) on all host
     cores: the index is built once, then forked workers each search their own query window like the
     reference's `find_hit.py -a <cores>` slices.  Returns per-step wall times and counters."""
     global _SESSION
     import multiprocessing as mp
     L = _oracle_lib()
-    f = FLAGS
+    f = flags or FLAGS
     h = L.orc_session_open(fasta.encode(), fasta.encode(), f['expect'], f['v'], f['max_miss'], -1, -1, f['thr'],
                            f['flt'].encode(), f['ssd'].encode(), f['nr'].encode(), f['step'], f['ht'], f['chk'])
     assert h, 'oracle session failed'
@@ -130,14 +148,20 @@ def cpu_arm(fasta, n_total, steps, warmup, per_worker, first_query=0):
     _SESSION = (L, h)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     workers = max(1, min(cores, 64))
-    times, counters = [], [0] * 7
+    times, counters, parity = [], [0] * 7, None
     with mp.get_context('fork').Pool(workers) as pool:
         q = first_query
         for s in range(warmup + steps):
             jobs = []
             for w in range(workers):
                 a = q % max(1, n_total - per_worker)
-                jobs.append((a, a + per_worker))
+                # the rows of the first window of the first timed step are kept: the GPU arm checks its own rows
+                # for the same queries against them (parity_check, outside every timed region)
+                keep = parity_out if (parity_out and s == warmup and w == 0) else ''
+                if keep:
+                    open(keep, 'wb').close()
+                    parity = (a, a + per_worker)
+                jobs.append((a, a + per_worker, keep))
                 q += per_worker
             t0 = time.perf_counter()
             res = pool.map(_cpu_worker, jobs, chunksize=1)
@@ -146,34 +170,48 @@ def cpu_arm(fasta, n_total, steps, warmup, per_worker, first_query=0):
                 times.append(dt)
                 for _, st in res:
                     counters = [a + b for a, b in zip(counters, st)]
-    return dict(times=times, workers=workers, per_step=workers * per_worker, build_s=build_s, counters=counters)
+    return dict(times=times, workers=workers, per_step=workers * per_worker, build_s=build_s, counters=counters,
+                parity=parity if parity_out else None)
+
+
+def oracle_build_flags():
+    try:
+        for line in open(os.path.join(ROOT, 'oracle', 'Makefile')):
+            if line.startswith('CXXFLAGS'):
+                return 'g++ ' + line.split('=', 1)[1].strip()
+    except OSError:
+        pass
+    return None
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     n, taxa = args.n, args.taxa
-    fasta = dataset(n, taxa)
-    r = cpu_arm(fasta, n, args.steps, args.warmup, args.cpu_queries)
+    fasta = dataset(n, taxa, config=args.config)
+    r = cpu_arm(fasta, n, args.steps, args.warmup, args.cpu_queries, flags=flags_of(args), parity_out=args.parity_out)
     tot = sum(r['times'])
     value = r['per_step'] * len(r['times']) / tot
     sample = '%d workers x %d queries per step against all %d targets (index built once: %.1f s, not timed)' % (
         r['workers'], args.cpu_queries, n, r['build_s'])
-    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'proteins/s', 'n_gpus': args.gpus,
+    line = {'impl': 'reference', 'metric': metric_of(args), 'value': value, 'unit': 'proteins/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / len(r['times']),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic',
             'config': workload_config(args, r['per_step']),
             'cpu_baseline': {'value': value, 'unit': 'proteins/s', 'cores': r['workers'], 'kind': 'port',
-                             'sample': sample},
+                             'sample': sample, 'build': oracle_build_flags()},
+            'parity_window': r['parity'],
             'e2e': {'value': value, 'unit': 'proteins/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gcups_cpu': r['counters'][5] / tot / 1e9}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(args, block):
-    return {'workload': 'BASELINE config 2: synthetic %d proteins (%d taxa, ~350 aa) all-vs-all, blastp -e 1e-5 '
-                        '-s 111111 -r aa9 -M 120000000 -c 50000 -j 1' % (args.n, args.taxa),
-            'step': 'one block of %d queries per GPU against the full target index (2 chunks resident in HBM)' % block,
+    f = flags_of(args)
+    nch = (args.n + FLAGS['chk'] - 1) // FLAGS['chk']
+    return {'workload': 'BASELINE config %d: synthetic %d proteins (%d taxa) all-vs-all, blastp -e %g '
+                        '-s %s -r aa9 -M 120000000 -c 50000 -j 1' % (args.config, args.n, args.taxa, f['expect'], f['ssd']),
+            'step': 'one block of %d queries per GPU against the full target index (%d chunks resident in HBM)' % (block, nch),
             'l2': 'every step uses a new query block; seed-hit buffers are GBs per step (>> 126 MB L2)'}
 
 
@@ -195,6 +233,158 @@ def reduce_over_ranks(vals, dist, device):
     return [(mx[i] if i in MAX_IDX else sm[i]).item() for i in range(len(vals))]
 
 
+def full_job(args, rank, world, local, fasta, barrier, out_dir):
+    """The whole find_hit job (SURVEY.md 8d metric 1): FASTA file in -> OUT written.  Every rank parses the FASTA,
+    loads the targets, builds the complete index, seg-masks and searches ITS query slice (balanced by residues,
+    swiftortho_b200.find_hit.slices_by_residues) and writes a part file; rank 0 concatenates the parts in query
+    order (bin/find_hit.py:135-146).  Returns the rank's wall time and counters; the timed region starts after the
+    barrier and ends when the rank's part (rank 0: the merged OUT) is on disk."""
+    import ctypes as C
+    import numpy as np
+    from swiftortho_b200 import find_hit
+    from swiftortho_b200 import search as so
+    barrier()
+    t0 = time.perf_counter()
+    F = so.Fasta(fasta)
+    S = so.Searcher(device=local, **flags_of(args))
+    S.set_targets(F)
+    info = S.build_index()
+    t_index = time.perf_counter() - t0
+    sl = find_hit.slices_by_residues(F, 0, F.N, world)
+    a, b = sl[rank] if rank < len(sl) else (0, 0)
+    part = os.path.join(out_dir, 'bench_full.%012d' % a)
+    open(part, 'wb').close()
+    lib = S.lib
+    nrows = 0
+    if b > a:
+        off = np.ascontiguousarray(F.offsets[a:b + 1])
+        so.check(lib.so_set_queries(S.h, C.c_void_p(F._res.value), off.ctypes.data, b - a))
+        S.stats(reset=True)
+        for q0 in range(0, b - a, args.full_block):
+            rows = S.search(q0, min(b - a, q0 + args.full_block))
+            rows.view()['query'] += a
+            so.check(lib.so_write_rows(rows.ptr, rows.n, F.h, F.h, part.encode(), 1))
+            nrows += rows.n
+    st = S.stats()
+    t_part = time.perf_counter() - t0
+    barrier()
+    out = os.path.join(out_dir, 'bench_full.sc')
+    if rank == 0:
+        find_hit._concat(out, [os.path.join(out_dir, 'bench_full.%012d' % s0) for s0, _ in sl])
+    dt = time.perf_counter() - t0
+    props = None
+    if rank == 0:
+        props = table_properties(out, args.full_check_rows)
+        os.remove(out)
+    S.close()
+    F.close()
+    return dict(wall=dt, t_index=t_index, t_part=t_part, queries=b - a, rows=nrows, stats=st, info=info, props=props,
+                n_total=F.N)
+
+
+def table_properties(path, max_rows):
+    """Size-independent properties of a hit table (first `max_rows` rows): queries ascending, bits descending inside a
+    query, 16 columns, and the best hit of a query is (almost always) the query itself."""
+    last_q, last_bit, firsts, queries, rows, ok = -1, None, 0, 0, 0, True
+    with open(path, 'rb') as f:
+        for ln in f:
+            c = ln.rstrip(b'\n').split(b'\t')
+            if len(c) != 16:
+                ok = False
+                break
+            q, bit = int(c[14]), int(c[11])
+            if q < last_q or (q == last_q and bit > last_bit):
+                ok = False
+                break
+            if q != last_q:
+                queries += 1
+                firsts += c[0] == c[1]
+            last_q, last_bit = q, bit
+            rows += 1
+            if rows >= max_rows:
+                break
+    return {'ordered': ok, 'rows_checked': rows, 'queries_checked': queries,
+            'self_hit_first_frac': firsts / max(1, queries)}
+
+
+def run_full(args, rank, world, local, dist, fasta):
+    """`--mode full`: strong scaling of one whole job (the north-star measurement for config 3)."""
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+    shm = '/dev/shm' if os.path.isdir('/dev/shm') else CACHE
+    out_dir = os.path.join(shm, 'swiftortho_b200_full')
+    os.makedirs(out_dir, exist_ok=True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    r = full_job(args, rank, world, local, fasta, barrier, out_dir)
+    clk = clocks.stop() if rank == 0 else None
+    st = r['stats']
+    vals = [r['wall'], r['t_index'], r['t_part'], float(r['queries']), float(r['rows']), st['ms_ungap_kernel'], float(st['ungap_steps']),
+            float(st['h2d_bytes']), float(st['d2h_bytes']), float(st['kernel_launches']), float(st['dp_cells']), st['ms_dp'],
+            float(st['seed_hits']), float(st['candidates']), float(st['alignments']), st['ms_sort'], st['ms_select'], st['ms_seed'],
+            st['ms_traceback'], st['ms_host'], float(st['redo_blocks'])]
+    if dist is not None:
+        import torch
+        t = torch.tensor(vals, dtype=torch.float64, device='cuda')
+        mx, sm = t.clone(), t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        mxi = (0, 1, 2, 5, 11, 15, 16, 17, 18, 19)
+        vals = [(mx[i] if i in mxi else sm[i]).item() for i in range(len(vals))]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    (wall, t_index, t_part, nq, nrows, ms_x, steps, h2d, d2h, launches, cells, ms_dp, hits, cands, alns, ms_sort, ms_sel, ms_seed,
+     ms_tb, ms_host, redo) = vals
+    int_peak = json.load(open(os.path.join(ROOT, 'profiles', 'int_peak.json')))
+    ach = 6.0 * steps / max(world, 1) / (ms_x * 1e-3) / 1e9 if ms_x > 0 else 0.0
+    value = nq / wall
+    line = {'metric': metric_of(args), 'value': value, 'unit': 'proteins/s', 'n_gpus': world, 'steps': 1, 'warmup': 0,
+            'ms_per_step': 1e3 * wall, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'int32',
+            'data': 'synthetic',
+            'config': dict(workload_config(args, args.full_block),
+                           step='the whole job: FASTA parsed, targets loaded, complete index built on every rank, %d queries split '
+                                'by residues over %d rank(s), 16-column parts written and concatenated by rank 0' % (int(nq), world)),
+            'roofline': {'kernel': 'k_xdrop', 'bound': 'int32', 'achieved': ach, 'peak': int_peak['gops_measured'], 'unit': 'Gop/s',
+                         'frac': ach / int_peak['gops_measured'], 'traffic': None,
+                         'timing': 'CUDA events on the launching streams (two production lanes share the GPU), max over ranks',
+                         'peak_source': 'tools/int_peak.cu measured on this pool (profiles/int_peak.json)'},
+            'e2e': {'value': value, 'unit': 'proteins/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'note': 'the job is end to end by construction: host FASTA file in, text table out'},
+            'gpu_launches': int(launches), 'clocks': clk,
+            'wall_s': wall, 'index_build_s_max': t_index, 'part_written_s_max': t_part, 'rows': int(nrows),
+            'seed_hits': hits, 'candidates': cands, 'alignments': alns, 'dp_cells': cells, 'redo_blocks': int(redo),
+            'stage_ms_max_rank': dict(seed=ms_seed, grouping=ms_sort, xdrop=ms_x, select=ms_sel, dp=ms_dp, traceback=ms_tb, host=ms_host),
+            'index_chunks': len(r['info']), 'table_properties': r['props']}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def parity_check(S, F, so, window, ref_path):
+    """Rows of the query window the CPU arm kept, recomputed on the GPU through the public API and compared byte for
+    byte with the oracle's text (outside every timed region)."""
+    import ctypes as C
+    import numpy as np
+    if not window or not os.path.exists(ref_path):
+        return {'status': 'skipped'}
+    a, b = window
+    want = open(ref_path, 'rb').read()
+    off = np.ascontiguousarray(F.offsets[a:b + 1])
+    so.check(S.lib.so_set_queries(S.h, C.c_void_p(F._res.value), off.ctypes.data, b - a))
+    rows = S.search(0, b - a)
+    rows.view()['query'] += a
+    outp = ref_path + '.gpu'
+    so.check(S.lib.so_write_rows(rows.ptr, rows.n, F.h, F.h, outp.encode(), 0))
+    got = open(outp, 'rb').read()
+    os.remove(outp)
+    return {'status': 'ok' if got == want else 'MISMATCH', 'queries': [a, b], 'rows': want.count(b'\n'),
+            'checker': 'oracle port (oracle/fsearch_oracle.cpp), byte comparison of the 16-column text'}
+
+
 def run_ours(args, rank, world, local):
     dist = None
     if world > 1:
@@ -203,10 +393,13 @@ def run_ours(args, rank, world, local):
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     n, taxa, B = args.n, args.taxa, args.block
-    fasta = dataset(n, taxa, rank)
+    fasta = dataset(n, taxa, rank, config=args.config)
     from swiftortho_b200 import search as so
+    if args.mode == 'full':
+        run_full(args, rank, world, local, dist, fasta)
+        return
     F = so.Fasta(fasta)
-    S = so.Searcher(device=local, **FLAGS)
+    S = so.Searcher(device=local, **flags_of(args))
     t0 = time.perf_counter()
     S.set_targets(F)
     info = S.build_index()
@@ -364,7 +557,7 @@ def run_ours(args, rank, world, local):
                'note': '14 INT ops per cell (SURVEY.md 8d); achieved = %d config-shaped pairs in one so_align_batch, '
                        'k_banded_dp time by CUDA events; in_pipeline = same kernel inside the search steps (small '
                        'launches sharing the GPU with the seeding kernels)' % args.align_pairs}
-    line = {'metric': METRIC, 'value': value, 'unit': 'proteins/s', 'n_gpus': world, 'steps': args.steps,
+    line = {'metric': metric_of(args), 'value': value, 'unit': 'proteins/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic', 'config': workload_config(args, B),
             'roofline': roof, 'roofline_grouping': hbm, 'roofline_dp': dp_roof, 'gapped_gcups': gcups_alone,
@@ -377,16 +570,48 @@ def run_ours(args, rank, world, local):
             'index_build_ms': index_ms, 'index': info, 'alignments_per_query': alignments / max(1.0, nq),
             'seed_hits_per_query': seed_hits / max(1.0, nq)}
     if world == 1 and not args.no_cpu:
-        # CPU baseline (the oracle port) in a child process that never touches CUDA
+        # CPU baseline (the oracle port) in a child process that never touches CUDA; it keeps the rows of one query
+        # window, which the GPU path then has to reproduce byte for byte (parity_check)
+        shm = '/dev/shm' if os.path.isdir('/dev/shm') else CACHE
+        pout = os.path.join(shm, 'swiftortho_b200_parity_%d.sc' % os.getpid())
         out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2',
-                              '--warmup', '1', '--n', str(n), '--taxa', str(taxa), '--cpu-queries', str(args.cpu_queries)],
+                              '--warmup', '1', '--n', str(n), '--taxa', str(taxa), '--cpu-queries', str(args.cpu_queries),
+                              '--config', str(args.config), '--parity-out', pout],
                              stdout=subprocess.PIPE, text=True, cwd=ROOT)
         try:
             ref = json.loads(out.stdout.strip().splitlines()[-1])
             line['cpu_baseline'] = ref['cpu_baseline']
             line['cpu_baseline']['gcups'] = ref.get('gcups_cpu')
+            line['parity_check'] = parity_check(S, F, so, ref.get('parity_window'), pout)
         except Exception as e:  # noqa: BLE001
             line['cpu_baseline'] = {'error': repr(e)}
+        try:
+            os.remove(pout)
+        except OSError:
+            pass
+    if world == 1 and not args.no_full:
+        # SURVEY.md 8d metric (1): the whole job, FASTA in -> OUT written, index build and query preparation included
+        S.close()
+        shm = '/dev/shm' if os.path.isdir('/dev/shm') else CACHE
+        out_dir = os.path.join(shm, 'swiftortho_b200_full')
+        os.makedirs(out_dir, exist_ok=True)
+        r = full_job(args, 0, 1, local, fasta, lambda: None, out_dir)
+        line['full_run'] = {'proteins_per_s': r['queries'] / r['wall'], 'wall_s': r['wall'], 'queries': r['queries'],
+                            'rows': r['rows'], 'index_build_s': r['t_index'], 'table_properties': r['props'],
+                            'what': 'whole find_hit job on one GPU: FASTA parse, H2D, index build, seg + S3 order, search, '
+                                    '16-column text written (SURVEY.md 8d metric 1)'}
+    c3 = []
+    for k in (1, 2, 4, 8):
+        pth = os.path.join(ROOT, 'profiles', 'bench_r02_config3_n%d.json' % k)
+        if os.path.exists(pth):
+            try:
+                d = json.loads(open(pth).read().strip().splitlines()[-1])
+                c3.append({'n_gpus': d['n_gpus'], 'proteins_per_s': d['value'], 'wall_s': d['wall_s'], 'source': 'profiles/' + os.path.basename(pth)})
+            except Exception:  # noqa: BLE001
+                pass
+    if c3:
+        line['config3'] = {'scaling': 'strong', 'note': 'committed measurements of `bench.py --config 3 --mode full` (1 M proteins, 20 '
+                           'chunks, queries split by residues over the ranks, index build included); not re-run here', 'runs': c3}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -404,7 +629,16 @@ def main():
     ap.add_argument('--cpu-queries', type=int, default=4, help='queries per CPU worker per step (bounded sample)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--align-pairs', type=int, default=300000, help='pairs of the alignment-only GCUPS measurement')
+    ap.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS), help='BASELINE.json config (default 2 = headline)')
+    ap.add_argument('--mode', default='steps', choices=['steps', 'full'],
+                    help='steps: timed query blocks against the resident index (default); full: one whole job, strong scaling')
+    ap.add_argument('--full-block', type=int, default=8192, help='queries per so_search call of the whole-job run')
+    ap.add_argument('--full-check-rows', type=int, default=2000000)
+    ap.add_argument('--no-full', action='store_true', help='skip the whole-job record of the default run')
+    ap.add_argument('--parity-out', default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.n == 100000 and args.taxa == 20 and args.config != 2:
+        args.n, args.taxa = CONFIGS[args.config][0], CONFIGS[args.config][1]
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

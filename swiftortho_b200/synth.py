@@ -106,6 +106,66 @@ def generate(n, taxa, lengths='gamma', seed=20261017, max_len=None):
     return headers, seqs
 
 
+def _taxon_copies(job):
+    """One taxon of generate_parallel: its own PCG64 stream (seed, taxon), same per-copy model as generate()."""
+    seed, t, ancestors, pars = job
+    rng = np.random.Generator(np.random.PCG64([seed, t]))
+    fam = len(ancestors)
+    rates = rng.uniform(0.05, 0.55, size=fam)
+    lc = rng.random(fam) < 0.02
+    headers, seqs = [], []
+    for f in range(fam):
+        s = _mutate(rng, ancestors[f], rates[f])
+        if lc[f]:
+            s = _low_complexity(rng, s)
+        headers.append('T%03d|g%07d_0' % (t, f))
+        seqs.append(s)
+    for c, f in enumerate(pars):
+        s = _mutate(rng, ancestors[f], rng.uniform(0.02, 0.2))
+        headers.append('T%03d|g%07d_%d' % (t, f, c + 1))
+        seqs.append(s)
+    return to_fasta_bytes(headers, seqs), len(seqs)
+
+
+def write_parallel(path, n, taxa, lengths='gamma', seed=20261017, workers=None):
+    """The same families model with one independent random stream per taxon (PCG64([seed, taxon])), so the taxa
+    are generated by a process pool: used for the 1 M-protein config 3 (the single-stream generate() needs two
+    minutes there).  Deterministic in (n, taxa, lengths, seed), independent of the worker count."""
+    import multiprocessing as mp
+    import os
+    rng = np.random.Generator(np.random.PCG64([seed, 1 << 20]))
+    fam = max(1, int(n / (taxa + 0.05)))
+    while fam * taxa > n:
+        fam -= 1
+    npar = n - fam * taxa
+    if lengths == 'gamma':
+        ln = np.clip(rng.gamma(2.0, 175.0, size=fam), 50, 2000).astype(np.int64)
+    else:
+        ln = np.clip(rng.lognormal(5.6, 0.9, size=fam), 50, 5000).astype(np.int64)
+    par_fams = rng.choice(fam, size=npar, replace=npar > fam)
+    par_taxon = rng.integers(0, taxa, size=npar)
+    par_of = {}
+    for f, t in zip(par_fams, par_taxon):
+        par_of.setdefault(int(t), []).append(int(f))
+    ancestors = [AA[rng.choice(20, size=int(l), p=RR)] for l in ln]
+    jobs = [(seed, t, ancestors, par_of.get(t, [])) for t in range(taxa)]
+    workers = workers or min(32, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1))
+    total = 0
+    with open(path, 'wb') as f:
+        if workers <= 1 or taxa <= 1:
+            for j in jobs:
+                b, k = _taxon_copies(j)
+                f.write(b)
+                total += k
+        else:
+            with mp.get_context('fork').Pool(workers) as pool:
+                for b, k in pool.imap(_taxon_copies, jobs, chunksize=1):
+                    f.write(b)
+                    total += k
+    assert total == n, (total, n)
+    return n
+
+
 def to_fasta_bytes(headers, seqs, width=60):
     out = io.BytesIO()
     for h, s in zip(headers, seqs):
@@ -122,6 +182,8 @@ def write_config(path, config_id, n=None, taxa=None, max_len=None):
     c = CONFIGS[config_id]
     n = c['n'] if n is None else n
     taxa = c['taxa'] if taxa is None else taxa
+    if config_id == 3 and max_len is None:
+        return write_parallel(path, n, taxa, c['lengths'], seed=20261017 + config_id)
     h, s = generate(n, taxa, c['lengths'], seed=20261017 + config_id, max_len=max_len)
     with open(path, 'wb') as f:
         f.write(to_fasta_bytes(h, s))
