@@ -1200,7 +1200,7 @@ __device__ __forceinline__ void ung_steps16(int &v, int &d, int &alive, int one,
 }
 #undef SO_XS
 
-enum { kXdBuf = 48, kXdBufBytes = 16 * kXdBuf * (8 + 2) };  // per-warp record buffer of k_xdrop<FAST> (16 warps per CTA)
+enum { kXdBuf = 48, kXdBufBytes = 16 * kXdBuf * (8 + 2) + 16 * 32 };  // per-warp record buffer of k_xdrop<FAST> (16 warps per CTA)
 // warp-collective: the staged records go to their queries' regions, one global atomic per query present
 __device__ __forceinline__ void xd_flush(const uint64_t *wrec, const uint16_t *wqi, int cnt, uint64_t *__restrict__ creg,
                                          size_t ccap, uint32_t *__restrict__ qcount, uint32_t *__restrict__ flags) {
@@ -1252,6 +1252,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
     uint64_t *wrec = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_tab) + kUngTabBytes) + (threadIdx.x >> 5) * kXdBuf;
     uint16_t *wqi = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(s_tab) + kUngTabBytes + (blockDim.x >> 5) * kXdBuf * 8) +
                     (threadIdx.x >> 5) * kXdBuf;
+    uint8_t *widx = reinterpret_cast<uint8_t *>(s_tab) + kUngTabBytes + (blockDim.x >> 5) * kXdBuf * 10 + (threadIdx.x >> 5) * 32;
     int wcount = 0;  // warp-uniform
     for (int k = threadIdx.x; k < kUngRows * 32 * 32; k += blockDim.x) {
         const int e = k >> 5, ct = e >> 5, cq = e & 31;
@@ -1364,50 +1365,112 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                     }
                 }
             }
-            unsigned need = __ballot_sync(0xffffffffu, !has && !fin);
-            for (int tries = 0; need != 0u && tries < (FAST ? 3 : 1); tries++, need = __ballot_sync(0xffffffffu, !has && !fin)) {
-                if (pool_next == pool_end && !exhausted) {
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(counters + 2, kBatch);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (base >= G)
-                        exhausted = true;
-                    else {
-                        pool_next = (uint32_t)base;
-                        pool_end = (uint32_t)min((unsigned long long)G, base + kBatch);
-                        // the batch's descriptors (512 x 8 B = 32 lines) are pulled into L2 ahead of their use
-                        if (pool_next + (uint32_t)lane * 16u < pool_end)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(desc + pool_next + lane * 16));
-                    }
-                }
-                if (!has && !fin) {
-                    const uint32_t mine = pool_next + __popc(need & ((1u << lane) - 1));
-                    if (mine < pool_end) {
-                        const uint2 ds = desc[mine];
-                        if (!FAST || ds.x != kDescSkipX) {
-                            gi = mine;
-                            xt = ds.x;
-                            uq = ds.y & 0xffffffu;
-                            noleft = (ds.y & kDescNoLeft) != 0;
-                            multi = (ds.y & kDescSingle) == 0;
-                            qcur = 0;  // chains only use qst differences: the first seed of a described pair counts from 0
-                            pairm = multi && (ds.y & kDescPair) != 0 && vals == nullptr;
-                            if (multi) nmulti++;
-                            if (pairm)
-                                e = (ds.y >> 27) + 1u;
-                            else if (multi) {
-                                e = FAST ? mine : gheads[mine];
-                                qcur = FAST ? (int)(ssub[e] & qmask) : (int)((uint32_t)keys[e] & qmask);
-                            }
-                            phase = 0, acc = 0, chained = false, lim = kNoLimit;
-                            has = true;
-                            setup = true;
-                            if (FAST) ngroups++;
+            if (FAST) {
+                // The pool is a range of HIT positions; 32 consecutive descriptors are fetched at a time (one coalesced
+                // load), the heads among them go to the lanes that need a group in order (head rank = need rank, the
+                // holder's lane index travels through a 32-byte shared-memory table), positions behind the last head
+                // that found a taker stay in the pool.  Skipped (non-head) entries cost nothing.
+                unsigned need = __ballot_sync(0xffffffffu, !has && !fin);
+                for (int tries = 0; need != 0u && tries < 3; tries++) {
+                    if (pool_next == pool_end && !exhausted) {
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(counters + 2, kBatch);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (base >= G)
+                            exhausted = true;
+                        else {
+                            pool_next = (uint32_t)base;
+                            pool_end = (uint32_t)min((unsigned long long)G, base + kBatch);
+                            if (pool_next + (uint32_t)lane * 16u < pool_end)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(desc + pool_next + lane * 16));
                         }
-                    } else if (exhausted)
-                        fin = true;  // otherwise the pool is refilled at the next service
+                    }
+                    const bool needer = !has && !fin;
+                    if (pool_next == pool_end) {  // nothing left anywhere
+                        if (needer && exhausted) fin = true;
+                        break;
+                    }
+                    uint2 ds = make_uint2(kDescSkipX, 0u);
+                    if (pool_next + (uint32_t)lane < pool_end) ds = desc[pool_next + lane];
+                    const bool head = ds.x != kDescSkipX;
+                    const unsigned hm = __ballot_sync(0xffffffffu, head);
+                    const int nh = __popc(hm), nn = __popc(need);
+                    if (head) widx[__popc(hm & ((1u << lane) - 1u))] = (uint8_t)lane;
+                    __syncwarp();
+                    const int nr = __popc(need & ((1u << lane) - 1u));
+                    const bool take = needer && nr < nh;
+                    const int src = take ? (int)widx[nr] : lane;
+                    const uint32_t adv = nh <= nn ? min(32u, pool_end - pool_next) : (uint32_t)widx[nn - 1] + 1u;
+                    const uint32_t dx = __shfl_sync(0xffffffffu, ds.x, src), dy = __shfl_sync(0xffffffffu, ds.y, src);
+                    __syncwarp();
+                    if (take) {
+                        gi = pool_next + (uint32_t)src;
+                        xt = dx;
+                        uq = dy & 0xffffffu;
+                        noleft = (dy & kDescNoLeft) != 0;
+                        multi = (dy & kDescSingle) == 0;
+                        qcur = 0;  // chains only use qst differences: the first seed of a described pair counts from 0
+                        pairm = multi && (dy & kDescPair) != 0;
+                        if (multi) nmulti++;
+                        if (pairm)
+                            e = (dy >> 27) + 1u;
+                        else if (multi) {
+                            e = gi;
+                            qcur = (int)(ssub[e] & qmask);
+                        }
+                        phase = 0, acc = 0, chained = false, lim = kNoLimit;
+                        has = true;
+                        setup = true;
+                        ngroups++;
+                    }
+                    pool_next += adv;
+                    need = __ballot_sync(0xffffffffu, !has && !fin);
                 }
-                pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
+            } else {
+            unsigned need = __ballot_sync(0xffffffffu, !has && !fin);
+                for (int tries = 0; need != 0u && tries < 1; tries++, need = __ballot_sync(0xffffffffu, !has && !fin)) {
+                    if (pool_next == pool_end && !exhausted) {
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(counters + 2, kBatch);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (base >= G)
+                            exhausted = true;
+                        else {
+                            pool_next = (uint32_t)base;
+                            pool_end = (uint32_t)min((unsigned long long)G, base + kBatch);
+                            // the batch's descriptors (512 x 8 B = 32 lines) are pulled into L2 ahead of their use
+                            if (pool_next + (uint32_t)lane * 16u < pool_end)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(desc + pool_next + lane * 16));
+                        }
+                    }
+                    if (!has && !fin) {
+                        const uint32_t mine = pool_next + __popc(need & ((1u << lane) - 1));
+                        if (mine < pool_end) {
+                            const uint2 ds = desc[mine];
+                            {
+                                gi = mine;
+                                xt = ds.x;
+                                uq = ds.y & 0xffffffu;
+                                noleft = (ds.y & kDescNoLeft) != 0;
+                                multi = (ds.y & kDescSingle) == 0;
+                                qcur = 0;  // chains only use qst differences: the first seed of a described pair counts from 0
+                                pairm = multi && (ds.y & kDescPair) != 0 && vals == nullptr;
+                                if (multi) nmulti++;
+                                if (pairm)
+                                    e = (ds.y >> 27) + 1u;
+                                else if (multi) {
+                                    e = gheads[mine];
+                                    qcur = (int)((uint32_t)keys[e] & qmask);
+                                }
+                                phase = 0, acc = 0, chained = false, lim = kNoLimit;
+                                has = true;
+                                setup = true;
+                            }
+                        } else if (exhausted)
+                            fin = true;  // otherwise the pool is refilled at the next service
+                    }
+                    pool_next = min(pool_end, pool_next + (uint32_t)__popc(need));
+                }
             }
             if (__all_sync(0xffffffffu, fin)) break;
             if (setup) {
@@ -1644,6 +1707,7 @@ __device__ __forceinline__ uint32_t cand_plan(CandSmem &s, uint32_t b0) {
 
 __global__ void __launch_bounds__(kCandThreads) k_cand_sort(const uint64_t *__restrict__ creg, size_t ccap,
                                                            const uint32_t *__restrict__ qcount, int nq, BlockGeom g,
+                                                           const uint64_t *__restrict__ qoff,
                                                            uint64_t *__restrict__ gbuf, uint64_t *__restrict__ bvals,
                                                            size_t bcap, uint32_t *__restrict__ bcount, int bq0,
                                                            uint32_t *__restrict__ next, uint32_t *__restrict__ flags,
@@ -1657,10 +1721,9 @@ __global__ void __launch_bounds__(kCandThreads) k_cand_sort(const uint64_t *__re
     if (s.flag) return;
     const int Lb = g.qst_bits + g.diag_bits, esh = 20 + g.diag_bits, rank_bits = g.qst_bits + g.hd_bits;
     const int sh1 = 20 + Lb + max(0, g.hd_bits - 13);  // records: bin = top 13 bits of (target + 1)
-    const int sh2 = esh + max(0, rank_bits - 13);      // words:   bin = top 13 bits of the rank
+    // words: bin = top 13 bits of the rank below the query's length (the rank starts with a query position)
     const uint32_t dmask = (1u << g.diag_bits) - 1u, hdmask = (1u << g.hd_bits) - 1u;
     uint64_t *C = gbuf + (size_t)blockIdx.x * ccap;    // this CTA's candidate words
-    constexpr int per = kCandBins / kCandThreads;
     for (;;) {
         if (tid == 0) s.q = (int)atomicAdd(next, 1u);
         __syncthreads();
@@ -1671,7 +1734,13 @@ __global__ void __launch_bounds__(kCandThreads) k_cand_sort(const uint64_t *__re
         if (n == 0) continue;
         if ((size_t)n > ccap) continue;  // region overflow: k_xdrop raised the redo flag
         const uint64_t *src = creg + (size_t)q * ccap;
-        // ---- 1 + 2: records by (target, qst, diagonal), fold per target -> candidate words in C
+        int qlb = 1;
+        {
+            const uint32_t ql = (uint32_t)(qoff[g.qb0 + q + 1] - qoff[g.qb0 + q]);
+            while (qlb < g.qst_bits && (1u << qlb) <= ql) qlb++;
+        }
+        const int sh2 = esh + max(0, qlb + g.hd_bits - 13);
+        // ---- 1 + 2: records by target bin, fold per target -> candidate words in C
         cand_histogram(s, src, n, sh1);
         if (tid == 0) s.nc = 0;
         for (uint32_t b0 = 0; b0 < (uint32_t)kCandBins;) {
@@ -1688,49 +1757,30 @@ __global__ void __launch_bounds__(kCandThreads) k_cand_sort(const uint64_t *__re
                 if (b >= b0 && b < b1) s.f[atomicAdd(&s.bin[b], 1u) - base] = e;
             }
             __syncthreads();
-            // bins of the pass, `per` consecutive ones per thread: s.bin[b] is now the END of bin b
-            uint64_t words[4];
-            uint32_t nw = 0, wbase = 0;
-            for (int pass = 0; pass < 2; pass++) {  // pass 0 counts the candidates, pass 1 writes them
-                uint32_t cnt = 0;
-                for (uint32_t b = b0 + (uint32_t)tid * per; b < min(b1, b0 + (uint32_t)(tid + 1) * per); b++) {
-                    const uint32_t lo = (b == b0 ? base : s.bin[b - 1]) - base, hi = s.bin[b] - base;
-                    if (pass == 0)
-                        for (uint32_t i = lo + 1; i < hi; i++) {  // insertion sort of the bin
-                            const uint64_t x = s.f[i];
-                            uint32_t j = i;
-                            while (j > lo && s.f[j - 1] > x) s.f[j] = s.f[j - 1], j--;
-                            s.f[j] = x;
-                        }
-                    for (uint32_t i = lo; i < hi;) {
-                        const uint64_t e0 = s.f[i];
-                        const uint32_t t = (uint32_t)(e0 >> (20 + Lb));
-                        const uint32_t first = (uint32_t)(e0 >> 20) & ((1u << Lb) - 1u);
-                        uint32_t best = (uint32_t)e0 & 0xfffffu, brk = first;
-                        uint32_t k = i + 1;
-                        for (; k < hi; k++) {
-                            const uint64_t e = s.f[k];
-                            if ((uint32_t)(e >> (20 + Lb)) != t) break;
-                            const uint32_t sc = (uint32_t)e & 0xfffffu;
-                            if (sc > best) best = sc, brk = (uint32_t)(e >> 20) & ((1u << Lb) - 1u);
-                        }
-                        i = k;
-                        if (pass == 1) {
-                            const uint64_t rank = ((uint64_t)(first >> g.diag_bits) << g.hd_bits) | (uint64_t)(hdmask - t);
-                            const uint64_t w = (rank << esh) | ((uint64_t)best << g.diag_bits) | (uint64_t)(brk & dmask);
-                            if (nw < 4)
-                                words[nw] = w;  // the usual handful goes out together below
-                            else
-                                C[wbase + nw] = w;
-                            nw++;
-                        } else
-                            cnt++;
+            // s.bin[b] is now the END of bin b.  One thread per record: the records of its target all lie in its bin
+            // (a few records); the one that comes first in dict order (smallest qst | diagonal) folds the target
+            const uint32_t m1 = s.bin[b1 - 1] - base;
+            for (uint32_t i = tid; i < m1; i += kCandThreads) {
+                const uint64_t e0 = s.f[i];
+                const uint32_t b = (uint32_t)(e0 >> sh1);
+                const uint32_t lo = (b == b0 ? base : s.bin[b - 1]) - base, hi = s.bin[b] - base;
+                const uint32_t t = (uint32_t)(e0 >> (20 + Lb));
+                const uint32_t first = (uint32_t)(e0 >> 20) & ((1u << Lb) - 1u);
+                uint32_t best = (uint32_t)e0 & 0xfffffu, brk = first;
+                bool head = true;
+                for (uint32_t k = lo; k < hi; k++) {
+                    const uint64_t e = s.f[k];
+                    if (k == i || (uint32_t)(e >> (20 + Lb)) != t) continue;
+                    const uint32_t rk = (uint32_t)(e >> 20) & ((1u << Lb) - 1u), sc = (uint32_t)e & 0xfffffu;
+                    if (rk < first) {
+                        head = false;
+                        break;
                     }
+                    if (sc > best || (sc == best && rk < brk)) best = sc, brk = rk;
                 }
-                if (pass == 0) {
-                    wbase = cnt ? atomicAdd(&s.nc, cnt) : 0u;  // order inside C is irrelevant (sorted next)
-                } else {
-                    for (uint32_t k = 0; k < min(nw, 4u); k++) C[wbase + k] = words[k];
+                if (head) {
+                    const uint64_t rank = ((uint64_t)(first >> g.diag_bits) << g.hd_bits) | (uint64_t)(hdmask - t);
+                    C[atomicAdd(&s.nc, 1u)] = (rank << esh) | ((uint64_t)best << g.diag_bits) | (uint64_t)(brk & dmask);
                 }
             }
             __syncthreads();
@@ -2419,7 +2469,7 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
                                                                 qoff2[1], (uint32_t)Lq64, nullptr, nullptr, d_ctl, 1, d_cellid,
                                                                 g.diag_bits, d_creg, ccap, d_qcount, d_flags);
             stamp();
-            k_cand_sort<<<sgrid, kCandThreads, sizeof(CandSmem), st>>>(d_creg, ccap, d_qcount, nq, g, (uint64_t *)scratch[SC_GBUF].p,
+            k_cand_sort<<<sgrid, kCandThreads, sizeof(CandSmem), st>>>(d_creg, ccap, d_qcount, nq, g, c->d_qoff, (uint64_t *)scratch[SC_GBUF].p,
                                                                       bs.vals.p, bs.capq, bs.count.p, (int)(sb.s0 - b0), d_lcount + 3,
                                                                       d_flags, d_ctl);
             stamp();
