@@ -437,7 +437,7 @@ def run_ours(args, rank, world, local):
     # ---- kernel-timing pass: the same steps with ONE production lane, so the CUDA-event stage times
     #      inside so_search are not inflated by the second lane's kernels sharing the GPU.  The roofline
     #      figures (kernel durations) come from this pass; `value` above is the two-lane pipeline.
-    S.set_lanes(1)
+    S.set_lanes(0)   # one lane, alignment rounds serialised with candidate production
     S.search(*block_of(args.warmup + args.steps))
     S.stats(reset=True)
     ksteps = max(1, min(2, args.steps))
@@ -445,8 +445,9 @@ def run_ours(args, rank, world, local):
         S.search(*block_of(args.warmup + s))
     st = dict(st)
     stk = S.stats(reset=True)
+    gcups_pipe = stk['dp_cells'] / (stk['ms_dp'] * 1e-3) / 1e9 if stk['ms_dp'] > 0 else 0.0
     S.set_lanes(2)
-    for k in ('ms_ungap', 'ms_ungap_kernel', 'ms_sort', 'ms_seed', 'ms_select'):
+    for k in ('ms_ungap', 'ms_ungap_kernel', 'ms_sort', 'ms_seed', 'ms_select', 'ms_dp', 'ms_traceback'):
         st[k] = stk[k] * args.steps / ksteps      # same blocks as the first `ksteps` timed steps
 
     # ---- end-to-end arm: host buffers -> public API -> text rows, every step
@@ -505,14 +506,14 @@ def run_ours(args, rank, world, local):
             st['ms_seed'], st['ms_select'], st['ms_traceback'], st['ms_host'], float(st['seed_hits']),
             float(st['kernel_launches']), float(st['ungap_steps']), float(st['alignments']),
             float(st2['h2d_bytes']), float(st2['d2h_bytes']), gcups_alone, gcups_alone_tb,
-            st['ms_ungap_kernel'], float(st['groups']), float(st['multi_groups'])]
+            st['ms_ungap_kernel'], float(st['groups']), float(st['multi_groups']), float(st['alignments_used']), gcups_pipe]
     vals = reduce_over_ranks(vals, dist, 'cuda' if dist is not None else None)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     (dt, dt2, nq, e2e_q, cells, ms_dp, ms_ungap, ms_sort, ms_seed, ms_select, ms_tb, ms_host, seed_hits, launches,
-     ungap_steps, alignments, h2d, d2h, gcups_alone, gcups_alone_tb, ms_xdrop, groups, multi_groups) = vals
+     ungap_steps, alignments, h2d, d2h, gcups_alone, gcups_alone_tb, ms_xdrop, groups, multi_groups, aln_used, gcups_pipe) = vals
     value = nq / dt
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(
         os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
@@ -549,14 +550,16 @@ def run_ours(args, rank, world, local):
            'algorithmic_bytes': '32 B per seed hit x %.3g hits per step' % (seed_hits / max(world, 1) / args.steps),
            'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback B200_PROFILING.md'}
     hbm['frac'] = hbm['achieved'] / hbm['peak']
-    gcups = cells / max(world, 1) / (ms_dp * 1e-3) / 1e9 if ms_dp > 0 else 0.0
+    gcups = gcups_pipe / max(world, 1)
     dp_roof = {'kernel': 'k_banded_dp', 'bound': 'int32', 'achieved': gcups_alone / max(world, 1), 'unit': 'GCUPS per GPU',
                'peak': int_peak['gops_measured'] / 14.0, 'frac': gcups_alone / max(world, 1) / (int_peak['gops_measured'] / 14.0),
                'with_traceback': gcups_alone_tb / max(world, 1), 'in_pipeline': gcups,
+               'in_pipeline_frac': gcups / (int_peak['gops_measured'] / 14.0),
                'cells_per_step': cells / args.steps / max(world, 1),
                'note': '14 INT ops per cell (SURVEY.md 8d); achieved = %d config-shaped pairs in one so_align_batch, '
-                       'k_banded_dp time by CUDA events; in_pipeline = same kernel inside the search steps (small '
-                       'launches sharing the GPU with the seeding kernels)' % args.align_pairs}
+                       'k_banded_dp time by CUDA events; in_pipeline = the same kernel on the alignment rounds of the search steps, '
+                       'timed in the measurement mode (one lane, rounds serialised with candidate production, so the '
+                       'events see the kernel alone)' % args.align_pairs}
     line = {'metric': metric_of(args), 'value': value, 'unit': 'proteins/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic', 'config': workload_config(args, B),
@@ -568,6 +571,7 @@ def run_ours(args, rank, world, local):
                                                                       select=ms_select, dp=ms_dp, traceback=ms_tb,
                                                                       host=ms_host).items()},
             'index_build_ms': index_ms, 'index': info, 'alignments_per_query': alignments / max(1.0, nq),
+            'alignments_wasted_frac': 1.0 - aln_used / max(1.0, alignments),
             'seed_hits_per_query': seed_hits / max(1.0, nq)}
     if world == 1 and not args.no_cpu:
         # CPU baseline (the oracle port) in a child process that never touches CUDA; it keeps the rows of one query

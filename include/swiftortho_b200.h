@@ -190,10 +190,12 @@ typedef struct so_stats {
     double ms_ungap_kernel;  /* X-drop kernels alone (k_single_ungap + k_group_ungap), inside ms_ungap */
     int64_t multi_groups;    /* diagonal groups holding more than one seed (chained path)            */
     int64_t redo_blocks;     /* query blocks the sync-free path handed back to the general path      */
+    int64_t alignments_used; /* alignments the sequential stop rule consumed (alignments - this = wasted) */
 } so_stats;
 int so_stats_get(const so_ctx *c, so_stats *s);
 /* tuning hooks (no reference counterpart): queries per seeding sub-block (0 = adaptive), and the number
- * of candidate-production lanes (streams) so_search overlaps (1 or 2, default 2) */
+ * of candidate-production lanes (streams) so_search overlaps (1 or 2, default 2; 0 = one lane and alignment rounds
+ * serialised with candidate production: measurement mode for per-kernel CUDA-event times) */
 int so_set_sub_block(so_ctx *c, int64_t n);
 int so_set_lanes(so_ctx *c, int n);
 int so_stats_reset(so_ctx *c);

@@ -54,7 +54,7 @@ class so_stats(C.Structure):
                [(n, C.c_double) for n in ('ms_seed', 'ms_sort', 'ms_ungap', 'ms_select', 'ms_align', 'ms_dp',
                                           'ms_traceback', 'ms_host', 'ms_total')] + \
                [('h2d_bytes', C.c_int64), ('d2h_bytes', C.c_int64), ('ms_ungap_kernel', C.c_double),
-                ('multi_groups', C.c_int64), ('redo_blocks', C.c_int64)]
+                ('multi_groups', C.c_int64), ('redo_blocks', C.c_int64), ('alignments_used', C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

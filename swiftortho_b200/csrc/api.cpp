@@ -89,6 +89,7 @@ struct QueryState {
     i64 qord = 0;                 // global query ordinal
     i64 limit = 0;                // min(vmax, len(hits))
     i64 next = 0;                 // next candidate (in sorted order) to align
+    i64 lead = 0;                 // candidates up to the last one whose UNGAPPED score already passes the e-value
     double mmiss = 0;
     i64 unmch = 0, bv = 0;
     bool done = false;
@@ -98,7 +99,12 @@ struct QueryState {
     i64 req_first = 0, req_count = 0;  // candidates covered
 };
 
-static const i64 kRound = 64;
+// Alignment rounds.  The stop rule (fsearch.py:3103) is sequential per query: it ends after ceil(mmiss) consecutive
+// misses.  A round therefore submits, per unfinished query, exactly the candidates the rule is certain to reach:
+// first round = the candidates up to the last one whose ungapped diagonal score alone passes the e-value (they are
+// hits unless the banded alignment scores lower) + ceil(mmiss); later rounds = ceil(mmiss - unmch).  Alignments the
+// reference would not have computed only arise when the `bv >= v + mmiss` half of the rule fires inside a round.
+static const i64 kRoundMax = 4096;
 
 }  // namespace so
 
@@ -484,7 +490,7 @@ int so_set_sub_block(so_ctx *c, int64_t n) {
 // test / tuning hook: number of candidate-production lanes used by so_search (1 or 2; default 2).  bench.py
 // uses 1 to time the kernels of a step without a second stream sharing the GPU.
 int so_set_lanes(so_ctx *c, int n) {
-    if (!c || n < 1 || n > 2) return SO_EINVAL;
+    if (!c || n < 0 || n > 2) return SO_EINVAL;
     c->n_lanes = n;
     return SO_OK;
 }
@@ -533,6 +539,10 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     std::map<int, Job> jobs;  // by block number
     int next_blk = 0;         // next block the worker consumes
     const int nprod = c->n_lanes >= 2 ? 2 : 1;
+    // n_lanes == 0: measurement mode: one lane, and candidate production and alignment rounds never share the GPU, so
+    // the CUDA-event durations of the kernels are not inflated by kernels of the other stage
+    const bool serial = c->n_lanes == 0;
+    std::mutex gpu_mu;
     int producers_left = nprod;
     bool abort_all = false;
     bool producer_done = false, slot_busy[kSlots] = {false, false, false, false};
@@ -544,7 +554,8 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     // queries whose candidates are selected but not aligned yet: alignment rounds run over several blocks
     // at once so one launch carries enough alignments to fill the GPU
     std::vector<QueryState> pending;
-    const size_t kAlignBatch = 2048;
+    size_t kAlignBatch = 4096;
+    if (const char *e = getenv("SO_ALIGN_BATCH")) kAlignBatch = (size_t)std::max(1, atoi(e));  // tuning hook
 
     const i64 selcap = std::max<i64>(1, std::min<i64>(vmax, capq));
     auto order_block = [&](i64 b0, i64 b1, int slot, const std::function<void()> &release_slot) -> int {
@@ -566,7 +577,13 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             s.mmiss = mm;
             s.done = s.limit == 0;
             s.sel.resize((size_t)s.limit);
-            for (i64 i = 0; i < s.limit; i++) s.sel[(size_t)i] = so::unpack_cand(hs[(size_t)k * (size_t)selcap + (size_t)i]);
+            const i64 li = (i64)(c->q_off[(size_t)s.qord + 1] - c->q_off[(size_t)s.qord]);
+            for (i64 i = 0; i < s.limit; i++) {
+                const so_cand cd = so::unpack_cand(hs[(size_t)k * (size_t)selcap + (size_t)i]);
+                s.sel[(size_t)i] = cd;
+                const i64 lj = (i64)(c->t_off[(size_t)cd.target + 1] - c->t_off[(size_t)cd.target]);
+                if (so::bit2e(D, li, lj, so::score2bit((i64)cd.score)) <= P.expect) s.lead = i + 1;
+            }
         });
         wstats.ms_host += th.ms();
         c->prof.order_ms += th.ms();
@@ -576,12 +593,14 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     };
 
     auto align_pending = [&]() -> int {
+        std::unique_lock<std::mutex> gl(gpu_mu, std::defer_lock);
+        if (serial) gl.lock();
         std::vector<QueryState> qs;
         qs.swap(pending);
         const i64 nq = (i64)qs.size();
         if (nq == 0) return SO_OK;
         // alignment rounds: the stop rule (fsearch.py:3103) is sequential per query, so each round
-        // aligns the next kRound candidates of every unfinished query and the host replays the rule
+        // aligns the next candidates of every unfinished query (see kRoundMax) and the host replays the rule
         Timer trd;
         std::vector<so_pair> pairs;
         std::vector<so_aln> alns;
@@ -600,7 +619,9 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 if (s.done) continue;
                 const i64 qi_ord = s.qord;
                 const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
-                const i64 hi = std::min<i64>(s.limit, s.next + kRound);
+                const i64 left = (i64)std::ceil(s.mmiss - (double)s.unmch);
+                const i64 want = s.next == 0 ? s.lead + (i64)std::ceil(s.mmiss) : std::max<i64>(left, 1);
+                const i64 hi = std::min<i64>(s.limit, s.next + std::min<i64>(want, kRoundMax));
                 for (i64 h = s.next; h < hi; h++) {
                     const int ci = (int)h;
                     const so_cand &cd = s.sel[(size_t)ci];
@@ -645,7 +666,8 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 const i64 qi_ord = s.qord;
                 const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
                 for (; r < reqs.size() && reqs[r].q == k; r++) {
-                    if (s.done) continue;
+                    if (s.done) continue;  // computed but never reached by the sequential rule (counted as wasted)
+                    wstats.alignments_used += reqs[r].count;
                     const Req &rq = reqs[r];
                     const so_cand &cd = s.sel[(size_t)rq.cand];
                     const i64 lj = (i64)(c->t_off[(size_t)cd.target + 1] - c->t_off[(size_t)cd.target]);
@@ -772,6 +794,8 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             // PASS 1 (fsearch.py:2990-3016): candidates of every chunk, appended on the device to the block's
             // per-query lists in chunk order; then the device selection and the copy of the selected candidates
             Timer tc;
+            std::unique_lock<std::mutex> gl(gpu_mu, std::defer_lock);
+            if (serial) gl.lock();
             cudaStream_t st = pid ? c->stream1 : c->stream;
             so::BlockStore &bs = c->bstore[pid];
             const i64 nqb = b1 - b0;
@@ -866,6 +890,7 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     worker.join();
     c->stats.ms_host += wstats.ms_host;
     c->stats.queries += wstats.queries;
+    c->stats.alignments_used += wstats.alignments_used;
     so::merge_align_stats(c);
     so::merge_lane_stats(c);
     if (prod_rc != SO_OK) {

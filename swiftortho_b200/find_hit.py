@@ -135,6 +135,7 @@ def search_fanout(qry, ref, outfile, start, end, ngpu, ndev, tmpdir, params):
     The reference always removes OUT first (`rm -f`, :126) and `cat`s the parts in ascending start order; `-O`
     only reaches the part files."""
     (exp, bv, rstart, rend, miss, thr, step, flt, ht, chk, ssd, nr) = params
+    os.makedirs(tmpdir, exist_ok=True)
     Q = Fasta(qry)
     N = len(Q)
     Start = 0 if start < 0 else start
