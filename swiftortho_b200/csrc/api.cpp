@@ -90,6 +90,7 @@ struct QueryState {
     i64 limit = 0;                // min(vmax, len(hits))
     i64 next = 0;                 // next candidate (in sorted order) to align
     i64 lead = 0;                 // candidates up to the last one whose UNGAPPED score already passes the e-value
+    i64 last_hits = 0;            // candidates of the last round that gave a row
     double mmiss = 0;
     i64 unmch = 0, bv = 0;
     bool done = false;
@@ -554,8 +555,6 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     // queries whose candidates are selected but not aligned yet: alignment rounds run over several blocks
     // at once so one launch carries enough alignments to fill the GPU
     std::vector<QueryState> pending;
-    size_t kAlignBatch = 4096;
-    if (const char *e = getenv("SO_ALIGN_BATCH")) kAlignBatch = (size_t)std::max(1, atoi(e));  // tuning hook
 
     const i64 selcap = std::max<i64>(1, std::min<i64>(vmax, capq));
     auto order_block = [&](i64 b0, i64 b1, int slot, const std::function<void()> &release_slot) -> int {
@@ -592,125 +591,29 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
         return SO_OK;
     };
 
-    auto align_pending = [&]() -> int {
-        std::unique_lock<std::mutex> gl(gpu_mu, std::defer_lock);
-        if (serial) gl.lock();
-        std::vector<QueryState> qs;
-        qs.swap(pending);
-        const i64 nq = (i64)qs.size();
-        if (nq == 0) return SO_OK;
-        // alignment rounds: the stop rule (fsearch.py:3103) is sequential per query, so each round
-        // aligns the next candidates of every unfinished query (see kRoundMax) and the host replays the rule
-        Timer trd;
-        std::vector<so_pair> pairs;
-        std::vector<so_aln> alns;
-        struct Req {
-            int q;        // block-local query
-            int first;    // first pair of this candidate
-            int count;    // pairs (tiles) of this candidate
-            int cand;     // index into cands
-        };
-        std::vector<Req> reqs;
-        for (;;) {
-            pairs.clear();
-            reqs.clear();
-            for (i64 k = 0; k < nq; k++) {
-                QueryState &s = qs[(size_t)k];
-                if (s.done) continue;
-                const i64 qi_ord = s.qord;
-                const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
-                const i64 left = (i64)std::ceil(s.mmiss - (double)s.unmch);
-                const i64 want = s.next == 0 ? s.lead + (i64)std::ceil(s.mmiss) : std::max<i64>(left, 1);
-                const i64 hi = std::min<i64>(s.limit, s.next + std::min<i64>(want, kRoundMax));
-                for (i64 h = s.next; h < hi; h++) {
-                    const int ci = (int)h;
-                    const so_cand &cd = s.sel[(size_t)ci];
-                    const i64 lj = (i64)(c->t_off[(size_t)cd.target + 1] - c->t_off[(size_t)cd.target]);
-                    Req r;
-                    r.q = (int)k, r.first = (int)pairs.size(), r.cand = ci, r.count = 0;
-                    if (li < 4096 && lj < 4096) {
-                        so_pair p;
-                        p.query = qi_ord, p.target = cd.target, p.q_off = 0, p.q_len = (int32_t)li, p.t_off = 0;
-                        p.t_len = (int32_t)lj, p.qst = (int32_t)cd.qi, p.sst = (int32_t)cd.qj;
-                        pairs.push_back(p);
-                        r.count = 1;
-                    } else {
-                        // kswat_st_long (fsearch.py:1480-1498): 4096-tiles down the diagonal; a tile
-                        // whose target slice is empty is skipped (undefined in the reference)
-                        i64 j = cd.qj;
-                        for (i64 i = cd.qi; i < li; i += 4096, j += 4096) {
-                            if (j >= lj) continue;
-                            so_pair p;
-                            p.query = qi_ord, p.target = cd.target, p.q_off = (int32_t)i;
-                            p.q_len = (int32_t)std::min<i64>(4096, li - i), p.t_off = (int32_t)j;
-                            p.t_len = (int32_t)std::min<i64>(4096, lj - j), p.qst = 0, p.sst = 0;
-                            pairs.push_back(p);
-                            r.count++;
-                        }
-                    }
-                    reqs.push_back(r);
-                }
-            }
-            if (reqs.empty()) break;
-            alns.resize(pairs.size());
-            Timer ta;
-            int rc = so::align_pairs(c, pairs.data(), (i64)pairs.size(), alns.data());
-            if (rc != SO_OK) return rc;
-            c->prof.align_ms += ta.ms();
-            Timer tr;
-            // replay (fsearch.py:3062-3106)
-            size_t r = 0;
-            while (r < reqs.size()) {
-                const int k = reqs[r].q;
-                QueryState &s = qs[(size_t)k];
-                const i64 qi_ord = s.qord;
-                const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
-                for (; r < reqs.size() && reqs[r].q == k; r++) {
-                    if (s.done) continue;  // computed but never reached by the sequential rule (counted as wasted)
-                    wstats.alignments_used += reqs[r].count;
-                    const Req &rq = reqs[r];
-                    const so_cand &cd = s.sel[(size_t)rq.cand];
-                    const i64 lj = (i64)(c->t_off[(size_t)cd.target + 1] - c->t_off[(size_t)cd.target]);
-                    const bool longpath = !(li < 4096 && lj < 4096);
-                    bool any = false;
-                    for (int t = 0; t < rq.count; t++) {
-                        const so_aln &a = alns[(size_t)(rq.first + t)];
-                        const so_pair &p = pairs[(size_t)(rq.first + t)];
-                        const i64 bit = so::score2bit(a.raw_score);
-                        const double e = so::bit2e(D, li, lj, bit);
-                        if (e <= P.expect) {
-                            so_hit hrow;
-                            memset(&hrow, 0, sizeof hrow);
-                            hrow.query = qi_ord, hrow.target = cd.target, hrow.qlen = (int32_t)li, hrow.tlen = (int32_t)lj;
-                            hrow.aln_len = a.aln_len, hrow.mismatch = a.mismatch, hrow.gaps = a.gaps;
-                            hrow.qst = a.qst + p.q_off + 1, hrow.qed = a.qed + p.q_off;
-                            hrow.sst = a.sst + p.t_off + 1, hrow.sed = a.sed + p.t_off;
-                            hrow.raw_score = a.raw_score, hrow.n_ident = a.n_ident, hrow.bit = bit;
-                            hrow.identity = a.aln_len ? (double)a.n_ident * (100. / (double)a.aln_len) : NAN;
-                            hrow.evalue = e;
-                            s.rows.push_back(hrow);
-                            any = true;
-                            s.bv++;
-                        }
-                    }
-                    (void)longpath;
-                    if (any)
-                        s.unmch = 0;
-                    else
-                        s.unmch++;
-                    s.next++;
-                    if ((double)s.unmch >= s.mmiss || (double)s.bv >= (double)P.v + s.mmiss) s.done = true;
-                }
-                if (s.next >= s.limit) s.done = true;
-            }
-            wstats.ms_host += tr.ms();
-            c->prof.replay_ms += tr.ms();
-        }
-        c->prof.rounds_ms += trd.ms();
-        // final per-query order: qsort_u by -bit, first v rows (fsearch.py:3108-3110)
+    // ---- rolling alignment pool.  `pending` holds the queries whose candidates are selected, in query order; the
+    // worker issues ONE alignment launch per iteration that carries the next round of EVERY unfinished query (first
+    // rounds of newly arrived blocks together with later rounds of the stragglers), replays the sequential stop rule
+    // on the host and retires finished queries from the front in query order.
+    std::deque<QueryState> pool;
+    struct Req {
+        int q;      // index into the pool
+        int first;  // first pair of this candidate
+        int count;  // pairs (tiles) of this candidate
+        int cand;   // index into sel
+    };
+    std::vector<so_pair> pairs;
+    std::vector<so_aln> alns;
+    std::vector<Req> reqs;
+
+    auto finalize_front = [&]() {
+        // final per-query order: qsort_u by -bit, first v rows (fsearch.py:3108-3110); queries leave in query order
         Timer tf;
-        so::parallel_for(nq, [&](i64 k) {
-            QueryState &s = qs[(size_t)k];
+        size_t nfin = 0;
+        while (nfin < pool.size() && pool[nfin].done) nfin++;
+        if (nfin == 0) return;
+        so::parallel_for((i64)nfin, [&](i64 k) {
+            QueryState &s = pool[(size_t)k];
             const i64 n = (i64)s.rows.size();
             if (n == 0) return;
             std::vector<uint64_t> v((size_t)n);
@@ -723,55 +626,185 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             for (i64 i = 0; i < lim; i++) sorted.push_back(s.rows[(size_t)(uint32_t)v[(size_t)i]]);
             s.rows.swap(sorted);
         });
-        for (i64 k = 0; k < nq; k++) {
-            all_rows.insert(all_rows.end(), qs[(size_t)k].rows.begin(), qs[(size_t)k].rows.end());
+        for (size_t k = 0; k < nfin; k++) {
+            all_rows.insert(all_rows.end(), pool[k].rows.begin(), pool[k].rows.end());
             wstats.queries++;
         }
+        pool.erase(pool.begin(), pool.begin() + (std::ptrdiff_t)nfin);
         wstats.ms_host += tf.ms();
         c->prof.final_ms += tf.ms();
+    };
+
+    // one round over every unfinished query of the pool; returns SO_OK (and does nothing when all are finished)
+    auto align_round = [&]() -> int {
+        std::unique_lock<std::mutex> gl(gpu_mu, std::defer_lock);
+        if (serial) gl.lock();
+        Timer trd;
+        pairs.clear();
+        reqs.clear();
+        const i64 nq = (i64)pool.size();
+        for (i64 k = 0; k < nq; k++) {
+            QueryState &s = pool[(size_t)k];
+            if (s.done) continue;
+            const i64 qi_ord = s.qord;
+            const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
+            // candidates the stop rule is certain to reach (see kRoundMax); a query that is still finding hits also
+            // gets as many more as it found in its last round, so long hit lists need O(log) rounds
+            const i64 left = std::max<i64>((i64)std::ceil(s.mmiss - (double)s.unmch), 1);
+            const i64 want = s.next == 0 ? s.lead + (i64)std::ceil(s.mmiss) : left + s.last_hits;
+            const i64 hi = std::min<i64>(s.limit, s.next + std::min<i64>(want, kRoundMax));
+            s.last_hits = 0;
+            for (i64 h = s.next; h < hi; h++) {
+                const int ci = (int)h;
+                const so_cand &cd = s.sel[(size_t)ci];
+                const i64 lj = (i64)(c->t_off[(size_t)cd.target + 1] - c->t_off[(size_t)cd.target]);
+                Req r;
+                r.q = (int)k, r.first = (int)pairs.size(), r.cand = ci, r.count = 0;
+                if (li < 4096 && lj < 4096) {
+                    so_pair p;
+                    p.query = qi_ord, p.target = cd.target, p.q_off = 0, p.q_len = (int32_t)li, p.t_off = 0;
+                    p.t_len = (int32_t)lj, p.qst = (int32_t)cd.qi, p.sst = (int32_t)cd.qj;
+                    pairs.push_back(p);
+                    r.count = 1;
+                } else {
+                    // kswat_st_long (fsearch.py:1480-1498): 4096-tiles down the diagonal; a tile
+                    // whose target slice is empty is skipped (undefined in the reference)
+                    i64 j = cd.qj;
+                    for (i64 i = cd.qi; i < li; i += 4096, j += 4096) {
+                        if (j >= lj) continue;
+                        so_pair p;
+                        p.query = qi_ord, p.target = cd.target, p.q_off = (int32_t)i;
+                        p.q_len = (int32_t)std::min<i64>(4096, li - i), p.t_off = (int32_t)j;
+                        p.t_len = (int32_t)std::min<i64>(4096, lj - j), p.qst = 0, p.sst = 0;
+                        pairs.push_back(p);
+                        r.count++;
+                    }
+                }
+                reqs.push_back(r);
+            }
+        }
+        if (reqs.empty()) return SO_OK;
+        alns.resize(pairs.size());
+        Timer ta;
+        int rc = so::align_pairs(c, pairs.data(), (i64)pairs.size(), alns.data());
+        if (rc != SO_OK) return rc;
+        c->prof.align_ms += ta.ms();
+        Timer tr;
+        // replay (fsearch.py:3062-3106)
+        size_t r = 0;
+        while (r < reqs.size()) {
+            const int k = reqs[r].q;
+            QueryState &s = pool[(size_t)k];
+            const i64 qi_ord = s.qord;
+            const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
+            for (; r < reqs.size() && reqs[r].q == k; r++) {
+                if (s.done) continue;  // computed but never reached by the sequential rule (counted as wasted)
+                wstats.alignments_used += reqs[r].count;
+                const Req &rq = reqs[r];
+                const so_cand &cd = s.sel[(size_t)rq.cand];
+                const i64 lj = (i64)(c->t_off[(size_t)cd.target + 1] - c->t_off[(size_t)cd.target]);
+                bool any = false;
+                for (int t = 0; t < rq.count; t++) {
+                    const so_aln &a = alns[(size_t)(rq.first + t)];
+                    const so_pair &p = pairs[(size_t)(rq.first + t)];
+                    const i64 bit = so::score2bit(a.raw_score);
+                    const double e = so::bit2e(D, li, lj, bit);
+                    if (e <= P.expect) {
+                        so_hit hrow;
+                        memset(&hrow, 0, sizeof hrow);
+                        hrow.query = qi_ord, hrow.target = cd.target, hrow.qlen = (int32_t)li, hrow.tlen = (int32_t)lj;
+                        hrow.aln_len = a.aln_len, hrow.mismatch = a.mismatch, hrow.gaps = a.gaps;
+                        hrow.qst = a.qst + p.q_off + 1, hrow.qed = a.qed + p.q_off;
+                        hrow.sst = a.sst + p.t_off + 1, hrow.sed = a.sed + p.t_off;
+                        hrow.raw_score = a.raw_score, hrow.n_ident = a.n_ident, hrow.bit = bit;
+                        hrow.identity = a.aln_len ? (double)a.n_ident * (100. / (double)a.aln_len) : NAN;
+                        hrow.evalue = e;
+                        s.rows.push_back(hrow);
+                        any = true;
+                        s.bv++;
+                    }
+                }
+                if (any)
+                    s.unmch = 0, s.last_hits++;
+                else
+                    s.unmch++;
+                s.next++;
+                if ((double)s.unmch >= s.mmiss || (double)s.bv >= (double)P.v + s.mmiss) s.done = true;
+            }
+            if (s.next >= s.limit) s.done = true;
+        }
+        wstats.ms_host += tr.ms();
+        c->prof.replay_ms += tr.ms();
+        c->prof.rounds_ms += trd.ms();
         return SO_OK;
     };
 
     std::thread worker([&]() {
         cudaSetDevice(c->device);
         for (;;) {
-            Job j;
+            // absorb every block that is ready (in block order)
+            for (;;) {
+                Job j;
+                bool have = false;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    bool active = false;
+                    for (const auto &q : pool)
+                        if (!q.done) {
+                            active = true;
+                            break;
+                        }
+                    if (!active) cv.wait(lk, [&] { return jobs.count(next_blk) || producer_done; });
+                    if (jobs.count(next_blk)) {
+                        j = jobs[next_blk];
+                        jobs.erase(next_blk);
+                        next_blk++;
+                        have = true;
+                    }
+                }
+                if (!have) break;
+                bool released = false;
+                auto release = [&]() {
+                    if (released) return;
+                    released = true;
+                    std::lock_guard<std::mutex> lk(mu);
+                    slot_busy[j.slot] = false;
+                    cv.notify_all();
+                };
+                if (worker_rc == SO_OK) {
+                    int rc = order_block(j.b0, j.b1, j.slot, release);
+                    if (rc != SO_OK) {
+                        std::lock_guard<std::mutex> lk(mu);
+                        worker_rc = rc;
+                        worker_err = so::get_error();
+                        cv.notify_all();
+                    }
+                }
+                release();
+            }
+            for (auto &q : pending) pool.push_back(std::move(q));
+            pending.clear();
+            bool active = false;
+            for (const auto &q : pool)
+                if (!q.done) {
+                    active = true;
+                    break;
+                }
+            if (active && worker_rc == SO_OK) {
+                int rc = align_round();
+                if (rc != SO_OK) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    worker_rc = rc;
+                    worker_err = so::get_error();
+                    cv.notify_all();
+                }
+            }
+            if (worker_rc != SO_OK)
+                for (auto &q : pool) q.done = true;  // drain: nothing more is aligned after an error
+            finalize_front();
             {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return jobs.count(next_blk) || producer_done; });
-                if (!jobs.count(next_blk)) break;
-                j = jobs[next_blk];
-                jobs.erase(next_blk);
-                next_blk++;
-            }
-            bool released = false;
-            auto release = [&]() {
-                if (released) return;
-                released = true;
                 std::lock_guard<std::mutex> lk(mu);
-                slot_busy[j.slot] = false;
-                cv.notify_all();
-            };
-            int rc = worker_rc == SO_OK ? order_block(j.b0, j.b1, j.slot, release) : SO_OK;
-            bool last;
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                last = jobs.empty() && producer_done;  // (a producer still running re-checks with the next block)
-            }
-            if (rc == SO_OK && worker_rc == SO_OK && (pending.size() >= kAlignBatch || last)) rc = align_pending();
-            if (rc != SO_OK && worker_rc == SO_OK) {
-                std::lock_guard<std::mutex> lk(mu);
-                worker_rc = rc;
-                worker_err = so::get_error();
-                cv.notify_all();
-            }
-            release();
-        }
-        if (worker_rc == SO_OK && !pending.empty()) {
-            int rc = align_pending();
-            if (rc != SO_OK) {
-                worker_rc = rc;
-                worker_err = so::get_error();
+                if (pool.empty() && producer_done && !jobs.count(next_blk)) break;
             }
         }
     });

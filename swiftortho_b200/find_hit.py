@@ -238,7 +238,8 @@ def search_split_reference(qry, ref, outfile, start, end, ngpu, ndev, tmpdir, pa
     if rank == 0:
         # `*.sc` in the reference's command expands in lexicographic order
         merge_part_tables(sorted(scs), params[1], outfile)
-        shutil.rmtree(ref_dir, ignore_errors=True)
+        if not os.environ.get('SO_KEEP_PARTS'):                        # debugging aid
+            shutil.rmtree(ref_dir, ignore_errors=True)
 
 
 def _run_id():

@@ -9,7 +9,7 @@
 
     python tests/golden/make_split_golden.py        # needs /root/reference (this container only)
 
-Output: tests/golden/synth60_split.sc (reference FASTA = tests/golden/synth60.fsa, SO_MAX_CHR = 4000, -v 7).
+Output: tests/golden/synth60_split.sc (reference FASTA = tests/golden/synth60.fsa, SO_MAX_CHR = 4000, -v 3).
 """
 import os
 import shutil
@@ -25,7 +25,7 @@ sys.setrecursionlimit(100000)
 import run_reference  # noqa: E402
 
 MAX_CHR = 4000
-BV = '7'
+BV = '3'
 AA9 = 'AST,CFILMVY,DN,EQ,G,H,KR,P,W'
 
 
@@ -43,6 +43,7 @@ def main():
     work = tempfile.mkdtemp()
     REFFSA = os.path.join(work, 'ref.fsa')
     shutil.copy(os.path.join(HERE, 'synth60.fsa'), REFFSA)
+    NQ = sum(1 for line in open(REFFSA) if line.startswith('>'))
     parts = []
 
     def blastp(start, end):                      # the hook: keep a copy of the part the reference would search now
@@ -64,7 +65,9 @@ def main():
     ref_dir = '%s_parts' % REFFSA
     for p, sc in parts:
         tmp = tempfile.mkdtemp()
-        argv = ['-p', 'blastp', '-i', REFFSA, '-d', p, '-e', '1e-5', '-v', BV, '-l', '-1', '-u', '-1', '-L', '-1', '-U', '-1',
+        # find_hit.py always passes the query range explicitly (-l 0 -u N for one worker, bin/find_hit.py:107-120); with -u -1
+        # the core would stop at query len(part) (lib/fsearch.py:2980-2981)
+        argv = ['-p', 'blastp', '-i', REFFSA, '-d', p, '-e', '1e-5', '-v', BV, '-l', '0', '-u', str(NQ), '-L', '-1', '-U', '-1',
                 '-m', '1e-3', '-t', '-1', '-j', '1', '-F', 'T', '-D', '', '-O', 'wb', '-M', '1000003', '-c', '50000',
                 '-s', '111111', '-r', AA9, '-o', sc, '-T', tmp]
         print('reference search against', os.path.basename(p), flush=True)
