@@ -336,11 +336,25 @@ int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
         }
         order[(size_t)k] = (int)k;
     }
-    std::sort(order.begin(), order.end(), [&](int a, int b) {
-        if (prep[(size_t)a].len0 != prep[(size_t)b].len0) return prep[(size_t)a].len0 > prep[(size_t)b].len0;
-        if (prep[(size_t)a].len1 != prep[(size_t)b].len1) return prep[(size_t)a].len1 > prep[(size_t)b].len1;
-        return a < b;
-    });
+    // order: len0 descending, then len1 descending, then pair index (tasks of similar length share a warp); two stable
+    // counting passes (lengths are at most 4096) instead of a comparison sort: a round carries up to ~10^5 tasks
+    if (n > 64) {
+        std::vector<int> tmp((size_t)n), cnt(4098);
+        for (int pass = 0; pass < 2; pass++) {
+            std::fill(cnt.begin(), cnt.end(), 0);
+            const std::vector<int> &src = pass == 0 ? order : tmp;
+            std::vector<int> &dst = pass == 0 ? tmp : order;
+            auto key = [&](int k) { return 4096 - (pass == 0 ? prep[(size_t)k].len1 : prep[(size_t)k].len0); };
+            for (i64 k = 0; k < n; k++) cnt[(size_t)key(src[(size_t)k]) + 1]++;
+            for (int b = 0; b < 4097; b++) cnt[(size_t)b + 1] += cnt[(size_t)b];
+            for (i64 k = 0; k < n; k++) dst[(size_t)cnt[(size_t)key(src[(size_t)k])]++] = src[(size_t)k];
+        }
+    } else
+        std::sort(order.begin(), order.end(), [&](int a, int b) {
+            if (prep[(size_t)a].len0 != prep[(size_t)b].len0) return prep[(size_t)a].len0 > prep[(size_t)b].len0;
+            if (prep[(size_t)a].len1 != prep[(size_t)b].len1) return prep[(size_t)a].len1 > prep[(size_t)b].len1;
+            return a < b;
+        });
     std::vector<AlnTask> sorted((size_t)n);
     for (i64 k = 0; k < n; k++) sorted[(size_t)k] = tasks[(size_t)order[(size_t)k]];
     const i64 nwarps = (n + 31) / 32;

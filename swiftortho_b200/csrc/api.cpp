@@ -91,6 +91,7 @@ struct QueryState {
     i64 next = 0;                 // next candidate (in sorted order) to align
     i64 lead = 0;                 // candidates up to the last one whose UNGAPPED score already passes the e-value
     i64 last_hits = 0;            // candidates of the last round that gave a row
+    int rounds = 0;               // alignment rounds this query took part in
     double mmiss = 0;
     i64 unmch = 0, bv = 0;
     bool done = false;
@@ -101,10 +102,10 @@ struct QueryState {
 };
 
 // Alignment rounds.  The stop rule (fsearch.py:3103) is sequential per query: it ends after ceil(mmiss) consecutive
-// misses.  A round therefore submits, per unfinished query, exactly the candidates the rule is certain to reach:
-// first round = the candidates up to the last one whose ungapped diagonal score alone passes the e-value (they are
-// hits unless the banded alignment scores lower) + ceil(mmiss); later rounds = ceil(mmiss - unmch).  Alignments the
-// reference would not have computed only arise when the `bv >= v + mmiss` half of the rule fires inside a round.
+// misses.  The first round of a query submits exactly the candidates the rule is certain to reach: the candidates
+// up to the last one whose ungapped diagonal score alone passes the e-value (they are hits unless the banded
+// alignment scores lower) + ceil(mmiss).  Most queries end there with no alignment the reference would not have
+// computed; the others continue with rounds of 64, 128, ... candidates.
 static const i64 kRoundMax = 4096;
 
 }  // namespace so
@@ -648,10 +649,12 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             if (s.done) continue;
             const i64 qi_ord = s.qord;
             const i64 li = (i64)(c->q_off[(size_t)qi_ord + 1] - c->q_off[(size_t)qi_ord]);
-            // candidates the stop rule is certain to reach (see kRoundMax); a query that is still finding hits also
-            // gets as many more as it found in its last round, so long hit lists need O(log) rounds
+            // first round: the candidates the stop rule is certain to reach (see kRoundMax); a query that needs more
+            // rounds (its hits go on beyond the ungapped prediction) then takes 64, 128, 256, ... candidates per round,
+            // so every query finishes within a few launches (a round trip costs more than the alignments it saves)
             const i64 left = std::max<i64>((i64)std::ceil(s.mmiss - (double)s.unmch), 1);
-            const i64 want = s.next == 0 ? s.lead + (i64)std::ceil(s.mmiss) : left + s.last_hits;
+            const i64 want = s.next == 0 ? s.lead + (i64)std::ceil(s.mmiss) : std::max<i64>(left, (i64)64 << std::min(s.rounds - 1, 6));
+            s.rounds++;
             const i64 hi = std::min<i64>(s.limit, s.next + std::min<i64>(want, kRoundMax));
             s.last_hits = 0;
             for (i64 h = s.next; h < hi; h++) {
@@ -739,22 +742,22 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
         return SO_OK;
     };
 
+    size_t kMinFresh = 2048;  // new queries that trigger an alignment round while blocks are still being produced
+    if (const char *e = getenv("SO_ALIGN_BATCH")) kMinFresh = (size_t)std::max(1, atoi(e));  // tuning hook
     std::thread worker([&]() {
         cudaSetDevice(c->device);
+        size_t fresh = 0;
         for (;;) {
-            // absorb every block that is ready (in block order)
+            // absorb blocks (in block order) until a round is due
             for (;;) {
                 Job j;
                 bool have = false;
                 {
                     std::unique_lock<std::mutex> lk(mu);
-                    bool active = false;
-                    for (const auto &q : pool)
-                        if (!q.done) {
-                            active = true;
-                            break;
-                        }
-                    if (!active) cv.wait(lk, [&] { return jobs.count(next_blk) || producer_done; });
+                    // a round is worth launching once enough new queries are in (first rounds carry most of the
+                    // alignments) or nothing more will come; until then wait for the next block
+                    const bool go = fresh >= kMinFresh || (producer_done && !jobs.count(next_blk));
+                    if (!go) cv.wait(lk, [&] { return jobs.count(next_blk) || producer_done; });
                     if (jobs.count(next_blk)) {
                         j = jobs[next_blk];
                         jobs.erase(next_blk);
@@ -781,7 +784,10 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                     }
                 }
                 release();
+                fresh += (size_t)(j.b1 - j.b0);
+                if (fresh >= kMinFresh) break;
             }
+            fresh = 0;
             for (auto &q : pending) pool.push_back(std::move(q));
             pending.clear();
             bool active = false;
