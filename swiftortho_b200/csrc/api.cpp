@@ -104,8 +104,8 @@ struct QueryState {
 // Alignment rounds.  The stop rule (fsearch.py:3103) is sequential per query: it ends after ceil(mmiss) consecutive
 // misses.  The first round of a query submits exactly the candidates the rule is certain to reach: the candidates
 // up to the last one whose ungapped diagonal score alone passes the e-value (they are hits unless the banded
-// alignment scores lower) + ceil(mmiss).  Most queries end there with no alignment the reference would not have
-// computed; the others continue with rounds of 64, 128, ... candidates.
+// alignment scores lower, plus those above a diagonal score random pairs rarely reach) + ceil(mmiss).  Most queries
+// end there; the others continue with exactly ceil(mmiss - unmch) more, then with rounds of 64, 128, ... candidates.
 static const i64 kRoundMax = 4096;
 
 }  // namespace so
@@ -582,7 +582,9 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 const so_cand cd = so::unpack_cand(hs[(size_t)k * (size_t)selcap + (size_t)i]);
                 s.sel[(size_t)i] = cd;
                 const i64 lj = (i64)(c->t_off[(size_t)cd.target + 1] - c->t_off[(size_t)cd.target]);
-                if (so::bit2e(D, li, lj, so::score2bit((i64)cd.score)) <= P.expect) s.lead = i + 1;
+                // (random diagonals rarely chain above ~60: e^(-0.267 x) tail; a homolog's best diagonal usually does,
+                // even when indels keep its ungapped score below the e-value cut)
+                if (cd.score >= 60 || so::bit2e(D, li, lj, so::score2bit((i64)cd.score)) <= P.expect) s.lead = i + 1;
             }
         });
         wstats.ms_host += th.ms();
@@ -653,7 +655,9 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             // rounds (its hits go on beyond the ungapped prediction) then takes 64, 128, 256, ... candidates per round,
             // so every query finishes within a few launches (a round trip costs more than the alignments it saves)
             const i64 left = std::max<i64>((i64)std::ceil(s.mmiss - (double)s.unmch), 1);
-            const i64 want = s.next == 0 ? s.lead + (i64)std::ceil(s.mmiss) : std::max<i64>(left, (i64)64 << std::min(s.rounds - 1, 6));
+            const i64 want = s.next == 0   ? s.lead + (i64)std::ceil(s.mmiss)
+                             : s.rounds == 1 ? left
+                                             : std::max<i64>(left, (i64)64 << std::min(s.rounds - 2, 6));
             s.rounds++;
             const i64 hi = std::min<i64>(s.limit, s.next + std::min<i64>(want, kRoundMax));
             s.last_hits = 0;
@@ -742,7 +746,8 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
         return SO_OK;
     };
 
-    size_t kMinFresh = 2048;  // new queries that trigger an alignment round while blocks are still being produced
+    size_t kMinFresh = 1;  // new queries that trigger an alignment round (the worker takes every block that arrived
+                           // while it was busy with the previous round, so rounds grow by themselves under load)
     if (const char *e = getenv("SO_ALIGN_BATCH")) kMinFresh = (size_t)std::max(1, atoi(e));  // tuning hook
     std::thread worker([&]() {
         cudaSetDevice(c->device);
@@ -785,7 +790,6 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 }
                 release();
                 fresh += (size_t)(j.b1 - j.b0);
-                if (fresh >= kMinFresh) break;
             }
             fresh = 0;
             for (auto &q : pending) pool.push_back(std::move(q));
