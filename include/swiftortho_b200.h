@@ -179,6 +179,11 @@ int so_qsort_prefix_device(so_ctx *c, const uint32_t *keys, int64_t n, int64_t n
 int so_write_rows(const so_hit *rows, int64_t n, const so_fasta *queries, const so_fasta *targets, const char *path,
                   int append);
 
+/* R   redundancy pre-filter — the device half of scripts/nr_flt.py:8-27 (exact-duplicate collapse
+ * before the search, scripts/run_all_fast.py:110-119): hashes[n] receives a 64-bit content hash of every sequence
+ * of a packed set (H0 layout).  The host groups by hash and confirms equality byte for byte (swiftortho_b200/nr.py). */
+int so_seq_hash(int device, const uint8_t *residues, const uint64_t *offsets, int64_t n, uint64_t *hashes);
+
 /* counters of the last so_search / so_align_batch call (for bench.py) */
 typedef struct so_stats {
     int64_t queries, seed_hits, groups, candidates, alignments, dp_cells, rows;

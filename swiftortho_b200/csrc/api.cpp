@@ -514,16 +514,16 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     const i64 vmax = (i64)std::max(100., std::max((double)(P.v + 100), (double)P.v * 1.1));  // fsearch.py:3059
     std::vector<so_hit> all_rows;
     const size_t nch = c->chunks.size();
-    // query block size: candidates of a block are held packed in pinned memory, one buffer per chunk
-    i64 QB = std::max<i64>(64, std::min<i64>(512, 4096 / (i64)std::max<size_t>(1, nch)));
+    // query block size: the candidates of a block live in per-query device lists (select.cu)
+    i64 QB = 512;
     if (const char *e = getenv("SO_QUERY_BLOCK")) QB = std::max<i64>(16, atoll(e));  // tuning hook
     const int kSlots = 4;
     // at most one candidate per (query, target): fixed per-query capacity of the device lists
     i64 capq = 0;
     for (const auto &ix : c->chunks) capq += ix.c1 - ix.c0;
     capq = std::max<i64>(capq, 1);
-    // keep one lane's lists within ~3 GB
-    QB = std::max<i64>(16, std::min<i64>(QB, (i64)(3000000000ll / (capq * 8))));
+    // keep one lane's lists within ~6 GB (512 queries against up to 1.4 M targets)
+    QB = std::max<i64>(16, std::min<i64>(QB, (i64)(6000000000ll / (capq * 8))));
     if (c->cand_pool.size() < 2) c->cand_pool.resize(2);
     {
         int rc = so::upload_search_config(c);
