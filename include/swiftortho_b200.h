@@ -184,6 +184,18 @@ int so_write_rows(const so_hit *rows, int64_t n, const so_fasta *queries, const 
  * of a packed set (H0 layout).  The host groups by hash and confirms equality byte for byte (swiftortho_b200/nr.py). */
 int so_seq_hash(int device, const uint8_t *residues, const uint64_t *offsets, int64_t n, uint64_t *hashes);
 
+/* O   orthology inference, device half — bin/find_orth.py:158-234 (`blastparse`: best score per
+ * target inside a query group) and :298-348 (`get_qIPO`: per-taxon maxima, in-paralog / ortholog / co-ortholog call).
+ * Rows are the filtered hit table: group_offsets[n_groups + 1] delimits the runs of equal query id; ids are ranks in
+ * byte order of the id strings, taxa small integers, score the (normalised) double.  cls[row] = 0 not a candidate
+ * (or not the best row of its target), 1 IP, 2 OT, 3 CO. */
+int so_orth_classify(int device, const uint64_t *group_offsets, int64_t n_groups, const uint32_t *qrank,
+                     const uint32_t *srank, const uint32_t *qtax, const uint32_t *stax, const double *score,
+                     uint32_t n_taxa, uint8_t *cls);
+/* device radix sort of 64-bit keys with 32-bit payloads, in place (the reference's `sort` calls,
+ * bin/find_orth.py:476-478, 499-501, 552-554, on (id rank << 32 | id rank) keys) */
+int so_sort_pairs_u64(int device, uint64_t *keys, uint32_t *vals, int64_t n);
+
 /* counters of the last so_search / so_align_batch call (for bench.py) */
 typedef struct so_stats {
     int64_t queries, seed_hits, groups, candidates, alignments, dp_cells, rows;

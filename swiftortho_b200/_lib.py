@@ -91,6 +91,8 @@ SYMBOLS = {
     'so_search': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _P(_P(so_hit)), _P(C.c_int64)]),
     'so_write_rows': (C.c_int, [_P(so_hit), C.c_int64, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]),
     'so_seq_hash': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'so_orth_classify': (C.c_int, [C.c_int, C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p]),
+    'so_sort_pairs_u64': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
     'so_stats_get': (C.c_int, [C.c_void_p, _P(so_stats)]),
     'so_stats_reset': (C.c_int, [C.c_void_p]),
     'so_set_sub_block': (C.c_int, [C.c_void_p, C.c_int64]),
