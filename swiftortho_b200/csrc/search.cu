@@ -2033,8 +2033,8 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
             sub = std::max<i64>(1, nq / 2);
             continue;
         }
-        if (H > 0xfffffff0ull) {
-            set_error("query %lld produces too many seed hits", (long long)b0);
+        if (H > 0x7fffff00ull) {  // (the library sorts below take 32-bit signed item counts)
+            set_error("query %lld alone produces %llu seed hits; the limit is 2^31", (long long)b0, (unsigned long long)H);
             return SO_ELIMIT;
         }
         stats.seed_hits += (i64)H;

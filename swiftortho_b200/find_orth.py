@@ -57,41 +57,45 @@ def parse_args(argv):
 
 
 def read_table(path):
-    """Columns of a .sc / m8 file the reference reads (bin/find_orth.py:165-197): ids, identity, alignment length,
-    query coordinates, score, query length (or, for 12-column m8 input, max(qst, qed) of the id's first row)."""
+    """Columns of a .sc / m8 file the reference reads (bin/find_orth.py:165-197): ids (as sorted categories), identity,
+    alignment length, query coordinates, score, query length (or, for 12-column m8 input, max(qst, qed) of the id's
+    first row).  Rows with a non-numeric field among columns 3..12 (13, 14) are skipped like the reference's
+    try / except (:178-187)."""
     import pandas as pd
-    df = pd.read_csv(path, sep='\t', header=None, dtype=str, keep_default_na=False, na_filter=False, quoting=3, engine='c')
-    ncol = df.shape[1]
+    with open(path, 'rb') as f:
+        first = f.readline()
+    ncol = first.count(b'\t') + 1 if first else 0
     if ncol < 12:
+        if not first:
+            return None
         raise ValueError('%s: at least 12 tab-separated columns expected' % path)
-    num = {}
-    ok = np.ones(len(df), dtype=bool)
-    for c in range(2, 12):                       # a row with a non-numeric field among columns 3..12 is skipped (:178-182)
-        v = pd.to_numeric(df[c], errors='coerce')
-        ok &= ~v.isna().to_numpy() | (df[c].str.lower().isin(['nan', '+nan', '-nan'])).to_numpy()
-        num[c] = v.to_numpy(dtype=np.float64)
-    qid = df[0].to_numpy(dtype=object)
-    sid = df[1].to_numpy(dtype=object)
-    if ncol > 13:
-        qv = pd.to_numeric(df[12], errors='coerce')
-        sv = pd.to_numeric(df[13], errors='coerce')
-        ok &= ~(qv.isna().to_numpy() | sv.isna().to_numpy())
-        qln = qv.to_numpy(dtype=np.float64)
-    else:
-        qln = None
+    numeric = list(range(2, 12)) + ([12, 13] if ncol > 13 else [])
+    kw = dict(sep='\t', header=None, keep_default_na=False, na_filter=False, quoting=3, engine='c', usecols=[0, 1] + numeric)
+    try:                                         # fast path: every numeric field parses
+        df = pd.read_csv(path, dtype={**{0: 'category', 1: 'category'}, **{c: np.float64 for c in numeric}}, **kw)
+        ok = np.ones(len(df), dtype=bool)
+        num = {c: df[c].to_numpy() for c in numeric}
+    except (ValueError, TypeError):              # some row holds text in a numeric column: parse leniently, drop those rows
+        df = pd.read_csv(path, dtype=str, **kw)
+        ok = np.ones(len(df), dtype=bool)
+        num = {}
+        for c in numeric:
+            v = pd.to_numeric(df[c], errors='coerce')
+            ok &= ~v.isna().to_numpy() | df[c].str.lower().isin(['nan', '+nan', '-nan']).to_numpy()
+            num[c] = v.to_numpy(dtype=np.float64)
+        df[0], df[1] = df[0].astype('category'), df[1].astype('category')
     keep = np.nonzero(ok)[0]
-    t = dict(qid=qid[keep], sid=sid[keep], idy=num[2][keep], aln=num[3][keep], qst=num[6][keep], qed=num[7][keep],
-             score=num[11][keep])
-    if qln is not None:
-        t['qln'] = qln[keep]
-    else:                                        # len_dict (:188-193): first row of the id decides
-        first = {}
-        out = np.empty(len(keep), dtype=np.float64)
-        for i, (q, a, b) in enumerate(zip(t['qid'], t['qst'], t['qed'])):
-            if q not in first:
-                first[q] = max(a, b)
-            out[i] = first[q]
-        t['qln'] = out
+    qcat, scat = df[0].cat, df[1].cat
+    t = dict(qnames=np.asarray(qcat.categories, dtype=object), snames=np.asarray(scat.categories, dtype=object),
+             qcode=qcat.codes.to_numpy()[keep].astype(np.int64), scode=scat.codes.to_numpy()[keep].astype(np.int64),
+             idy=num[2][keep], aln=num[3][keep], qst=num[6][keep], qed=num[7][keep], score=num[11][keep])
+    if ncol > 13:
+        t['qln'] = num[12][keep]
+    else:                                        # len_dict (:188-193): the first row of a query id decides
+        _, first_row = np.unique(t['qcode'], return_index=True)
+        ln = np.zeros(len(t['qnames']), dtype=np.float64)
+        ln[t['qcode'][first_row]] = np.maximum(t['qst'], t['qed'])[first_row]
+        t['qln'] = ln[t['qcode']]
     return t
 
 
@@ -103,23 +107,25 @@ def find_orth(path, coverage=.5, identity=0., norm='no', sep='|', out=None, devi
     out = out or sys.stdout
     lib = _lib.load()
     t = read_table(path)
-    qid, sid = t['qid'], t['sid']
-    for a in (qid, sid):
-        for s in a:
-            assert sep in s                                              # bin/find_orth.py:173
+    if t is None:
+        return
+    # ---- ids -> ranks in byte order of the id strings (what the reference's LC_ALL=C line sorts compare first)
+    key = lambda x: x.encode('latin-1', 'replace')                      # noqa: E731
+    names = np.array(sorted(set(t['qnames']) | set(t['snames']), key=key), dtype=object)
+    for x in names:
+        assert sep in x                                                  # bin/find_orth.py:173
+    rank_of = {x: i for i, x in enumerate(names)}
+    qmap = np.fromiter((rank_of[x] for x in t['qnames']), dtype=np.uint32, count=len(t['qnames']))
+    smap = np.fromiter((rank_of[x] for x in t['snames']), dtype=np.uint32, count=len(t['snames']))
     # ---- filter (bin/find_orth.py:195-198)
     qcv = (1. + np.abs(t['qed'] - t['qst'])) / t['qln']
     keep = ~((qcv < coverage) | (t['idy'] < identity))
-    qid, sid, score, aln = qid[keep], sid[keep], t['score'][keep], t['aln'][keep]
-    n = len(qid)
+    qr, sr = np.ascontiguousarray(qmap[t['qcode'][keep]]), np.ascontiguousarray(smap[t['scode'][keep]])
+    score, aln = t['score'][keep], t['aln'][keep]
+    n = len(qr)
     if n == 0:
         return
-    # ---- ids -> ranks in byte order, taxa -> codes
-    names = np.array(sorted(set(qid) | set(sid), key=lambda s: s.encode('latin-1', 'replace')), dtype=object)
-    rank_of = {s: i for i, s in enumerate(names)}
-    qr = np.fromiter((rank_of[s] for s in qid), dtype=np.uint32, count=n)
-    sr = np.fromiter((rank_of[s] for s in sid), dtype=np.uint32, count=n)
-    tax_names = [s.split(sep)[0] for s in names]
+    tax_names = [x.split(sep)[0] for x in names]
     tax_code = {}
     tax = np.fromiter((tax_code.setdefault(x, len(tax_code)) for x in tax_names), dtype=np.uint32, count=len(names))
     # ---- query groups = runs of equal query id among the kept rows (:200-206)
