@@ -432,7 +432,7 @@ enum { kCellSmall = 8, kCellWarp = 192, kCellMax = 16384 };
 // device-wide scan over the cells is needed (k_unit_scan turns the <= 16 K item totals into item bases).  A cell
 // above `cell_max` hits raises flags[0] (the block is then redone through the device-wide sort).
 // Scatter pass (SCATTER = true): cursors start at ubase[item] + cell_local[..].
-template <bool SCATTER>
+template <bool SCATTER, int UU = 0>
 __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__ slot_off, BlockGeom g,
                                                     const uint64_t *__restrict__ qoff,
                                                     const uint32_t *__restrict__ slot_st, const uint32_t *__restrict__ slot_cnt,
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__
     __shared__ int s_qi;
     __shared__ uint32_t s_next_slot;
     const int lane = threadIdx.x & 31;
-    constexpr int U = SCATTER ? 4 : 8;  // bucket rows in flight per warp (the loops are latency bound)
+    constexpr int U = UU ? UU : (SCATTER ? 4 : 8);  // bucket rows in flight per warp (the loops are latency bound)
     for (;;) {            // CTAs draw queries from a counter: no wave quantisation with one 200 KB CTA per SM
         if (threadIdx.x == 0) {
             s_qi = (int)atomicAdd(next_query, 1u);
@@ -665,10 +665,20 @@ __global__ void __launch_bounds__(256) k_cell_small(const uint32_t *__restrict__
                                                     uint32_t *__restrict__ wlist,
                                                     uint32_t *__restrict__ blist, uint32_t *__restrict__ lcount,
                                                     const uint32_t *__restrict__ flags) {
-    if (flags[0]) return;
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t qi = 0, t = 0, off = 0, n = 0;
-    if (c < ncells) cell_extent(c, NB, NBh, nsplit, cell_local, ubase, qi, t, off, n);
+    // 2-D launch: blockIdx.y = query, x = target (no division per thread; `flags` is not consulted here: a block that
+    // is going to be redone only queues its large cells, which k_cell_block then skips)
+    (void)flags;
+    (void)ncells;
+    const uint32_t qi = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = qi * NB + t;
+    uint32_t off = 0, n = 0;
+    if (t < NB) {
+        const uint32_t unit = nsplit == 1 ? qi : qi * nsplit + t / NBh;
+        const uint32_t ub = ubase[unit];
+        off = ub + cell_local[c];
+        const bool last = (t + 1 == NB) || (nsplit != 1 && (t + 1) % NBh == 0);
+        n = (last ? ubase[unit + 1] : ub + cell_local[c + 1]) - off;
+    }
     {   // larger cells are queued: one atomic per warp and list
         const int lane = threadIdx.x & 31;
         const bool qw = n > (uint32_t)kCellSmall && n <= (uint32_t)kCellWarp, qb = n > (uint32_t)kCellWarp;
@@ -1914,6 +1924,7 @@ int upload_search_config(so_ctx *c) {
     SO_CUDA(cudaFuncSetAttribute(k_cell_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CellBlockSmem)));
     SO_CUDA(cudaFuncSetAttribute(k_cell_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     SO_CUDA(cudaFuncSetAttribute(k_cell_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SO_CUDA(cudaFuncSetAttribute(k_cell_pass<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     SO_CUDA(cudaFuncSetAttribute(k_cand_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CandSmem)));
     g_cell_max = kCellMax;
     if (const char *cm = getenv("SO_CELL_MAX")) g_cell_max = (uint32_t)std::max(1, std::min((int)kCellMax, atoi(cm)));  // test hook
@@ -2454,9 +2465,13 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
             k_cell_pass<false><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit, d_cloc,
                                                              d_utot, nullptr, nullptr, g_cell_max, d_flags, d_qcount + nq);
             k_unit_scan<<<1, 1024, 0, st>>>(d_utot, U, d_ubase, d_ctl, d_flags);
-            k_cell_pass<true><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit, d_cloc,
-                                                            nullptr, d_ubase, d_sub, g_cell_max, d_flags, d_lcount + 2);
-            k_cell_small<<<(ncells + 255) / 256, 256, 0, st>>>(d_cloc, d_ubase, ncells, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa,
+            if (getenv("SO_SCATTER_U8"))
+                k_cell_pass<true, 8><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit,
+                                                                   d_cloc, nullptr, d_ubase, d_sub, g_cell_max, d_flags, d_lcount + 2);
+            else
+                k_cell_pass<true><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit, d_cloc,
+                                                                nullptr, d_ubase, d_sub, g_cell_max, d_flags, d_lcount + 2);
+            k_cell_small<<<dim3((NB + 255) / 256, (unsigned)nq), 256, 0, st>>>(d_cloc, d_ubase, ncells, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa,
                                                               d_sub, d_ssub, d_desc, d_cellid, d_wlist, d_blist, d_lcount, d_flags);
             k_cell_warp<<<148 * 4, 256, 0, st>>>(d_cloc, d_ubase, d_wlist, d_lcount, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa, d_sub,
                                                 d_ssub, d_desc, d_cellid, d_flags);
