@@ -432,7 +432,7 @@ enum { kCellSmall = 8, kCellWarp = 192, kCellMax = 16384 };
 // device-wide scan over the cells is needed (k_unit_scan turns the <= 16 K item totals into item bases).  A cell
 // above `cell_max` hits raises flags[0] (the block is then redone through the device-wide sort).
 // Scatter pass (SCATTER = true): cursors start at ubase[item] + cell_local[..].
-template <bool SCATTER, int UU = 0>
+template <bool SCATTER>
 __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__ slot_off, BlockGeom g,
                                                     const uint64_t *__restrict__ qoff,
                                                     const uint32_t *__restrict__ slot_st, const uint32_t *__restrict__ slot_cnt,
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(1024) k_cell_pass(const uint32_t *__restrict__
     __shared__ int s_qi;
     __shared__ uint32_t s_next_slot;
     const int lane = threadIdx.x & 31;
-    constexpr int U = UU ? UU : (SCATTER ? 4 : 8);  // bucket rows in flight per warp (the loops are latency bound)
+    constexpr int U = SCATTER ? 4 : 8;  // bucket rows in flight per warp (8 in the scatter pass measured the same)
     for (;;) {            // CTAs draw queries from a counter: no wave quantisation with one 200 KB CTA per SM
         if (threadIdx.x == 0) {
             s_qi = (int)atomicAdd(next_query, 1u);
@@ -1071,6 +1071,15 @@ __global__ void __launch_bounds__(256) k_ung_marks(const uint64_t *__restrict__ 
     dst[offR + (n - 1 - (uint32_t)x)] = (uint8_t)(kUngStop << shift);
 }
 
+// 16 byte-shifted copies of a view (copy s holds view[j + s] at j), each `stride` bytes long: k_xdrop<FAST> reads its
+// query window with one 16-byte aligned load whatever the alignment of the position
+__global__ void __launch_bounds__(256) k_ung_shift(const uint8_t *__restrict__ src, uint32_t total, uint8_t *__restrict__ dst,
+                                                   uint32_t stride, uint8_t fill) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+    if (j >= stride) return;
+    dst[(size_t)s * stride + j] = j + s < total ? src[j + s] : fill;
+}
+
 static void ung_layout(uint32_t n, uint32_t off[2], uint32_t &total) {
     const uint32_t r = (n + 15u) & ~15u;
     off[0] = kUngPad;
@@ -1251,7 +1260,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                                                   unsigned long long *__restrict__ counters, int one,
                                                   const uint32_t *__restrict__ cellid, int diag_bits,
                                                   uint64_t *__restrict__ creg, size_t ccap, uint32_t *__restrict__ qcount,
-                                                  uint32_t *__restrict__ flags) {
+                                                  uint32_t *__restrict__ flags, uint32_t qstride4) {
     extern __shared__ int s_tab[];  // [(ct << 5 | cq)][lane]; FAST: + per-warp record buffers
     const uint32_t G = FAST ? (uint32_t)counters[0] : G_;
     // FAST: groups that pass (score >= 25, self.min: fsearch.py:2224, 2707) leave one record
@@ -1488,13 +1497,22 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 const int o = (int)(tpos & 15u);
                 const uint32_t qpos = (phase ? qoffR + (Lq - uq) : qoffF + uq) - (uint32_t)o;
                 tci = tpos >> 4;
-                qci = qpos >> 4;
-                w1 = (qpos & 4u) != 0, w2 = (qpos & 8u) != 0, bs8 = (qpos & 3u) * 8u;
                 tc = T4[tci];
-                const uint4 a = Q4[qci];
-                carry = Q4[qci + 1];
-                tci += 1, qci += 2;
-                ung_qwindow(a, carry, w1, w2, bs8, W);
+                if (FAST) {
+                    // the query view exists in 16 byte-shifted copies: copy (qpos & 15) holds the wanted bytes 16-byte
+                    // aligned, so the window is one aligned load per iteration (no multiplexing of two chunks)
+                    qci = (qpos & 15u) * qstride4 + (qpos >> 4);
+                    const uint4 a = Q4[qci];
+                    W[0] = a.x, W[1] = a.y, W[2] = a.z, W[3] = a.w;
+                    tci += 1, qci += 1;
+                } else {
+                    qci = qpos >> 4;
+                    w1 = (qpos & 4u) != 0, w2 = (qpos & 8u) != 0, bs8 = (qpos & 3u) * 8u;
+                    const uint4 a = Q4[qci];
+                    carry = Q4[qci + 1];
+                    tci += 1, qci += 2;
+                    ung_qwindow(a, carry, w1, w2, bs8, W);
+                }
                 ung_mask_below(tc, o, kUngSkip);  // bytes before the start score nothing
                 if (lim < 16 - o) ung_mask_from(tc, o + lim, kUngStop);
                 lim -= 16 - o;
@@ -1514,7 +1532,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 ev[4 * j + 2] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xEE62u) << 4));
                 ev[4 * j + 3] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xFF73u) << 4));
             }
-            uint4 nq = carry;
+            uint4 nq = FAST ? make_uint4(W[0], W[1], W[2], W[3]) : carry;
             ldg128_if(tc, T4 + tci, alive);
             ldg128_if(nq, Q4 + qci, alive);
             ung_steps16(v, d, alive, one, ev);
@@ -1522,8 +1540,12 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 if (lim < 16) ung_mask_from(tc, lim, kUngStop);
             }
             lim -= 16;
-            ung_qwindow(carry, nq, w1, w2, bs8, W);
-            carry = nq;
+            if (FAST) {
+                W[0] = nq.x, W[1] = nq.y, W[2] = nq.z, W[3] = nq.w;
+            } else {
+                ung_qwindow(carry, nq, w1, w2, bs8, W);
+                carry = nq;
+            }
             tci += 1, qci += 1;
         }
     }
@@ -1897,7 +1919,7 @@ static int bits_for(uint64_t maxval) {  // bits needed to hold values 0..maxval
 
 enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TMP, SC_CKA, SC_CKB, SC_CVA, SC_CVB, SC_MISC,
        SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK, SC_QUNG, SC_DESC, SC_MLIST, SC_GKEY, SC_PLIST, SC_CELLLOC, SC_UNIT, SC_SUB, SC_SSUB,
-       SC_WLIST, SC_CREG, SC_QCOUNT, SC_GBUF, SC_CTL, SC_COUNT_ };
+       SC_WLIST, SC_CREG, SC_QCOUNT, SC_GBUF, SC_CTL, SC_QSHIFT, SC_COUNT_ };
 static_assert(SC_COUNT_ <= 64, "scratch slots");
 
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
@@ -1924,7 +1946,6 @@ int upload_search_config(so_ctx *c) {
     SO_CUDA(cudaFuncSetAttribute(k_cell_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CellBlockSmem)));
     SO_CUDA(cudaFuncSetAttribute(k_cell_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     SO_CUDA(cudaFuncSetAttribute(k_cell_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    SO_CUDA(cudaFuncSetAttribute(k_cell_pass<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     SO_CUDA(cudaFuncSetAttribute(k_cand_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CandSmem)));
     g_cell_max = kCellMax;
     if (const char *cm = getenv("SO_CELL_MAX")) g_cell_max = (uint32_t)std::max(1, std::min((int)kCellMax, atoi(cm)));  // test hook
@@ -2162,7 +2183,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                                                           (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
                                                           (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
                                                           qoff2[1], (uint32_t)Lq64, d_gscore, d_grank, d_counter, 1, nullptr, 0, nullptr, 0,
-                                                          nullptr, nullptr);
+                                                          nullptr, nullptr, 0u);
                     d_gkey = (const uint64_t *)scratch[SC_GKEY].p;
                     stats.kernel_launches += 2;
                 } else {
@@ -2437,6 +2458,11 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
         if ((rc = ung_build(st, stats, c->d_qcls + qa, c->d_qoff + sb.s0, (uint32_t)nq, qa, (uint32_t)Lq64, d_qung, qoff2, qtotal,
                             3)) != SO_OK)
             return rc;
+        const uint32_t qstride = (qtotal + 32u + 15u) & ~15u;
+        if ((rc = scratch[SC_QSHIFT].reserve((size_t)qstride * 16)) != SO_OK) return rc;
+        uint8_t *d_qsh = scratch[SC_QSHIFT].p;
+        k_ung_shift<<<dim3((qstride + 255) / 256, 16), 256, 0, st>>>(d_qung, qtotal, d_qsh, qstride, (uint8_t)(kUngStop << 3));
+        stats.kernel_launches += 1;
         for (size_t ch = 0; ch < nch; ch++) {
             const ChunkIndex &ix = c->chunks[ch];
             if (ix.n_seeds == 0 || (only_chunk >= 0 && (size_t)only_chunk != ch)) continue;
@@ -2465,12 +2491,8 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
             k_cell_pass<false><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit, d_cloc,
                                                              d_utot, nullptr, nullptr, g_cell_max, d_flags, d_qcount + nq);
             k_unit_scan<<<1, 1024, 0, st>>>(d_utot, U, d_ubase, d_ctl, d_flags);
-            if (getenv("SO_SCATTER_U8"))
-                k_cell_pass<true, 8><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit,
-                                                                   d_cloc, nullptr, d_ubase, d_sub, g_cell_max, d_flags, d_lcount + 2);
-            else
-                k_cell_pass<true><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit, d_cloc,
-                                                                nullptr, d_ubase, d_sub, g_cell_max, d_flags, d_lcount + 2);
+            k_cell_pass<true><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit, d_cloc,
+                                                            nullptr, d_ubase, d_sub, g_cell_max, d_flags, d_lcount + 2);
             k_cell_small<<<dim3((NB + 255) / 256, (unsigned)nq), 256, 0, st>>>(d_cloc, d_ubase, ncells, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa,
                                                               d_sub, d_ssub, d_desc, d_cellid, d_wlist, d_blist, d_lcount, d_flags);
             k_cell_warp<<<148 * 4, 256, 0, st>>>(d_cloc, d_ubase, d_wlist, d_lcount, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa, d_sub,
@@ -2480,9 +2502,9 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
             stamp();
             kx<<<148 * 2, 512, kUngTabBytes + kXdBufBytes, st>>>(d_desc, 0u, d_ssub, nullptr, nullptr, 0u, nullptr, g.qst_bits,
                                                                 (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
-                                                                (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
+                                                                (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qsh, qoff2[0],
                                                                 qoff2[1], (uint32_t)Lq64, nullptr, nullptr, d_ctl, 1, d_cellid,
-                                                                g.diag_bits, d_creg, ccap, d_qcount, d_flags);
+                                                                g.diag_bits, d_creg, ccap, d_qcount, d_flags, qstride / 16);
             stamp();
             k_cand_sort<<<sgrid, kCandThreads, sizeof(CandSmem), st>>>(d_creg, ccap, d_qcount, nq, g, c->d_qoff, (uint64_t *)scratch[SC_GBUF].p,
                                                                       bs.vals.p, bs.capq, bs.count.p, (int)(sb.s0 - b0), d_lcount + 3,
