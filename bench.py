@@ -260,11 +260,7 @@ def full_job(args, rank, world, local, fasta, barrier, out_dir):
         off = np.ascontiguousarray(F.offsets[a:b + 1])
         so.check(lib.so_set_queries(S.h, C.c_void_p(F._res.value), off.ctypes.data, b - a))
         S.stats(reset=True)
-        for q0 in range(0, b - a, args.full_block):
-            rows = S.search(q0, min(b - a, q0 + args.full_block))
-            rows.view()['query'] += a
-            so.check(lib.so_write_rows(rows.ptr, rows.n, F.h, F.h, part.encode(), 1))
-            nrows += rows.n
+        nrows = S.search_to_file(0, b - a, part, block=args.full_block, query_base=a, fasta=F)
     st = S.stats()
     t_part = time.perf_counter() - t0
     barrier()

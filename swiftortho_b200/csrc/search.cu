@@ -1071,15 +1071,6 @@ __global__ void __launch_bounds__(256) k_ung_marks(const uint64_t *__restrict__ 
     dst[offR + (n - 1 - (uint32_t)x)] = (uint8_t)(kUngStop << shift);
 }
 
-// 16 byte-shifted copies of a view (copy s holds view[j + s] at j), each `stride` bytes long: k_xdrop<FAST> reads its
-// query window with one 16-byte aligned load whatever the alignment of the position
-__global__ void __launch_bounds__(256) k_ung_shift(const uint8_t *__restrict__ src, uint32_t total, uint8_t *__restrict__ dst,
-                                                   uint32_t stride, uint8_t fill) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
-    if (j >= stride) return;
-    dst[(size_t)s * stride + j] = j + s < total ? src[j + s] : fill;
-}
-
 static void ung_layout(uint32_t n, uint32_t off[2], uint32_t &total) {
     const uint32_t r = (n + 15u) & ~15u;
     off[0] = kUngPad;
@@ -1260,7 +1251,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                                                   unsigned long long *__restrict__ counters, int one,
                                                   const uint32_t *__restrict__ cellid, int diag_bits,
                                                   uint64_t *__restrict__ creg, size_t ccap, uint32_t *__restrict__ qcount,
-                                                  uint32_t *__restrict__ flags, uint32_t qstride4) {
+                                                  uint32_t *__restrict__ flags) {
     extern __shared__ int s_tab[];  // [(ct << 5 | cq)][lane]; FAST: + per-warp record buffers
     const uint32_t G = FAST ? (uint32_t)counters[0] : G_;
     // FAST: groups that pass (score >= 25, self.min: fsearch.py:2224, 2707) leave one record
@@ -1497,22 +1488,13 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 const int o = (int)(tpos & 15u);
                 const uint32_t qpos = (phase ? qoffR + (Lq - uq) : qoffF + uq) - (uint32_t)o;
                 tci = tpos >> 4;
+                qci = qpos >> 4;
+                w1 = (qpos & 4u) != 0, w2 = (qpos & 8u) != 0, bs8 = (qpos & 3u) * 8u;
                 tc = T4[tci];
-                if (FAST) {
-                    // the query view exists in 16 byte-shifted copies: copy (qpos & 15) holds the wanted bytes 16-byte
-                    // aligned, so the window is one aligned load per iteration (no multiplexing of two chunks)
-                    qci = (qpos & 15u) * qstride4 + (qpos >> 4);
-                    const uint4 a = Q4[qci];
-                    W[0] = a.x, W[1] = a.y, W[2] = a.z, W[3] = a.w;
-                    tci += 1, qci += 1;
-                } else {
-                    qci = qpos >> 4;
-                    w1 = (qpos & 4u) != 0, w2 = (qpos & 8u) != 0, bs8 = (qpos & 3u) * 8u;
-                    const uint4 a = Q4[qci];
-                    carry = Q4[qci + 1];
-                    tci += 1, qci += 2;
-                    ung_qwindow(a, carry, w1, w2, bs8, W);
-                }
+                const uint4 a = Q4[qci];
+                carry = Q4[qci + 1];
+                tci += 1, qci += 2;
+                ung_qwindow(a, carry, w1, w2, bs8, W);
                 ung_mask_below(tc, o, kUngSkip);  // bytes before the start score nothing
                 if (lim < 16 - o) ung_mask_from(tc, o + lim, kUngStop);
                 lim -= 16 - o;
@@ -1532,7 +1514,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 ev[4 * j + 2] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xEE62u) << 4));
                 ev[4 * j + 3] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xFF73u) << 4));
             }
-            uint4 nq = FAST ? make_uint4(W[0], W[1], W[2], W[3]) : carry;
+            uint4 nq = carry;
             ldg128_if(tc, T4 + tci, alive);
             ldg128_if(nq, Q4 + qci, alive);
             ung_steps16(v, d, alive, one, ev);
@@ -1540,12 +1522,8 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 if (lim < 16) ung_mask_from(tc, lim, kUngStop);
             }
             lim -= 16;
-            if (FAST) {
-                W[0] = nq.x, W[1] = nq.y, W[2] = nq.z, W[3] = nq.w;
-            } else {
-                ung_qwindow(carry, nq, w1, w2, bs8, W);
-                carry = nq;
-            }
+            ung_qwindow(carry, nq, w1, w2, bs8, W);
+            carry = nq;
             tci += 1, qci += 1;
         }
     }
@@ -1919,7 +1897,7 @@ static int bits_for(uint64_t maxval) {  // bits needed to hold values 0..maxval
 
 enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TMP, SC_CKA, SC_CKB, SC_CVA, SC_CVB, SC_MISC,
        SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK, SC_QUNG, SC_DESC, SC_MLIST, SC_GKEY, SC_PLIST, SC_CELLLOC, SC_UNIT, SC_SUB, SC_SSUB,
-       SC_WLIST, SC_CREG, SC_QCOUNT, SC_GBUF, SC_CTL, SC_QSHIFT, SC_COUNT_ };
+       SC_WLIST, SC_CREG, SC_QCOUNT, SC_GBUF, SC_CTL, SC_COUNT_ };
 static_assert(SC_COUNT_ <= 64, "scratch slots");
 
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
@@ -2183,7 +2161,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                                                           (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
                                                           (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
                                                           qoff2[1], (uint32_t)Lq64, d_gscore, d_grank, d_counter, 1, nullptr, 0, nullptr, 0,
-                                                          nullptr, nullptr, 0u);
+                                                          nullptr, nullptr);
                     d_gkey = (const uint64_t *)scratch[SC_GKEY].p;
                     stats.kernel_launches += 2;
                 } else {
@@ -2458,11 +2436,6 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
         if ((rc = ung_build(st, stats, c->d_qcls + qa, c->d_qoff + sb.s0, (uint32_t)nq, qa, (uint32_t)Lq64, d_qung, qoff2, qtotal,
                             3)) != SO_OK)
             return rc;
-        const uint32_t qstride = (qtotal + 32u + 15u) & ~15u;
-        if ((rc = scratch[SC_QSHIFT].reserve((size_t)qstride * 16)) != SO_OK) return rc;
-        uint8_t *d_qsh = scratch[SC_QSHIFT].p;
-        k_ung_shift<<<dim3((qstride + 255) / 256, 16), 256, 0, st>>>(d_qung, qtotal, d_qsh, qstride, (uint8_t)(kUngStop << 3));
-        stats.kernel_launches += 1;
         for (size_t ch = 0; ch < nch; ch++) {
             const ChunkIndex &ix = c->chunks[ch];
             if (ix.n_seeds == 0 || (only_chunk >= 0 && (size_t)only_chunk != ch)) continue;
@@ -2502,9 +2475,9 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
             stamp();
             kx<<<148 * 2, 512, kUngTabBytes + kXdBufBytes, st>>>(d_desc, 0u, d_ssub, nullptr, nullptr, 0u, nullptr, g.qst_bits,
                                                                 (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
-                                                                (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qsh, qoff2[0],
+                                                                (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
                                                                 qoff2[1], (uint32_t)Lq64, nullptr, nullptr, d_ctl, 1, d_cellid,
-                                                                g.diag_bits, d_creg, ccap, d_qcount, d_flags, qstride / 16);
+                                                                g.diag_bits, d_creg, ccap, d_qcount, d_flags);
             stamp();
             k_cand_sort<<<sgrid, kCandThreads, sizeof(CandSmem), st>>>(d_creg, ccap, d_qcount, nq, g, c->d_qoff, (uint64_t *)scratch[SC_GBUF].p,
                                                                       bs.vals.p, bs.capq, bs.count.p, (int)(sb.s0 - b0), d_lcount + 3,

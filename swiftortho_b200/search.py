@@ -133,6 +133,44 @@ class Searcher:
         check(self.lib.so_write_rows(rows.ptr, rows.n, self.queries.h, self.targets.h, str(path).encode(),
                                      1 if append else 0))
 
+    def search_to_file(self, q_begin, q_end, path, block=8192, query_base=0, fasta=None):
+        """Search queries [q_begin, q_end) block by block and append the rows to `path`; a writer thread formats and
+        writes block i while block i + 1 is searched (the library calls release the GIL).  `query_base` is added to
+        the query ordinals (the loaded query set may be a slice of `fasta`)."""
+        import queue
+        import threading
+        fasta = fasta or self.queries
+        wq, err, nrows = queue.Queue(maxsize=2), [], [0]
+
+        def writer():
+            while True:
+                rows = wq.get()
+                if rows is None:
+                    return
+                try:
+                    if not err:
+                        check(self.lib.so_write_rows(rows.ptr, rows.n, fasta.h, self.targets.h, str(path).encode(), 1))
+                        nrows[0] += rows.n
+                except BaseException as e:  # noqa: BLE001
+                    err.append(e)
+
+        th = threading.Thread(target=writer)
+        th.start()
+        try:
+            for b in range(q_begin, q_end, block):
+                rows = self.search(b, min(q_end, b + block))
+                if query_base:
+                    rows.view()['query'] += query_base
+                wq.put(rows)
+                if err:
+                    break
+        finally:
+            wq.put(None)
+            th.join()
+        if err:
+            raise err[0]
+        return nrows[0]
+
     def stats(self, reset=False):
         s = so_stats()
         check(self.lib.so_stats_get(self.h, C.byref(s)))
@@ -201,9 +239,7 @@ def blastp(qry, ref, out, expect=1e-5, v=500, max_miss=1e-3, st=-1, ed=-1, rst=-
     first = 'a' not in wrt
     if first:
         open(out, 'wb').close()
-    for b in range(st, ed, block):
-        rows = S.search(b, min(ed, b + block))
-        S.write(rows, out, append=True)
+    S.search_to_file(st, ed, out, block=block)
     stats = S.stats()
     S.close()
     return stats
