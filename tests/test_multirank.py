@@ -47,3 +47,65 @@ def _rank_main(rank, world, port, tmp):
 def test_two_rank_gloo(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+
+
+def _fake_fasta(n=40):
+    class F:
+        offsets = np.concatenate([[0], np.cumsum(np.full(n, 100))]).astype(np.uint64)
+    return F
+
+
+def test_run_sharded_ignores_stale_markers_and_propagates_errors(tmp_path, monkeypatch):
+    """markers left behind by a crashed run must not be mistaken for this run's (every marker carries the
+    run id), a failing rank leaves an error marker that makes rank 0 raise, and the wait is bounded."""
+    from swiftortho_b200 import find_hit
+    tmp = str(tmp_path / 'tmpdir')
+    os.makedirs(tmp)
+    out = str(tmp_path / 'merged.sc')
+    # leftovers of an older run with another id: a complete-looking part + done marker of rank 1's slice
+    for name in ('merged.sc.000000000020', 'merged.sc.000000000020.old.done', 'merged.sc.000000000020.old'):
+        open(os.path.join(tmp, name), 'w').write('STALE\n')
+    monkeypatch.setenv('SO_RUN_ID', 'new')
+    monkeypatch.setenv('SO_SHARD_TIMEOUT', '1')
+
+    def worker(s, e, part):
+        with open(part, 'w') as f:
+            for q in range(s, e):
+                f.write('q%d\n' % q)
+    # rank 0 alone: rank 1 never reports -> bounded wait, no use of the stale files
+    with pytest.raises(TimeoutError):
+        find_hit.run_sharded(_fake_fasta(), 0, 40, 0, 2, out, tmp, 'wb', worker)
+    assert not os.path.exists(out) or 'STALE' not in open(out).read()
+    # rank 1 fails: error marker, rank 0 raises instead of waiting
+    def bad(s, e, part):
+        raise RuntimeError('boom')
+    with pytest.raises(RuntimeError):
+        find_hit.run_sharded(_fake_fasta(), 0, 40, 1, 2, out, tmp, 'wb', bad)
+    monkeypatch.setenv('SO_SHARD_TIMEOUT', '30')
+    with pytest.raises(RuntimeError, match='another rank failed'):
+        find_hit.run_sharded(_fake_fasta(), 0, 40, 0, 2, out, tmp, 'wb', worker)
+
+
+def test_split_reference_and_merge_reference_golden(tmp_path):
+    """Large-reference path, host half (bin/find_hit.py:296-351): the split rule and the merge command reproduce the
+    golden table made by the reference's own split loop, the reference search per part and the reference's merge
+    (tests/golden/make_split_golden.py); the per-part tables come from the CPU oracle here (the `-m gpu` twin of this
+    test, test_find_hit_cli_split_reference, runs the whole CLI on the device)."""
+    import shutil
+    from conftest import GOLDEN, Oracle
+    from swiftortho_b200 import find_hit
+    ref = str(tmp_path / 'ref.fsa')
+    shutil.copy(os.path.join(GOLDEN, 'synth60.fsa'), ref)
+    parts = find_hit.split_reference(ref, ref + '_parts', 4000)
+    assert [os.path.getsize(p) for p in parts] == [4308, 3914, 3872, 1100]
+    o = Oracle()
+    scs = []
+    for i, p in enumerate(parts):
+        sc = '%s_parts/%d.sc' % (ref, i)
+        o.blastp(ref, p, sc, {'-e': '1e-5', '-j': '1', '-M': '1000003', '-c': '50000', '-s': '111111', '-v': '3', '-l': '0',
+                              '-u': '60'})
+        scs.append(sc)
+    out = str(tmp_path / 'out.sc')
+    os.environ['LC_ALL'] = 'C'
+    find_hit.merge_part_tables(sorted(scs), 3, out)
+    assert open(out, 'rb').read() == open(os.path.join(GOLDEN, 'synth60_split.sc'), 'rb').read()
