@@ -522,13 +522,14 @@ def run_ours(args, rank, world, local):
     dev_ms = max(1e-9, ms_ungap + ms_sort + ms_seed + ms_select + ms_dp + ms_tb)
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_xdrop_r01.json')))
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_xdrop_r02.json')))
     except Exception:  # noqa: BLE001
         pass
     roof = {'kernel': 'k_xdrop', 'bound': 'int32', 'achieved': ach, 'peak': int_peak['gops_measured'],
             'unit': 'Gop/s', 'frac': ach / int_peak['gops_measured'],
             'traffic': traffic.get('dram_bytes_per_launch') if traffic else None,
             'traffic_note': traffic.get('note') if traffic else None,
+            'traffic_launch': traffic.get('launch') if traffic else None,
             'peak_source': 'tools/int_peak.cu measured on this pool (profiles/int_peak.json)',
             'algorithmic_ops': '6 INT ops per X-drop extension step (SURVEY.md 8d) x %.3g steps per step' % (
                 ungap_steps / max(world, 1) / args.steps),
@@ -632,7 +633,7 @@ def main():
     ap.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS), help='BASELINE.json config (default 2 = headline)')
     ap.add_argument('--mode', default='steps', choices=['steps', 'full'],
                     help='steps: timed query blocks against the resident index (default); full: one whole job, strong scaling')
-    ap.add_argument('--full-block', type=int, default=8192, help='queries per so_search call of the whole-job run')
+    ap.add_argument('--full-block', type=int, default=65536, help='queries per so_search call of the whole-job run')
     ap.add_argument('--full-check-rows', type=int, default=2000000)
     ap.add_argument('--no-full', action='store_true', help='skip the whole-job record of the default run')
     ap.add_argument('--parity-out', default=None, help=argparse.SUPPRESS)

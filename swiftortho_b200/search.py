@@ -221,7 +221,7 @@ class _Rows:
 
 
 def blastp(qry, ref, out, expect=1e-5, v=500, max_miss=1e-3, st=-1, ed=-1, rst=-1, red=-1, thr=-1, flt='T',
-           ssd='111111', nr=AA9, step=4, ht=-1, chk=50000, wrt='w', device=0, block=8192):
+           ssd='111111', nr=AA9, step=4, ht=-1, chk=50000, wrt='w', device=0, block=65536):
     """Drop-in for the `fsearch-c -p blastp` run (lib/fsearch.py:2968 + 3231-3256): searches queries
     [st, ed) of `qry` against `ref` and writes the 16-column rows to `out`.  Returns the stats dict."""
     if ht < 2:
