@@ -980,35 +980,57 @@ int so_write_rows(const so_hit *rows, int64_t n, const so_fasta *queries, const 
     std::atomic<int> bad(0);
     so::parallel_for(nslices, [&](so::i64 sl) {
         std::string &buf = bufs[(size_t)sl];
-        buf.reserve((size_t)kSlice * 160);
-        char num[256];
-        const int64_t k1 = std::min<int64_t>(n, (sl + 1) * kSlice);
-        for (int64_t k = sl * kSlice; k < k1; k++) {
-            const so_hit &r = rows[k];
+        const int64_t k0 = sl * kSlice, k1 = std::min<int64_t>(n, (sl + 1) * kSlice);
+        // one pass for the size (ids and headers vary), one pass writing into the buffer: no per-field allocation
+        size_t cap = 0;
+        for (int64_t k = k0; k < k1; k++) {
             const char *hq, *ht;
             int64_t lq, lt;
-            if (so_fasta_header(queries, r.query, &hq, &lq) != SO_OK || so_fasta_header(targets, r.target, &ht, &lt) != SO_OK) {
+            if (so_fasta_header(queries, rows[k].query, &hq, &lq) != SO_OK || so_fasta_header(targets, rows[k].target, &ht, &lt) != SO_OK) {
                 bad = 1;
                 return;
             }
+            cap += (size_t)lq + 2 * (size_t)lt + 13 * 24 + 900;
+        }
+        buf.resize(cap);
+        char *p = &buf[0];
+        auto put_int = [&](long long v) {
+            char t[24];
+            int m = 0;
+            unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+            do t[m++] = (char)('0' + u % 10), u /= 10;
+            while (u);
+            if (v < 0) *p++ = '-';
+            while (m) *p++ = t[--m];
+        };
+        for (int64_t k = k0; k < k1; k++) {
+            const so_hit &r = rows[k];
+            const char *hq, *ht;
+            int64_t lq, lt;
+            so_fasta_header(queries, r.query, &hq, &lq);
+            so_fasta_header(targets, r.target, &ht, &lt);
             // ids = header up to the first space (fsearch.py:3066)
             int64_t iq = 0, it = 0;
             while (iq < lq && hq[iq] != ' ') iq++;
             while (it < lt && ht[it] != ' ') it++;
-            buf.append(hq, (size_t)iq);
-            buf += '\t';
-            buf.append(ht, (size_t)it);
-            buf += '\t';
-            buf += so::fmt_identity(r.identity);
-            snprintf(num, sizeof num, "\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t", r.aln_len, r.mismatch, r.gaps, r.qst, r.qed, r.sst,
-                     r.sed);
-            buf += num;
-            buf += so::f2s(r.evalue);
-            snprintf(num, sizeof num, "\t%lld\t%d\t%d\t%lld\t", (long long)r.bit, r.qlen, r.tlen, (long long)r.query);
-            buf += num;
-            buf.append(ht, (size_t)lt);
-            buf += '\n';
+            memcpy(p, hq, (size_t)iq), p += iq, *p++ = '\t';
+            memcpy(p, ht, (size_t)it), p += it, *p++ = '\t';
+            p += so::fmt_identity_to(p, r.identity), *p++ = '\t';
+            put_int(r.aln_len), *p++ = '\t';
+            put_int(r.mismatch), *p++ = '\t';
+            put_int(r.gaps), *p++ = '\t';
+            put_int(r.qst), *p++ = '\t';
+            put_int(r.qed), *p++ = '\t';
+            put_int(r.sst), *p++ = '\t';
+            put_int(r.sed), *p++ = '\t';
+            p += so::f2s_to(p, r.evalue), *p++ = '\t';
+            put_int((long long)r.bit), *p++ = '\t';
+            put_int(r.qlen), *p++ = '\t';
+            put_int(r.tlen), *p++ = '\t';
+            put_int((long long)r.query), *p++ = '\t';
+            memcpy(p, ht, (size_t)lt), p += lt, *p++ = '\n';
         }
+        buf.resize((size_t)(p - &buf[0]));
     });
     if (bad) {
         fclose(f);

@@ -56,5 +56,7 @@ i64 score2bit(i64 raw);
 double bit2e(i64 D, i64 ql, i64 tl, i64 bit);
 std::string f2s(double e);
 std::string fmt_identity(double idy);
+int f2s_to(char *out, double e);              // same text into a caller buffer (>= 400 bytes); returns the length
+int fmt_identity_to(char *out, double idy);
 
 }  // namespace so

@@ -329,33 +329,56 @@ i64 score2bit(i64 raw) { return (i64)((.267 * (double)raw + 3.1941832122778293) 
 
 double bit2e(i64 D, i64 ql, i64 tl, i64 bit) { return (double)(D * ql * tl) * std::pow(2, -(double)bit); }
 
-static std::string six(double x) {  // RPython str(float): '%.6f'
-    char b[400];
-    snprintf(b, sizeof b, "%.6f", x);
-    return b;
-}
+// RPython str(float) is '%.6f'.  The *_to variants write into a caller buffer (>= 400 bytes) and return the length:
+// so_write_rows formats ~10^5 rows per call and must not allocate per field.
+static int six_to(char *b, double x) { return snprintf(b, 400, "%.6f", x); }
 
-std::string f2s(double e) {
-    if (e <= 0) return "0";
-    if (e >= 1e-3) return six(e);
+int f2s_to(char *out, double e) {
+    if (e <= 0) {
+        out[0] = '0', out[1] = 0;
+        return 1;
+    }
+    if (e >= 1e-3) return six_to(out, e);
     double frac = std::log10(e);
     frac -= (double)(i64)frac;
     if (frac < 0) frac = 1 + frac;
-    double mant = std::pow(10, frac);
-    std::string ex = six(std::log10(e / mant));
-    size_t dot = ex.find('.');
-    ex.resize(dot == std::string::npos ? 0 : dot);
-    std::string m = six(mant);
-    dot = m.find('.');
-    m.resize(dot == std::string::npos ? 2 : dot + 3);
-    return m + "e" + ex;
+    const double mant = std::pow(10, frac);
+    char m[400], ex[400];
+    int lm = six_to(m, mant), le = six_to(ex, std::log10(e / mant));
+    const char *dm = (const char *)memchr(m, '.', (size_t)lm);
+    const char *de = (const char *)memchr(ex, '.', (size_t)le);
+    const int nm = dm ? std::min(lm, (int)(dm - m) + 3) : std::min(lm, 2);   // mantissa truncated to 2 decimals
+    const int ne = de ? (int)(de - ex) : 0;                                   // integer part of the exponent text
+    memcpy(out, m, (size_t)nm);
+    out[nm] = 'e';
+    memcpy(out + nm + 1, ex, (size_t)ne);
+    out[nm + 1 + ne] = 0;
+    return nm + 1 + ne;
 }
 
-std::string fmt_identity(double idy) {  // lib/fsearch.py:3235-3237
-    std::string s = std::isnan(idy) ? std::string("nan") : six(idy);
-    size_t dot = s.find('.');
-    s.resize(std::min(s.size(), dot == std::string::npos ? (size_t)2 : dot + 3));
-    return s;
+int fmt_identity_to(char *out, double idy) {  // lib/fsearch.py:3235-3237
+    int n;
+    if (std::isnan(idy)) {
+        memcpy(out, "nan", 4);
+        n = 3;
+    } else
+        n = six_to(out, idy);
+    const char *dot = (const char *)memchr(out, '.', (size_t)n);
+    n = std::min(n, dot ? (int)(dot - out) + 3 : 2);
+    out[n] = 0;
+    return n;
+}
+
+std::string f2s(double e) {
+    char b[400];
+    const int n = f2s_to(b, e);
+    return std::string(b, (size_t)n);
+}
+
+std::string fmt_identity(double idy) {
+    char b[400];
+    const int n = fmt_identity_to(b, idy);
+    return std::string(b, (size_t)n);
 }
 
 }  // namespace so
