@@ -226,7 +226,7 @@ int build_chunk_index(so_ctx *c, ChunkIndex &ix) {
                             c->stream));
     SO_CUDA(cudaMalloc((void **)&ix.d_start, ((size_t)P.nc + 1) * sizeof(uint32_t)));
     SO_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    std::vector<uint32_t> h_keys;
+    std::vector<uint32_t> h_counts;  // sizes of the non-empty buckets, in bucket order
     if (nslots > 0) {
         if ((rc = c->scratch[4].reserve((size_t)nslots * 4)) != SO_OK) return rc;
         if ((rc = c->scratch[5].reserve((size_t)nslots * 4)) != SO_OK) return rc;
@@ -247,13 +247,35 @@ int build_chunk_index(so_ctx *c, ChunkIndex &ix) {
         c->stats.kernel_launches += 2;
         c->stats.lib_launches += 1;
         SO_CUDA(cudaGetLastError());
-        h_keys.resize(nslots);
-        SO_CUDA(cudaMemcpyAsync(h_keys.data(), k_out, (size_t)nslots * 4, cudaMemcpyDeviceToHost, c->stream));
+        // bucket sizes: run lengths of the sorted keys (library), so only the ~4*10^5 non-empty bucket counts travel to
+        // the host instead of all keys; invalid slots carry key NC and form the last run
+        uint32_t *d_uniq = k_in, *d_runs = v_in;                 // (free after the sort)
+        uint32_t *d_nruns = (uint32_t *)c->scratch[11].p;
+        {
+            size_t t2 = 0;
+            cub::DeviceRunLengthEncode::Encode(nullptr, t2, k_out, d_uniq, d_runs, d_nruns, (int)nslots, c->stream);
+            if ((rc = c->scratch[10].reserve(t2 + 16)) != SO_OK) return rc;
+            if ((rc = c->scratch[11].reserve(std::max<size_t>(tmp, 64))) != SO_OK) return rc;
+            d_nruns = (uint32_t *)c->scratch[11].p;
+            SO_CUDA(cub::DeviceRunLengthEncode::Encode(c->scratch[10].p, t2, k_out, d_uniq, d_runs, d_nruns, (int)nslots, c->stream));
+            c->stats.lib_launches += 1;
+        }
+        uint32_t nruns = 0;
+        SO_CUDA(cudaMemcpyAsync(&nruns, d_nruns, 4, cudaMemcpyDeviceToHost, c->stream));
         SO_CUDA(cudaStreamSynchronize(c->stream));
-        c->stats.d2h_bytes += (i64)nslots * 4;
-        uint32_t nseeds = 0;
-        while (nseeds < nslots && h_keys[nseeds] < P.nc) nseeds++;  // invalid slots carry key NC and sort last
-        // (linear scan is fine: it also feeds the threshold below)
+        h_counts.resize(nruns);
+        uint32_t last_key = 0;
+        if (nruns) {
+            SO_CUDA(cudaMemcpyAsync(h_counts.data(), d_runs, (size_t)nruns * 4, cudaMemcpyDeviceToHost, c->stream));
+            SO_CUDA(cudaMemcpyAsync(&last_key, d_uniq + (nruns - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+            SO_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        c->stats.d2h_bytes += (i64)nruns * 4 + 8;
+        uint32_t nseeds = nslots;
+        if (nruns && last_key >= P.nc) {                         // the run of the invalid slots
+            nseeds -= h_counts.back();
+            h_counts.pop_back();
+        }
         ix.n_seeds = nseeds;
         if (nseeds > 0) {
             SO_CUDA(cudaMalloc((void **)&ix.d_locus, (size_t)nseeds * sizeof(uint32_t)));
@@ -277,14 +299,8 @@ int build_chunk_index(so_ctx *c, ChunkIndex &ix) {
     // at 1, sequential double accumulation; threshold = int(mu + 2 sd) (fsearch.py:2248-2250)
     {
         double N = 1, mu = 0.;
-        std::vector<uint32_t> counts;
-        for (uint32_t p = 0; p < ix.n_seeds;) {
-            uint32_t q = p + 1;
-            while (q < ix.n_seeds && h_keys[q] == h_keys[p]) q++;
-            counts.push_back(q - p);
-            ix.max_bucket = std::max<uint32_t>(ix.max_bucket, q - p);
-            p = q;
-        }
+        const std::vector<uint32_t> &counts = h_counts;
+        for (uint32_t v : counts) ix.max_bucket = std::max<uint32_t>(ix.max_bucket, v);
         for (uint32_t v : counts) mu += (double)v, N += 1;
         mu /= N;
         double sd = 0.;
