@@ -14,14 +14,14 @@
 //     on 2*10^5 random ranges with heavy ties, tests/test_oracle_golden.py::test_parallel_hoare_formula);
 //   * only ranges that intersect [0, need) are refined (the others cannot influence that prefix), like the
 //     host's quicksort_pruned.
-// One CTA per query: ranges above kSmall elements are partitioned by the whole CTA in global memory (stopper
+// One CTA per query: ranges above kSmall (512) elements are partitioned by the whole CTA in global memory (stopper
 // lists by ballot + prefix over the warps), smaller ranges are handed to single warps that finish the whole
 // sub-tree in shared memory.  Only the selected <= vmax candidates per query go back to the host.
 #include "context.h"
 
 namespace so {
 
-enum { kSelThreads = 256, kSelWarps = 8, kSmall = 1024, kBigStack = 64, kSmallList = 256, kWarpStack = 48 };
+enum { kSelThreads = 256, kSelWarps = 8, kSmall = 512, kBigStack = 64, kSmallList = 256, kWarpStack = 48 };
 constexpr double kPivotFracD = 0.3745401188473625;  // random() after init_genrand(42)
 
 struct SelSmem {
@@ -365,7 +365,7 @@ int BlockStore::prepare(so_ctx *c, i64 nq_, size_t capq_, int vmax_, cudaStream_
     if ((rc = sel_attrs(c->device)) != SO_OK) return rc;
     if ((rc = vals.reserve((size_t)nq * capq)) != SO_OK) return rc;
     if ((rc = count.reserve((size_t)nq + 8)) != SO_OK) return rc;
-    grid = 148 * 2;
+    grid = 148 * 4;  // 54 KB of shared memory per CTA: four resident CTAs per SM
     if ((i64)grid > nq) grid = (int)std::max<i64>(nq, 1);
     if ((rc = keys.reserve((size_t)grid * capq)) != SO_OK) return rc;
     if ((rc = la.reserve((size_t)grid * capq)) != SO_OK) return rc;
