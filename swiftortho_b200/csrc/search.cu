@@ -1226,9 +1226,29 @@ __device__ __forceinline__ void ung_steps16(int &v, int &d, int &alive, int one,
 }
 #undef SO_XS
 
-enum { kXdBuf = 48, kXdBufBytes = 16 * kXdBuf * (8 + 2) + 16 * 32 };  // per-warp record buffer of k_xdrop<FAST> (16 warps per CTA)
+enum { kXdBuf = 48, kXdBufBytes = 16 * kXdBuf * (8 + 2) + 16 * 32 };
+// the staging buffers are addressed with 32-bit shared-window addresses (generic 64-bit pointer arithmetic on them
+// cost 2.4 % of the kernel's instructions)
+__device__ __forceinline__ void sts_u64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint64_t lds_u64(uint32_t a) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}  // per-warp record buffer of k_xdrop<FAST> (16 warps per CTA)
 // warp-collective: the staged records go to their queries' regions, one global atomic per query present
-__device__ __forceinline__ void xd_flush(const uint64_t *wrec, const uint16_t *wqi, int cnt, uint64_t *__restrict__ creg,
+__device__ __forceinline__ void xd_flush(uint32_t wrec, uint32_t wqi, int cnt, uint64_t *__restrict__ creg,
                                          size_t ccap, uint32_t *__restrict__ qcount, uint32_t *__restrict__ flags) {
     const int lane = threadIdx.x & 31;
     for (int i0 = 0; i0 < cnt; i0 += 32) {
@@ -1236,8 +1256,8 @@ __device__ __forceinline__ void xd_flush(const uint64_t *wrec, const uint16_t *w
         const bool v = i < cnt;
         const unsigned act = __ballot_sync(0xffffffffu, v);
         if (v) {
-            const uint64_t r = wrec[i];
-            const uint32_t q = wqi[i];
+            const uint64_t r = lds_u64(wrec + 8u * (uint32_t)i);
+            const uint32_t q = lds_u16(wqi + 2u * (uint32_t)i);
             const unsigned peers = __match_any_sync(act, q);
             const int leader = __ffs(peers) - 1;
             uint32_t base = 0;
@@ -1275,10 +1295,11 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
     // in their query's region; records are staged per warp in shared memory and flushed kXdBuf / 3 at a time, so
     // a warp issues one global atomic per ~30 records instead of one per passing group (consecutive groups belong
     // to the same query: per-group atomics would serialise on one address)
-    uint64_t *wrec = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_tab) + kUngTabBytes) + (threadIdx.x >> 5) * kXdBuf;
-    uint16_t *wqi = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(s_tab) + kUngTabBytes + (blockDim.x >> 5) * kXdBuf * 8) +
-                    (threadIdx.x >> 5) * kXdBuf;
-    uint8_t *widx = reinterpret_cast<uint8_t *>(s_tab) + kUngTabBytes + (blockDim.x >> 5) * kXdBuf * 10 + (threadIdx.x >> 5) * 32;
+    // (recomputed where they are used, in the service block only: holding them costs registers in the step loop)
+#define XD_SBASE ((uint32_t)__cvta_generic_to_shared(s_tab) + (uint32_t)kUngTabBytes)
+#define XD_WREC (XD_SBASE + (threadIdx.x >> 5) * (kXdBuf * 8u))
+#define XD_WQI (XD_SBASE + 16u * (kXdBuf * 8u) + (threadIdx.x >> 5) * (kXdBuf * 2u))
+#define XD_WIDX (XD_SBASE + 16u * (kXdBuf * 10u) + (threadIdx.x >> 5) * 32u)
     int wcount = 0;  // warp-uniform
     for (int k = threadIdx.x; k < kUngRows * 32 * 32; k += blockDim.x) {
         const int e = k >> 5, ct = e >> 5, cq = e & 31;
@@ -1380,13 +1401,14 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                         const uint32_t cid = cellid[gi], key = ssub[gi];
                         const uint32_t rk = ((key & qmask) << diag_bits) | ((key & ~kHeadBit) >> qst_bits);
                         const int slot = wcount + __popc(pm & ((1u << lane) - 1u));
-                        wrec[slot] = ((uint64_t)(cid & 0xffffu) << (qst_bits + diag_bits + 20)) | ((uint64_t)rk << 20) | (uint64_t)(uint32_t)acc;
-                        wqi[slot] = (uint16_t)(cid >> 16);
+                        sts_u64(XD_WREC + 8u * (uint32_t)slot,
+                                ((uint64_t)(cid & 0xffffu) << (qst_bits + diag_bits + 20)) | ((uint64_t)rk << 20) | (uint64_t)(uint32_t)acc);
+                        sts_u16(XD_WQI + 2u * (uint32_t)slot, cid >> 16);
                     }
                     wcount += __popc(pm);
                     __syncwarp();
                     if (wcount > kXdBuf - 32) {
-                        xd_flush(wrec, wqi, wcount, creg, ccap, qcount, flags);
+                        xd_flush(XD_WREC, XD_WQI, wcount, creg, ccap, qcount, flags);
                         wcount = 0;
                     }
                 }
@@ -1421,12 +1443,12 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                     const bool head = ds.x != kDescSkipX;
                     const unsigned hm = __ballot_sync(0xffffffffu, head);
                     const int nh = __popc(hm), nn = __popc(need);
-                    if (head) widx[__popc(hm & ((1u << lane) - 1u))] = (uint8_t)lane;
+                    if (head) sts_u8(XD_WIDX + (uint32_t)__popc(hm & ((1u << lane) - 1u)), (uint32_t)lane);
                     __syncwarp();
                     const int nr = __popc(need & ((1u << lane) - 1u));
                     const bool take = needer && nr < nh;
-                    const int src = take ? (int)widx[nr] : lane;
-                    const uint32_t adv = nh <= nn ? min(32u, pool_end - pool_next) : (uint32_t)widx[nn - 1] + 1u;
+                    const int src = take ? (int)lds_u8(XD_WIDX + (uint32_t)nr) : lane;
+                    const uint32_t adv = nh <= nn ? min(32u, pool_end - pool_next) : lds_u8(XD_WIDX + (uint32_t)(nn - 1)) + 1u;
                     const uint32_t dx = __shfl_sync(0xffffffffu, ds.x, src), dy = __shfl_sync(0xffffffffu, ds.y, src);
                     __syncwarp();
                     if (take) {
@@ -1550,11 +1572,15 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
     nmulti = __reduce_add_sync(0xffffffffu, nmulti);
     if (lane == 0 && nmulti) atomicAdd(counters + 3, (unsigned long long)nmulti);  // statistic
     if (FAST) {
-        if (wcount) xd_flush(wrec, wqi, wcount, creg, ccap, qcount, flags);
+        if (wcount) xd_flush(XD_WREC, XD_WQI, wcount, creg, ccap, qcount, flags);
         ngroups = __reduce_add_sync(0xffffffffu, ngroups);
         if (lane == 0 && ngroups) atomicAdd(counters + 4, (unsigned long long)ngroups);  // statistic: diagonal groups
     }
 }
+#undef XD_SBASE
+#undef XD_WREC
+#undef XD_WQI
+#undef XD_WIDX
 
 // Pair selection over the PASSING groups only (score >= 25, self.min: fsearch.py:2224, 2707): `plist` holds
 // their group indices in ascending order (ordered stream compaction, cub::DeviceSelect), ~8 % of all groups.
