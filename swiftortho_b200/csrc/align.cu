@@ -199,6 +199,8 @@ __global__ void __launch_bounds__(128) k_banded_dp(const AlnTask *__restrict__ t
     }
 }
 
+// WAVE = the trace layout of k_banded_dp_wave: per task, words [row block of 16][lane h], 4 bits per row
+template <bool WAVE>
 __global__ void __launch_bounds__(128) k_traceback(const AlnTask *__restrict__ tasks, int n,
                                                    const uint64_t *__restrict__ warp_base,
                                                    const uint64_t *__restrict__ trace,
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(128) k_traceback(const AlnTask *__restrict__ t
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const AlnTask tk = tasks[t];
-    const uint64_t *tr = trace + warp_base[t >> 5] + (threadIdx.x & 31);
+    const uint64_t *tr = WAVE ? trace + warp_base[t] : trace + warp_base[t >> 5] + (threadIdx.x & 31);
     int i = dp[t].imax, j = dp[t].jmax;
     int al = 0, nid = 0, mis = 0, gap = 0, bad = 0;
     int run_type = 0, run_len = 0;  // 2: trace '-', 1: trace '|'
@@ -224,11 +226,20 @@ __global__ void __launch_bounds__(128) k_traceback(const AlnTask *__restrict__ t
                 bad = 1;
                 break;
             }
-            if (i != cached_row) {
-                word = tr[(size_t)(i - 1) * 32];
-                cached_row = i;
+            if (WAVE) {
+                const int key = ((i - 1) >> 4) * 16 + (d >> 1);  // (row block, lane)
+                if (key != cached_row) {
+                    word = tr[key];
+                    cached_row = key;
+                }
+                code = (int)((word >> (4 * ((i - 1) & 15) + 2 * (d & 1))) & 3);
+            } else {
+                if (i != cached_row) {
+                    word = tr[(size_t)(i - 1) * 32];
+                    cached_row = i;
+                }
+                code = (int)((word >> (2 * d)) & 3);
             }
-            code = (int)((word >> (2 * d)) & 3);
         }
         if (code == 0) break;
         al++;
@@ -260,6 +271,119 @@ __global__ void __launch_bounds__(128) k_traceback(const AlnTask *__restrict__ t
     TbOut o;
     o.i0 = i, o.j0 = j, o.al = al, o.nid = nid, o.mis = mis, o.gap = gap, o.bad = bad, o.pad = 0;
     out[t] = o;
+}
+
+// -----------------------------------------------------------------------------------------------
+// k_banded_dp_wave: the same recurrence with 16 LANES per alignment, for launches too small to fill the GPU with one
+// thread per alignment (an alignment round of the search pipeline carries ~2*10^4 tasks = 4 warps per SM for
+// k_banded_dp, whose cell chain is latency bound at that occupancy).
+//
+// Lane h of a half-warp owns band columns d = 2h and 2h + 1.  Cell (i, d) needs (i, d-1) [I], (i-1, d) [M] and
+// (i-1, d+1) [D]; with row i = T - h at macro-step T every lane computes its two cells per macro-step:
+//   sub-step 0: (i, 2h)   I <- lane h-1's cell (i, 2h-1), computed at macro-step T-1 (shuffle up, left guard for h = 0)
+//                         M, D <- own cells of row i-1 (macro-step T-1)
+//   sub-step 1: (i, 2h+1) I <- own cell of sub-step 0;  M <- own;  D <- lane h+1's cell (i-1, 2h+2), computed in
+//                         sub-step 0 of THIS macro-step (shuffle down, right-of-band constant for h = 15)
+// so all 16 lanes are busy from macro-step 16 on (pipeline fill / drain: 15 macro-steps per alignment).  Cells are the
+// packed values of k_banded_dp (score * 4 + trace code, DPX max3.relu, PRMT-looked-up gap adjustments); cells outside
+// the matrix evaluate to 0, which reproduces the guard cells.  "First strict maximum in row-major order"
+// (fsearch.py:1401): every lane keeps its own first maximum (its cells come in row-major order), the 16 lanes are
+// reduced on (score desc, row asc, column asc).  Trace: 4 bits per lane and row, 16 rows per 64-bit word, words laid out
+// [row block][lane] (one 128-byte line per half-warp and 16 rows); k_traceback<true> reads that layout.
+// -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_banded_dp_wave(const AlnTask *__restrict__ tasks, int n,
+                                                        const uint64_t *__restrict__ task_base,
+                                                        uint64_t *__restrict__ trace, DpOut *__restrict__ out, uint32_t ksel) {
+    __shared__ __align__(256) int8_t s_tbl4[kClasses * 256];
+    __shared__ uint8_t s_code[256];
+    for (int k = threadIdx.x; k < kClasses * kClasses; k += blockDim.x)
+        s_tbl4[(k / kClasses) * 256 + (k % kClasses)] = (int8_t)(4 * c_score[k]);
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_code[k] = c_code[k];
+    __syncthreads();
+    const uint32_t tblbase = (uint32_t)__cvta_generic_to_shared(s_tbl4);
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;  // one task per 16 lanes
+    const int h = threadIdx.x & 15;
+    const bool active = t < n;
+    AlnTask tk;
+    if (active)
+        tk = tasks[t];
+    else {
+        tk.s0 = tk.s1 = nullptr;
+        tk.len0 = tk.len1 = 0;
+    }
+    const int len0 = tk.len0;
+    const int nrows = active ? min(tk.len1, len0 + 16) : 0;
+    int wsteps = nrows ? nrows + 15 : 0;  // macro-steps of this alignment; the warp runs the longer of its two
+    wsteps = max(wsteps, __shfl_xor_sync(0xffffffffu, wsteps, 16));
+    uint64_t *tr = active ? trace + task_base[t] + h : trace;
+    const uint32_t KI = 42u | (43u << 8) | (4u << 16) | (45u << 24);
+    const uint32_t KD = 43u | (4u << 8) | (45u << 16) | (46u << 24);
+    // state of the lane's two columns after the previous row (row 0: score 0, not extendable)
+    int S3A = 3, S3B = 3, DcB = -43;  // DcB: vertical candidate of (i-1, 2h+1), used by cell A of row i
+    int IpB = -42;                    // horizontal candidate of the lane's cell B of row i, wanted by lane h+1 next macro-step
+    int best3 = 3, besti = 0, bestd = 0;
+    uint64_t acc = 0;
+    // column residues: cell A faces s0[i + 2h - 17], cell B faces s0[i + 2h - 16]; with i = T - h: s0[T + h - 17 (+1)]
+    int cA = 0;
+    {
+        const int j0 = 1 + h - 17;  // macro-step T = 1
+        cA = (active && j0 >= 0 && j0 < len0) ? s_code[tk.s0[j0]] : 0;
+    }
+    for (int T = 1; T <= wsteps; T++) {
+        const int i = T - h;
+        const bool vrow = i >= 1 && i <= nrows;
+        const int jb = T + h - 16;  // index into s0 of cell B's residue (= j - 1)
+        const int cB = (active && jb >= 0 && jb < len0) ? (int)s_code[tk.s0[jb]] : 0;
+        const uint32_t rowbase = tblbase + (vrow ? (uint32_t)s_code[tk.s1[i - 1]] << 8 : 0u);
+        // ---- sub-step 0: cell (i, 2h);  j = i + 2h - 16
+        int IpA = __shfl_up_sync(0xffffffffu, IpB, 1, 16);
+        if (h == 0) IpA = -42;
+        const int jA = i + 2 * h - 16;
+        const int MpA = S3A + lds_s8(rowbase + (uint32_t)cA);
+        int PA = __vimax3_s32_relu(IpA, MpA, DcB);
+        if (!(vrow && jA >= 1 && jA <= len0)) PA = 0;
+        const uint32_t tselA = ((uint32_t)PA & 3u) | ksel;
+        const int IpFromA = PA - (int)prmt_u32(KI, 0u, tselA);
+        const int DcFromA = PA - (int)prmt_u32(KD, 0u, tselA);
+        // ---- sub-step 1: cell (i, 2h + 1); its vertical neighbour (i-1, 2h+2) is lane h+1's cell A of this macro-step
+        int DcN = __shfl_down_sync(0xffffffffu, DcFromA, 1, 16);
+        if (h == 15) DcN = -43;
+        const int MpB = S3B + lds_s8(rowbase + (uint32_t)cB);
+        int PB = __vimax3_s32_relu(IpFromA, MpB, DcN);
+        if (!(vrow && jA + 1 >= 1 && jA + 1 <= len0)) PB = 0;
+        const uint32_t tselB = ((uint32_t)PB & 3u) | ksel;
+        IpB = PB - (int)prmt_u32(KI, 0u, tselB);
+        DcB = PB - (int)prmt_u32(KD, 0u, tselB);
+        S3A = PA | 3, S3B = PB | 3;
+        if (vrow) {
+            // first strict maximum, row-major inside the lane: (i, 2h) before (i, 2h+1), rows ascending
+            if (S3A > best3) best3 = S3A, besti = i, bestd = 2 * h;
+            if (S3B > best3) best3 = S3B, besti = i, bestd = 2 * h + 1;
+            const uint32_t nib = ((uint32_t)PA & 3u) | (((uint32_t)PB & 3u) << 2);
+            const int r = (i - 1) & 15;
+            acc |= (uint64_t)nib << (4 * r);
+            if (r == 15 || i == nrows) {
+                tr[(size_t)((i - 1) >> 4) * 16] = acc;
+                acc = 0;
+            }
+        }
+        cA = cB;  // next macro-step: cell A faces this macro-step's cell B residue
+    }
+    // reduce the 16 lanes: score desc, row asc, column asc
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        const int b3 = __shfl_xor_sync(0xffffffffu, best3, o, 16), bi = __shfl_xor_sync(0xffffffffu, besti, o, 16);
+        const int bd = __shfl_xor_sync(0xffffffffu, bestd, o, 16);
+        if (b3 > best3 || (b3 == best3 && (bi < besti || (bi == besti && bd < bestd)))) best3 = b3, besti = bi, bestd = bd;
+    }
+    if (active && h == 0) {
+        DpOut o;
+        o.score = best3 >> 2;
+        o.imax = o.score > 0 ? besti : 0;
+        o.jmax = o.score > 0 ? (besti + bestd - 16) : 0;
+        o.rows = nrows;
+        out[t] = o;
+    }
 }
 
 // cells the reference fills for (len0, len1): rows i = 1..l1-1, columns [max(1,i-16), min(i+16,l0))
@@ -357,18 +481,29 @@ int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
         });
     std::vector<AlnTask> sorted((size_t)n);
     for (i64 k = 0; k < n; k++) sorted[(size_t)k] = tasks[(size_t)order[(size_t)k]];
+    // small launches (alignment rounds of the search) use the 16-lanes-per-alignment kernel; SO_DP_WAVE=0/1 forces
+    i64 wave_below = 60000;
+    if (const char *e = getenv("SO_DP_WAVE")) wave_below = atoi(e) ? (i64)1 << 40 : 0;
+    const bool wave = n < wave_below;
     const i64 nwarps = (n + 31) / 32;
-    const i64 nwarps_pad = ((n + 127) / 128) * 4;
+    const i64 nwarps_pad = wave ? n : ((n + 127) / 128) * 4;  // wave: one base per TASK
     std::vector<uint64_t> wbase((size_t)nwarps_pad + 1, 0);
     i64 cells = 0;
-    for (i64 w = 0; w < nwarps_pad; w++) {
-        int rows = 0;
-        for (i64 k = w * 32; k < std::min<i64>(n, w * 32 + 32); k++) {
+    if (wave) {
+        for (i64 k = 0; k < n; k++) {
             const AlnTask &t = sorted[(size_t)k];
-            rows = std::max(rows, std::min(t.len1, t.len0 + 16));
+            const int rows = std::min(t.len1, t.len0 + 16);
+            wbase[(size_t)k + 1] = wbase[(size_t)k] + (uint64_t)((rows + 15) / 16) * 16;
         }
-        wbase[(size_t)w + 1] = wbase[(size_t)w] + (uint64_t)rows * 32;
-    }
+    } else
+        for (i64 w = 0; w < nwarps_pad; w++) {
+            int rows = 0;
+            for (i64 k = w * 32; k < std::min<i64>(n, w * 32 + 32); k++) {
+                const AlnTask &t = sorted[(size_t)k];
+                rows = std::max(rows, std::min(t.len1, t.len0 + 16));
+            }
+            wbase[(size_t)w + 1] = wbase[(size_t)w] + (uint64_t)rows * 32;
+        }
     (void)nwarps;
     size_t need_trace = (size_t)wbase[(size_t)nwarps_pad] + 64;
     int rc;
@@ -386,9 +521,15 @@ int align_pairs(so_ctx *c, const so_pair *pairs, i64 n, so_aln *out) {
     SO_CUDA(cudaMemcpyAsync(d_wb, wbase.data(), b_wb, cudaMemcpyHostToDevice, c->stream_aln));
     const int grid = (int)((n + 127) / 128);
     SO_CUDA(cudaEventRecord(c->ev_aln[0], c->stream_aln));
-    k_banded_dp<<<grid, 128, 0, c->stream_aln>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp, 0x4440u);
+    if (wave)
+        k_banded_dp_wave<<<(int)((n * 16 + 127) / 128), 128, 0, c->stream_aln>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp, 0x4440u);
+    else
+        k_banded_dp<<<grid, 128, 0, c->stream_aln>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp, 0x4440u);
     SO_CUDA(cudaEventRecord(c->ev_aln[1], c->stream_aln));
-    k_traceback<<<grid, 128, 0, c->stream_aln>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp, d_tb);
+    if (wave)
+        k_traceback<true><<<grid, 128, 0, c->stream_aln>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp, d_tb);
+    else
+        k_traceback<false><<<grid, 128, 0, c->stream_aln>>>(d_tasks, (int)n, d_wb, c->trace.p, d_dp, d_tb);
     SO_CUDA(cudaEventRecord(c->ev_aln[2], c->stream_aln));
     SO_CUDA(cudaGetLastError());
     std::vector<DpOut> h_dp((size_t)n);
