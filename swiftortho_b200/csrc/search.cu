@@ -1945,12 +1945,15 @@ static_assert(SC_COUNT_ <= 64, "scratch slots");
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
 
 static int g_xdrop_refill = 24;
+static int g_xdrop_ctas = 2;  // resident k_xdrop<FAST> CTAs per SM (SO_XDROP_CTAS: tuning hook; 1 leaves half the SM to the other lane's kernels)
 static uint32_t g_cell_max = kCellMax;  // cells above this many hits send the block to the general path (SO_CELL_MAX: test hook)
 static uint32_t g_cell_split = 0;  // target ranges per query in the cell passes; 0 = as few as fit shared memory (SO_CELL_SPLIT)  // idle lanes that trigger a refill in k_xdrop (SO_XDROP_REFILL: tuning hook)
 
 int upload_search_config(so_ctx *c) {
     const char *e = getenv("SO_XDROP_REFILL");
     g_xdrop_refill = e ? atoi(e) : 24;
+    g_xdrop_ctas = 2;
+    if (const char *xc = getenv("SO_XDROP_CTAS")) g_xdrop_ctas = std::max(1, std::min(2, atoi(xc)));
     g_cell_split = 0;
     if (const char *cs = getenv("SO_CELL_SPLIT")) g_cell_split = (uint32_t)std::max(0, std::min(8, atoi(cs)));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
@@ -2515,7 +2518,7 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
             k_cell_block<<<148 * 2, 512, sizeof(CellBlockSmem), st>>>(d_cloc, d_ubase, d_blist, d_lcount, NB, NBh, nsplit, g, c->d_qoff,
                                                                      c->d_toff, qa, d_sub, d_ssub, d_desc, d_cellid, d_flags);
             stamp();
-            kx<<<148 * 2, 512, kUngTabBytes + kXdBufBytes, st>>>(d_desc, 0u, d_ssub, nullptr, nullptr, 0u, nullptr, g.qst_bits,
+            kx<<<148 * g_xdrop_ctas, 512, kUngTabBytes + kXdBufBytes, st>>>(d_desc, 0u, d_ssub, nullptr, nullptr, 0u, nullptr, g.qst_bits,
                                                                 (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
                                                                 (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
                                                                 qoff2[1], (uint32_t)Lq64, nullptr, nullptr, d_ctl, 1, d_cellid,
