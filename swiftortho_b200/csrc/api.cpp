@@ -187,8 +187,9 @@ int so_ctx_create(int device, const so_params *p, so_ctx **out) {
     c->P = P;
     SO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SO_CUDA(cudaStreamCreateWithFlags(&c->stream_aln, cudaStreamNonBlocking));
-    SO_CUDA(cudaStreamCreateWithFlags(&c->stream1, cudaStreamNonBlocking));
-    for (auto &e : c->ev1) SO_CUDA(cudaEventCreate(&e));
+    for (auto &st : c->stream_x) SO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto &evs : c->ev_x)
+        for (auto &e : evs) SO_CUDA(cudaEventCreate(&e));
     for (auto &e : c->ev) SO_CUDA(cudaEventCreate(&e));
     for (auto &e : c->ev_aln) SO_CUDA(cudaEventCreate(&e));
     if ((rc = so::upload_tables()) != SO_OK) {
@@ -204,10 +205,13 @@ void so_ctx_destroy(so_ctx *c) {
     cudaSetDevice(c->device);
     for (auto &ix : c->chunks) so::free_chunk_index(ix);
     for (auto &s : c->scratch) s.release();
-    for (auto &s : c->scratch1) s.release();
-    for (auto &e : c->ev1)
-        if (e) cudaEventDestroy(e);
-    if (c->stream1) cudaStreamDestroy(c->stream1);
+    for (auto &sx : c->scratch_x)
+        for (auto &s : sx) s.release();
+    for (auto &evs : c->ev_x)
+        for (auto &e : evs)
+            if (e) cudaEventDestroy(e);
+    for (auto &st : c->stream_x)
+        if (st) cudaStreamDestroy(st);
     c->trace.release();
     if (c->d_tres) cudaFree(c->d_tres);
     if (c->d_qres) cudaFree(c->d_qres);
@@ -220,7 +224,7 @@ void so_ctx_destroy(so_ctx *c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &pc : c->cand_pool) pc.release();
     for (auto &b : c->bstore) b.release();
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < so_ctx::kMaxSlots; k++) {
         if (c->h_sel[k]) cudaFreeHost(c->h_sel[k]);
         if (c->h_sel_n[k]) cudaFreeHost(c->h_sel_n[k]);
     }
@@ -489,10 +493,10 @@ int so_set_sub_block(so_ctx *c, int64_t n) {
     return SO_OK;
 }
 
-// test / tuning hook: number of candidate-production lanes used by so_search (1 or 2; default 2).  bench.py
-// uses 1 to time the kernels of a step without a second stream sharing the GPU.
+// test / tuning hook: number of candidate-production lanes used by so_search (1 .. 4; default 2; 0 = measurement
+// mode).  bench.py uses 0 to time the kernels of a step without another stream sharing the GPU.
 int so_set_lanes(so_ctx *c, int n) {
-    if (!c || n < 0 || n > 2) return SO_EINVAL;
+    if (!c || n < 0 || n > so_ctx::kMaxLanes) return SO_EINVAL;
     c->n_lanes = n;
     return SO_OK;
 }
@@ -517,14 +521,15 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     // query block size: the candidates of a block live in per-query device lists (select.cu)
     i64 QB = 512;
     if (const char *e = getenv("SO_QUERY_BLOCK")) QB = std::max<i64>(16, atoll(e));  // tuning hook
-    const int kSlots = 4;
+    const int nprod = std::max(1, std::min<int>(c->n_lanes, so_ctx::kMaxLanes));
+    const int kSlots = 2 * nprod;  // a lane produces block k + nprod while the worker still orders block k
     // at most one candidate per (query, target): fixed per-query capacity of the device lists
     i64 capq = 0;
     for (const auto &ix : c->chunks) capq += ix.c1 - ix.c0;
     capq = std::max<i64>(capq, 1);
     // keep one lane's lists within ~6 GB (512 queries against up to 1.4 M targets)
     QB = std::max<i64>(16, std::min<i64>(QB, (i64)(6000000000ll / (capq * 8))));
-    if (c->cand_pool.size() < 2) c->cand_pool.resize(2);
+    if (c->cand_pool.size() < (size_t)so_ctx::kMaxLanes) c->cand_pool.resize((size_t)so_ctx::kMaxLanes);
     {
         int rc = so::upload_search_config(c);
         if (rc != SO_OK) return rc;
@@ -540,14 +545,13 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     std::condition_variable cv;
     std::map<int, Job> jobs;  // by block number
     int next_blk = 0;         // next block the worker consumes
-    const int nprod = c->n_lanes >= 2 ? 2 : 1;
     // n_lanes == 0: measurement mode: one lane, and candidate production and alignment rounds never share the GPU, so
     // the CUDA-event durations of the kernels are not inflated by kernels of the other stage
     const bool serial = c->n_lanes == 0;
     std::mutex gpu_mu;
     int producers_left = nprod;
     bool abort_all = false;
-    bool producer_done = false, slot_busy[kSlots] = {false, false, false, false};
+    bool producer_done = false, slot_busy[so_ctx::kMaxSlots] = {};
     int worker_rc = SO_OK;
     std::string worker_err;
     so_stats wstats;
@@ -818,8 +822,8 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             }
         }
     });
-    int prod_rcs[2] = {SO_OK, SO_OK};
-    std::string prod_errs[2];
+    int prod_rcs[so_ctx::kMaxLanes] = {};
+    std::string prod_errs[so_ctx::kMaxLanes];
     auto produce = [&](int pid) {
         cudaSetDevice(c->device);
         int rc = SO_OK;
@@ -839,7 +843,7 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
             Timer tc;
             std::unique_lock<std::mutex> gl(gpu_mu, std::defer_lock);
             if (serial) gl.lock();
-            cudaStream_t st = pid ? c->stream1 : c->stream;
+            cudaStream_t st = c->lane_stream(pid);
             so::BlockStore &bs = c->bstore[pid];
             const i64 nqb = b1 - b0;
             rc = bs.prepare(c, nqb, (size_t)capq, (int)selcap, st);
@@ -924,12 +928,14 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
         if (--producers_left == 0) producer_done = true;
         cv.notify_all();
     };
-    std::thread producer1;
-    if (nprod == 2) producer1 = std::thread(produce, 1);
+    std::vector<std::thread> producers;
+    for (int pid = 1; pid < nprod; pid++) producers.emplace_back(produce, pid);
     produce(0);
-    if (nprod == 2) producer1.join();
-    const int prod_rc = prod_rcs[0] != SO_OK ? prod_rcs[0] : prod_rcs[1];
-    const std::string prod_err = prod_rcs[0] != SO_OK ? prod_errs[0] : prod_errs[1];
+    for (auto &t : producers) t.join();
+    int prod_rc = SO_OK;
+    std::string prod_err;
+    for (int pid = 0; pid < nprod && prod_rc == SO_OK; pid++)
+        if (prod_rcs[pid] != SO_OK) prod_rc = prod_rcs[pid], prod_err = prod_errs[pid];
     worker.join();
     c->stats.ms_host += wstats.ms_host;
     c->stats.queries += wstats.queries;

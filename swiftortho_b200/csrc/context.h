@@ -163,14 +163,20 @@ struct so_ctx {
     so::DBuf<uint8_t> scratch[64];
     // second candidate-production lane (so_search runs two producer threads on alternating query blocks so
     // that one lane's host synchronisations and D2H copies overlap the other lane's kernels)
-    so::DBuf<uint8_t> scratch1[64];
-    cudaStream_t stream1 = nullptr;
-    cudaEvent_t ev1[8] = {};
-    std::vector<cudaEvent_t> ev_pool[2];
-    size_t ev_used[2] = {0, 0};      // per lane: stage events of the sync-free path, read at the end of a block
-    so_stats stats_lane[2] = {};
+    // (up to kMaxLanes lanes: lane 0 = scratch / stream / ev above, lanes 1.. = the *_x arrays; with more lanes than
+    // two, kernels of different stages -- issue-bound X-drop, latency-bound cell passes -- share the SMs more often)
+    enum { kMaxLanes = 4 };
+    so::DBuf<uint8_t> scratch_x[kMaxLanes - 1][64];
+    cudaStream_t stream_x[kMaxLanes - 1] = {};
+    cudaEvent_t ev_x[kMaxLanes - 1][8] = {};
+    so::DBuf<uint8_t> *lane_scratch(int lane) { return lane ? scratch_x[lane - 1] : scratch; }
+    cudaStream_t lane_stream(int lane) const { return lane ? stream_x[lane - 1] : stream; }
+    cudaEvent_t *lane_ev(int lane) { return lane ? ev_x[lane - 1] : ev; }
+    std::vector<cudaEvent_t> ev_pool[kMaxLanes];
+    size_t ev_used[kMaxLanes] = {};  // per lane: stage events of the sync-free path, read at the end of a block
+    so_stats stats_lane[kMaxLanes] = {};
     int n_lanes = 2;
-    double d2h_ms_lane[2] = {0, 0};
+    double d2h_ms_lane[kMaxLanes] = {};
     so::DBuf<uint64_t> trace;
     void *h_pinned = nullptr;
     size_t h_pinned_cap = 0;
@@ -179,10 +185,11 @@ struct so_ctx {
     so_stats stats_aln = {};                  // written by the alignment side only; merged by merge_align_stats
     so::HostProfile prof;
     std::vector<so::PackedCands> cand_pool;   // one pinned buffer per chunk, reused across query blocks
-    so::BlockStore bstore[2];                 // per production lane
-    uint64_t *h_sel[4] = {};                  // pinned, per pipeline slot: selected candidates of a block
-    uint32_t *h_sel_n[4] = {};
-    size_t h_sel_cap[4] = {};
+    so::BlockStore bstore[kMaxLanes];         // per production lane
+    enum { kMaxSlots = 2 * kMaxLanes };
+    uint64_t *h_sel[kMaxSlots] = {};          // pinned, per pipeline slot: selected candidates of a block
+    uint32_t *h_sel_n[kMaxSlots] = {};
+    size_t h_sel_cap[kMaxSlots] = {};
 };
 
 namespace so {

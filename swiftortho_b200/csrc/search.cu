@@ -1087,6 +1087,16 @@ __global__ void __launch_bounds__(256) k_ung_marks(const uint64_t *__restrict__ 
     dst[offR + (n - 1 - (uint32_t)x)] = (uint8_t)(kUngStop << shift);
 }
 
+// shifted copies of a view (copy s holds view[j + s * step] at j), each `stride` bytes long: with 16 copies one byte
+// apart k_xdrop<FAST> reads its query window with one 16-byte aligned load whatever the alignment of the position; with
+// 4 copies one word apart only the byte shift inside a word is left (no register multiplexing)
+__global__ void __launch_bounds__(256) k_ung_shift(const uint8_t *__restrict__ src, uint32_t total, uint8_t *__restrict__ dst,
+                                                   uint32_t stride, uint32_t step, uint8_t fill) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+    if (j >= stride) return;
+    dst[(size_t)s * stride + j] = j + s * step < total ? src[j + s * step] : fill;
+}
+
 static void ung_layout(uint32_t n, uint32_t off[2], uint32_t &total) {
     const uint32_t r = (n + 15u) & ~15u;
     off[0] = kUngPad;
@@ -1173,6 +1183,13 @@ __device__ __forceinline__ void ung_qwindow(const uint4 &a, const uint4 &b, bool
 #pragma unroll
     for (int j = 0; j < 4; j++) W[j] = __funnelshift_r(Z[j], Z[j + 1], bs8);
 }
+// the same window when the chunks come from a word-shifted copy of the view (ws = 0: only the byte shift is left)
+__device__ __forceinline__ void ung_qwindow0(const uint4 &a, const uint4 &b, uint32_t bs8, uint32_t W[4]) {
+    W[0] = __funnelshift_r(a.x, a.y, bs8);
+    W[1] = __funnelshift_r(a.y, a.z, bs8);
+    W[2] = __funnelshift_r(a.z, a.w, bs8);
+    W[3] = __funnelshift_r(a.w, b.x, bs8);
+}
 // shl.b32 clamps shift amounts above 31 (result 0), which C's << does not promise
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t x, int sh) {
     uint32_t r;
@@ -1226,7 +1243,7 @@ __device__ __forceinline__ void ung_steps16(int &v, int &d, int &alive, int one,
 }
 #undef SO_XS
 
-enum { kXdBuf = 48, kXdBufBytes = 16 * kXdBuf * (8 + 2) + 16 * 32 };
+enum { kXdBuf = 48, kXdBufBytes = 16 * kXdBuf * (8 + 2) + 16 * 32 };  // per 16 warps
 // the staging buffers are addressed with 32-bit shared-window addresses (generic 64-bit pointer arithmetic on them
 // cost 2.4 % of the kernel's instructions)
 __device__ __forceinline__ void sts_u64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
@@ -1276,8 +1293,11 @@ __device__ __forceinline__ void xd_flush(uint32_t wrec, uint32_t wqi, int cnt, u
 // FAST = the sync-free cell path: descriptors are indexed by HIT position (one per sorted hit; hits that are not the
 // head of their diagonal group carry kDescSkipX and are skipped), the number of hits comes from device memory
 // (counters[0], written by k_unit_scan) and chains walk the sorted cell-local keys `ssub` up to the next head bit.
-template <int kRefill, bool FAST>
-__global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc, uint32_t G_,
+// kWarps = warps per CTA: 16 (two CTAs per SM, each with its own score table) or 32 (one CTA per SM: one table, which
+// leaves ~100 KB of the SM to the L1 instead of 29 KB).  kQS = shifted copies of the query view (0: one view, the
+// window is multiplexed out of two aligned chunks; 4: word-shifted copies; 16: byte-shifted copies).
+template <int kRefill, bool FAST, int kWarps = 16, int kQS = 0>
+__global__ void __launch_bounds__(kWarps * 32, kWarps == 16 ? 2 : 1) k_xdrop(const uint2 *__restrict__ desc, uint32_t G_,
                                                   const uint32_t *__restrict__ ssub,
                                                   const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                   uint32_t nhits, const uint32_t *__restrict__ gheads, int qst_bits,
@@ -1287,7 +1307,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                                                   unsigned long long *__restrict__ counters, int one,
                                                   const uint32_t *__restrict__ cellid, int diag_bits,
                                                   uint64_t *__restrict__ creg, size_t ccap, uint32_t *__restrict__ qcount,
-                                                  uint32_t *__restrict__ flags) {
+                                                  uint32_t *__restrict__ flags, uint32_t qstride4) {
     extern __shared__ int s_tab[];  // [(ct << 5 | cq)][lane]; FAST: + per-warp record buffers
     const uint32_t G = FAST ? (uint32_t)counters[0] : G_;
     // FAST: groups that pass (score >= 25, self.min: fsearch.py:2224, 2707) leave one record
@@ -1298,8 +1318,8 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
     // (recomputed where they are used, in the service block only: holding them costs registers in the step loop)
 #define XD_SBASE ((uint32_t)__cvta_generic_to_shared(s_tab) + (uint32_t)kUngTabBytes)
 #define XD_WREC (XD_SBASE + (threadIdx.x >> 5) * (kXdBuf * 8u))
-#define XD_WQI (XD_SBASE + 16u * (kXdBuf * 8u) + (threadIdx.x >> 5) * (kXdBuf * 2u))
-#define XD_WIDX (XD_SBASE + 16u * (kXdBuf * 10u) + (threadIdx.x >> 5) * 32u)
+#define XD_WQI (XD_SBASE + (uint32_t)kWarps * (kXdBuf * 8u) + (threadIdx.x >> 5) * (kXdBuf * 2u))
+#define XD_WIDX (XD_SBASE + (uint32_t)kWarps * (kXdBuf * 10u) + (threadIdx.x >> 5) * 32u)
     int wcount = 0;  // warp-uniform
     for (int k = threadIdx.x; k < kUngRows * 32 * 32; k += blockDim.x) {
         const int e = k >> 5, ct = e >> 5, cq = e & 31;
@@ -1526,13 +1546,29 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 const int o = (int)(tpos & 15u);
                 const uint32_t qpos = (phase ? qoffR + (Lq - uq) : qoffF + uq) - (uint32_t)o;
                 tci = tpos >> 4;
-                qci = qpos >> 4;
-                w1 = (qpos & 4u) != 0, w2 = (qpos & 8u) != 0, bs8 = (qpos & 3u) * 8u;
                 tc = T4[tci];
-                const uint4 a = Q4[qci];
-                carry = Q4[qci + 1];
-                tci += 1, qci += 2;
-                ung_qwindow(a, carry, w1, w2, bs8, W);
+                if (kQS == 16) {
+                    // copy (qpos & 15) holds the wanted bytes 16-byte aligned: one aligned load per iteration
+                    qci = (qpos & 15u) * qstride4 + (qpos >> 4);
+                    const uint4 a = Q4[qci];
+                    W[0] = a.x, W[1] = a.y, W[2] = a.z, W[3] = a.w;
+                    tci += 1, qci += 1;
+                } else if (kQS == 4) {
+                    // copy ((qpos >> 2) & 3) holds the wanted words 16-byte aligned: only the byte shift is left
+                    qci = ((qpos >> 2) & 3u) * qstride4 + (qpos >> 4);
+                    bs8 = (qpos & 3u) * 8u;
+                    const uint4 a = Q4[qci];
+                    carry = Q4[qci + 1];
+                    tci += 1, qci += 2;
+                    ung_qwindow0(a, carry, bs8, W);
+                } else {
+                    qci = qpos >> 4;
+                    w1 = (qpos & 4u) != 0, w2 = (qpos & 8u) != 0, bs8 = (qpos & 3u) * 8u;
+                    const uint4 a = Q4[qci];
+                    carry = Q4[qci + 1];
+                    tci += 1, qci += 2;
+                    ung_qwindow(a, carry, w1, w2, bs8, W);
+                }
                 ung_mask_below(tc, o, kUngSkip);  // bytes before the start score nothing
                 if (lim < 16 - o) ung_mask_from(tc, o + lim, kUngStop);
                 lim -= 16 - o;
@@ -1552,7 +1588,7 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 ev[4 * j + 2] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xEE62u) << 4));
                 ev[4 * j + 3] = lds_s32(lanebase + (prmt_b32(W[j], tw[j], 0xFF73u) << 4));
             }
-            uint4 nq = carry;
+            uint4 nq = kQS == 16 ? make_uint4(W[0], W[1], W[2], W[3]) : carry;
             ldg128_if(tc, T4 + tci, alive);
             ldg128_if(nq, Q4 + qci, alive);
             ung_steps16(v, d, alive, one, ev);
@@ -1560,8 +1596,15 @@ __global__ void __launch_bounds__(512, 2) k_xdrop(const uint2 *__restrict__ desc
                 if (lim < 16) ung_mask_from(tc, lim, kUngStop);
             }
             lim -= 16;
-            ung_qwindow(carry, nq, w1, w2, bs8, W);
-            carry = nq;
+            if (kQS == 16) {
+                W[0] = nq.x, W[1] = nq.y, W[2] = nq.z, W[3] = nq.w;
+            } else if (kQS == 4) {
+                ung_qwindow0(carry, nq, bs8, W);
+                carry = nq;
+            } else {
+                ung_qwindow(carry, nq, w1, w2, bs8, W);
+                carry = nq;
+            }
             tci += 1, qci += 1;
         }
     }
@@ -1939,12 +1982,14 @@ static int bits_for(uint64_t maxval) {  // bits needed to hold values 0..maxval
 
 enum { SC_SLOTOFF = 12, SC_ST, SC_CNT, SC_OUT, SC_KA, SC_KB, SC_VA, SC_VB, SC_TMP, SC_CKA, SC_CKB, SC_CVA, SC_CVB, SC_MISC,
        SC_GIDX, SC_GHEAD, SC_GSCORE, SC_GRANK, SC_QUNG, SC_DESC, SC_MLIST, SC_GKEY, SC_PLIST, SC_CELLLOC, SC_UNIT, SC_SUB, SC_SSUB,
-       SC_WLIST, SC_CREG, SC_QCOUNT, SC_GBUF, SC_CTL, SC_COUNT_ };
+       SC_WLIST, SC_CREG, SC_QCOUNT, SC_GBUF, SC_CTL, SC_QSHIFT, SC_COUNT_ };
 static_assert(SC_COUNT_ <= 64, "scratch slots");
 
 static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memory: 24 B each)
 
 static int g_xdrop_refill = 24;
+static int g_xdrop_warps = 32;  // warps per k_xdrop<FAST> CTA: 16 (two CTAs per SM) or 32 (one, sharing one score table) (SO_XDROP_WARPS)
+static int g_xdrop_qs = 16;     // shifted copies of the query view: 0, 4 or 16 (SO_XDROP_QSHIFT)
 static int g_xdrop_ctas = 2;  // resident k_xdrop<FAST> CTAs per SM (SO_XDROP_CTAS: tuning hook; 1 leaves half the SM to the other lane's kernels)
 static uint32_t g_cell_max = kCellMax;  // cells above this many hits send the block to the general path (SO_CELL_MAX: test hook)
 static uint32_t g_cell_split = 0;  // target ranges per query in the cell passes; 0 = as few as fit shared memory (SO_CELL_SPLIT)  // idle lanes that trigger a refill in k_xdrop (SO_XDROP_REFILL: tuning hook)
@@ -1954,6 +1999,17 @@ int upload_search_config(so_ctx *c) {
     g_xdrop_refill = e ? atoi(e) : 24;
     g_xdrop_ctas = 2;
     if (const char *xc = getenv("SO_XDROP_CTAS")) g_xdrop_ctas = std::max(1, std::min(2, atoi(xc)));
+    // default: one 1024-thread CTA per SM (one score table: 122 KB of shared memory, which leaves ~124 KB of L1 instead
+    // of 29 KB) and 16 byte-shifted copies of the query view (measured: 64 -> 55 ms per 4096 queries; the copies alone,
+    // with two CTAs per SM, thrash the small L1: 85 ms).  Other refill thresholds use the two-CTA kernel.
+    g_xdrop_warps = e && atoi(e) != 24 ? 16 : 32, g_xdrop_qs = e && atoi(e) != 24 ? 0 : 16;
+    if (const char *xw = getenv("SO_XDROP_WARPS")) g_xdrop_warps = atoi(xw) == 32 ? 32 : 16;
+    if (const char *xq = getenv("SO_XDROP_QSHIFT")) g_xdrop_qs = atoi(xq) == 16 ? 16 : atoi(xq) == 4 ? 4 : 0;
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, true, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, true, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, true, 32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + 2 * kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, true, 32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + 2 * kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, true, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + 2 * kXdBufBytes));
     g_cell_split = 0;
     if (const char *cs = getenv("SO_CELL_SPLIT")) g_cell_split = (uint32_t)std::max(0, std::min(8, atoi(cs)));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
@@ -1976,7 +2032,7 @@ int upload_search_config(so_ctx *c) {
 }
 
 void merge_lane_stats(so_ctx *c) {
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < so_ctx::kMaxLanes; l++) {
         so_stats &a = c->stats_lane[l], &d = c->stats;
         d.seed_hits += a.seed_hits, d.groups += a.groups, d.candidates += a.candidates, d.ungap_steps += a.ungap_steps;
         d.kernel_launches += a.kernel_launches, d.lib_launches += a.lib_launches;
@@ -1992,8 +2048,8 @@ void merge_lane_stats(so_ctx *c) {
 // The caller uploads the search configuration (upload_search_config) once before the first call.
 int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, PackedCands &out, int lane, BlockStore *bs,
                      int bs_q0) {
-    so::DBuf<uint8_t> *scratch = lane ? c->scratch1 : c->scratch;
-    cudaEvent_t *ev = lane ? c->ev1 : c->ev;
+    so::DBuf<uint8_t> *scratch = c->lane_scratch(lane);
+    cudaEvent_t *ev = c->lane_ev(lane);
     so_stats &stats = c->stats_lane[lane];
     const Params &P = c->P;
     const i64 nq_total = q_end - q_begin;
@@ -2007,7 +2063,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
     i64 sub = c->sub_block > 0 ? c->sub_block : 256;
     if (const char *e = getenv("SO_SUB_BLOCK0")) sub = std::max<i64>(1, atoll(e));  // tuning hook: first sub-block
     i64 b0 = q_begin;
-    cudaStream_t st = lane ? c->stream1 : c->stream;
+    cudaStream_t st = c->lane_stream(lane);
     while (b0 < q_end) {
         i64 b1 = std::min<i64>(q_end, b0 + sub);
         const int nq = (int)(b1 - b0);
@@ -2206,7 +2262,7 @@ int chunk_candidates(so_ctx *c, const ChunkIndex &ix, i64 q_begin, i64 q_end, Pa
                                                           (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
                                                           (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
                                                           qoff2[1], (uint32_t)Lq64, d_gscore, d_grank, d_counter, 1, nullptr, 0, nullptr, 0,
-                                                          nullptr, nullptr);
+                                                          nullptr, nullptr, 0u);
                     d_gkey = (const uint64_t *)scratch[SC_GKEY].p;
                     stats.kernel_launches += 2;
                 } else {
@@ -2373,9 +2429,9 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
         getenv("SO_NO_FAST"))
         return SO_OK;
     if (!c->d_tung || c->q_off[(size_t)c->n_q] >= 0xfff00000ull || c->t_off[(size_t)c->n_t] >= 0xfff00000ull) return SO_OK;
-    so::DBuf<uint8_t> *scratch = lane ? c->scratch1 : c->scratch;
+    so::DBuf<uint8_t> *scratch = c->lane_scratch(lane);
     so_stats &stats = c->stats_lane[lane];
-    cudaStream_t st = lane ? c->stream1 : c->stream;
+    cudaStream_t st = c->lane_stream(lane);
     const size_t nch = c->chunks.size();
     // ---- sub-blocks: bounded seed hits (all chunks), query view below 2^24 bytes
     uint64_t thr_max = 0, maxb = 0;
@@ -2443,6 +2499,10 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
     const int refill = g_xdrop_refill;
     auto kx = refill <= 8 ? k_xdrop<8, true> : refill <= 12 ? k_xdrop<12, true> : refill <= 16 ? k_xdrop<16, true>
               : refill <= 20 ? k_xdrop<20, true> : k_xdrop<24, true>;
+    const int xw = g_xdrop_warps, xqs = g_xdrop_qs;
+    if (xw == 32 || xqs != 0)  // layout variants (refill 24 only)
+        kx = xw == 32 ? (xqs == 16 ? k_xdrop<24, true, 32, 16> : xqs == 4 ? k_xdrop<24, true, 32, 4> : k_xdrop<24, true, 32, 0>)
+                      : (xqs == 16 ? k_xdrop<24, true, 16, 16> : k_xdrop<24, true, 16, 4>);
     for (size_t si = 0; si < subs.size(); si++) {
         const Sub &sb = subs[si];
         const int nq = (int)(sb.s1 - sb.s0);
@@ -2481,6 +2541,16 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
         if ((rc = ung_build(st, stats, c->d_qcls + qa, c->d_qoff + sb.s0, (uint32_t)nq, qa, (uint32_t)Lq64, d_qung, qoff2, qtotal,
                             3)) != SO_OK)
             return rc;
+        const uint8_t *d_qview = d_qung;
+        uint32_t qstride = 0;
+        if (xqs) {
+            qstride = (qtotal + 64u + 15u) & ~15u;
+            if ((rc = scratch[SC_QSHIFT].reserve((size_t)qstride * (size_t)xqs)) != SO_OK) return rc;
+            k_ung_shift<<<dim3((qstride + 255) / 256, (unsigned)xqs), 256, 0, st>>>(d_qung, qtotal, scratch[SC_QSHIFT].p, qstride,
+                                                                                  xqs == 16 ? 1u : 4u, (uint8_t)(kUngStop << 3));
+            stats.kernel_launches += 1;
+            d_qview = scratch[SC_QSHIFT].p;
+        }
         for (size_t ch = 0; ch < nch; ch++) {
             const ChunkIndex &ix = c->chunks[ch];
             if (ix.n_seeds == 0 || (only_chunk >= 0 && (size_t)only_chunk != ch)) continue;
@@ -2518,11 +2588,10 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
             k_cell_block<<<148 * 2, 512, sizeof(CellBlockSmem), st>>>(d_cloc, d_ubase, d_blist, d_lcount, NB, NBh, nsplit, g, c->d_qoff,
                                                                      c->d_toff, qa, d_sub, d_ssub, d_desc, d_cellid, d_flags);
             stamp();
-            kx<<<148 * g_xdrop_ctas, 512, kUngTabBytes + kXdBufBytes, st>>>(d_desc, 0u, d_ssub, nullptr, nullptr, 0u, nullptr, g.qst_bits,
-                                                                (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
-                                                                (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qung, qoff2[0],
-                                                                qoff2[1], (uint32_t)Lq64, nullptr, nullptr, d_ctl, 1, d_cellid,
-                                                                g.diag_bits, d_creg, ccap, d_qcount, d_flags);
+            kx<<<xw == 32 ? 148 : 148 * g_xdrop_ctas, xw * 32, kUngTabBytes + (xw / 16) * kXdBufBytes, st>>>(
+                d_desc, 0u, d_ssub, nullptr, nullptr, 0u, nullptr, g.qst_bits, (const uint4 *)c->d_tung, c->tung_off[0], c->tung_off[1],
+                (uint32_t)c->t_off[(size_t)c->n_t], (const uint4 *)d_qview, qoff2[0], qoff2[1], (uint32_t)Lq64, nullptr, nullptr, d_ctl,
+                1, d_cellid, g.diag_bits, d_creg, ccap, d_qcount, d_flags, qstride / 16);
             stamp();
             k_cand_sort<<<sgrid, kCandThreads, sizeof(CandSmem), st>>>(d_creg, ccap, d_qcount, nq, g, c->d_qoff, (uint64_t *)scratch[SC_GBUF].p,
                                                                       bs.vals.p, bs.capq, bs.count.p, (int)(sb.s0 - b0), d_lcount + 3,
@@ -2538,9 +2607,9 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
 
 // after the block's stream synchronisation: flags, counters and stage times of block_candidates_fast
 int finish_fast_block(so_ctx *c, int lane, bool &redo) {
-    so::DBuf<uint8_t> *scratch = lane ? c->scratch1 : c->scratch;
+    so::DBuf<uint8_t> *scratch = c->lane_scratch(lane);
     so_stats &stats = c->stats_lane[lane];
-    cudaStream_t st = lane ? c->stream1 : c->stream;
+    cudaStream_t st = c->lane_stream(lane);
     redo = false;
     unsigned long long h[11] = {};
     SO_CUDA(cudaMemcpyAsync(h, scratch[SC_CTL].p, sizeof h, cudaMemcpyDeviceToHost, st));

@@ -2,9 +2,10 @@
 blocks (two warm-up steps, three timed steps of 4096 queries, two production lanes = the bench.py `value`
 pipeline), then one measurement-mode step for the per-stage CUDA-event times and the in-pipeline DP rate.
 
-    python tools/env_sweep.py [out.json] [B]
+    python tools/env_sweep.py [out.json] [B] [--stages]
 
 The hooks are read by so_search on every call, so the environment can change between calls."""
+import hashlib
 import json
 import os
 import sys
@@ -14,17 +15,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from swiftortho_b200 import search as so
 
-SETTINGS = [
-    ('baseline', {}),
-    ('align_batch_2048', {'SO_ALIGN_BATCH': '2048'}),
-    ('align_batch_4096', {'SO_ALIGN_BATCH': '4096'}),
-    ('query_block_592', {'SO_QUERY_BLOCK': '592'}),
-    ('query_block_1024', {'SO_QUERY_BLOCK': '1024'}),
-    ('xdrop_ctas_1', {'SO_XDROP_CTAS': '1'}),
-    ('xdrop_ctas_1_split_2', {'SO_XDROP_CTAS': '1', 'SO_CELL_SPLIT': '2'}),
-    ('baseline_again', {}),
+SETTINGS = [  # (name, production lanes, environment)
+    ('baseline', 2, {}),
+    ('w32', 2, {'SO_XDROP_WARPS': '32'}),
+    ('w16_q4', 2, {'SO_XDROP_QSHIFT': '4'}),
+    ('w32_q4', 2, {'SO_XDROP_WARPS': '32', 'SO_XDROP_QSHIFT': '4'}),
+    ('w16_q16', 2, {'SO_XDROP_QSHIFT': '16'}),
+    ('w32_q16', 2, {'SO_XDROP_WARPS': '32', 'SO_XDROP_QSHIFT': '16'}),
+    ('baseline_again', 2, {}),
 ]
-HOOKS = sorted({k for _, e in SETTINGS for k in e})
+HOOKS = sorted({k for _, _, e in SETTINGS for k in e})
 
 
 def main():
@@ -37,33 +37,35 @@ def main():
     S.build_index()
     S.set_queries(F)
     res = []
-    for name, env in SETTINGS:
+    for name, lanes, env in SETTINGS:
         for k in HOOKS:
             os.environ.pop(k, None)
         os.environ.update(env)
-        rec = {'name': name, 'env': env}
+        rec = {'name': name, 'lanes': lanes, 'env': env, 'queries_per_step': B}
         try:
-            S.set_lanes(2)
-            rows0 = None
+            S.set_lanes(lanes)
             for s in range(2):
                 S.search(s * B, (s + 1) * B)
             S.stats(reset=True)
             t0 = time.perf_counter()
             nrows = 0
+            md5 = hashlib.md5()
             for s in range(3):
                 r = S.search((2 + s) * B, (3 + s) * B)
                 nrows += r.n
+                md5.update(r.as_array().tobytes())
             dt = time.perf_counter() - t0
             st = S.stats(reset=True)
-            rec.update(ms_per_step=1e3 * dt / 3, proteins_per_s=3 * B / dt, rows=nrows,
+            rec.update(ms_per_step=1e3 * dt / 3, proteins_per_s=3 * B / dt, rows=nrows, rows_md5=md5.hexdigest(),
                        alignments=st['alignments'], alignments_used=st.get('alignments_used'))
-            S.set_lanes(0)
-            S.search(2 * B, 3 * B)
-            S.stats(reset=True)
-            S.search(2 * B, 3 * B)
-            k = S.stats(reset=True)
-            rec['stage_ms'] = {x: round(k[x], 2) for x in ('ms_seed', 'ms_sort', 'ms_ungap', 'ms_select', 'ms_dp', 'ms_traceback')}
-            rec['dp_gcups_in_pipeline'] = k['dp_cells'] / (k['ms_dp'] * 1e-3) / 1e9 if k['ms_dp'] > 0 else 0.0
+            if '--no-stages' not in sys.argv:
+                S.set_lanes(0)
+                S.search(2 * B, 3 * B)
+                S.stats(reset=True)
+                S.search(2 * B, 3 * B)
+                k = S.stats(reset=True)
+                rec['stage_ms'] = {x: round(k[x], 2) for x in ('ms_seed', 'ms_sort', 'ms_ungap', 'ms_select', 'ms_dp', 'ms_traceback')}
+                rec['dp_gcups_in_pipeline'] = k['dp_cells'] / (k['ms_dp'] * 1e-3) / 1e9 if k['ms_dp'] > 0 else 0.0
         except Exception as e:  # a setting the library rejects is recorded, the sweep goes on
             rec['error'] = repr(e)
         print(json.dumps(rec), flush=True)
