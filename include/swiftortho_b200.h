@@ -196,6 +196,23 @@ int so_orth_classify(int device, const uint64_t *group_offsets, int64_t n_groups
  * bin/find_orth.py:476-478, 499-501, 552-554, on (id rank << 32 | id rank) keys) */
 int so_sort_pairs_u64(int device, uint64_t *keys, uint32_t *vals, int64_t n);
 
+/* C   clustering, device half — bin/find_cluster.py.  Host arrays in, host arrays out.
+ * so_cc_labels: connected components of an undirected graph with n vertices and m edges (the reference's
+ *   nx.connected_components calls, bin/find_cluster.py:1508-1520, 1550-1556, 1690-1692, 1708-1718);
+ *   labels[v] = smallest vertex id of v's component.
+ * so_apc: affinity propagation as `apclust_blk` / `apclust` run it (bin/find_cluster.py:310-516) on the float32 table
+ *   fc2mat writes (:767-860): entries (row[e], col[e], sim[e]) in FILE ORDER, ks items, `sweeps` sweeps (the reference
+ *   always runs itr = 100), labels[i] = exemplar of item i (column of the first maximum of R + A in row i).
+ * so_mcl: Markov clustering as `mcl` runs it (bin/find_cluster.py:636-690) on a CSR float32 matrix with sorted,
+ *   duplicate-free rows: at most max_iter (100) iterations of column normalisation, X @ X, x ** inflation, convergence
+ *   test every check_every-th (5th) iteration, pruning below 1e-5.  Returns the final matrix (library-owned, so_free);
+ *   entries above 1e-5 are the edges whose connected components are the clusters.  iterations = iterations run. */
+int so_cc_labels(int device, int64_t n, int64_t m, const uint32_t *eu, const uint32_t *ev, uint32_t *labels);
+int so_apc(int device, int64_t n_rows, int64_t ks, const uint32_t *row, const uint32_t *col, const float *sim, double damp,
+           int sweeps, int32_t *labels);
+int so_mcl(int device, int64_t n, const int64_t *indptr, const uint32_t *indices, const float *data, double inflation,
+           int max_iter, int check_every, int64_t **out_indptr, uint32_t **out_indices, float **out_data, int *iterations);
+
 /* counters of the last so_search / so_align_batch call (for bench.py) */
 typedef struct so_stats {
     int64_t queries, seed_hits, groups, candidates, alignments, dp_cells, rows;

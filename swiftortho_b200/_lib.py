@@ -93,6 +93,10 @@ SYMBOLS = {
     'so_seq_hash': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'so_orth_classify': (C.c_int, [C.c_int, C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p]),
     'so_sort_pairs_u64': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
+    'so_cc_labels': (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'so_apc': (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]),
+    'so_mcl': (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int,
+                         _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_int)]),
     'so_stats_get': (C.c_int, [C.c_void_p, _P(so_stats)]),
     'so_stats_reset': (C.c_int, [C.c_void_p]),
     'so_set_sub_block': (C.c_int, [C.c_void_p, C.c_int64]),

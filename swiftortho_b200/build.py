@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libswiftortho_b200.so')
-SOURCES = ['api.cpp', 'fasta.cpp', 'host_algos.cpp', 'align.cu', 'search.cu', 'select.cu', 'dedupe.cu', 'orth.cu']
+SOURCES = ['api.cpp', 'fasta.cpp', 'host_algos.cpp', 'align.cu', 'search.cu', 'select.cu', 'dedupe.cu', 'orth.cu', 'cluster.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC,-O3,-Wall,-pthread', '--expt-relaxed-constexpr', '-Xptxas', '-v']
 

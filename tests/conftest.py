@@ -151,3 +151,61 @@ def kat():
 def golden_cases():
     with open(os.path.join(GOLDEN, 'cases.json')) as f:
         return json.load(f)
+
+
+class ClusterOracle:
+    """ctypes view of oracle/cluster_oracle.cpp (test infrastructure) with the backend interface of
+    swiftortho_b200.find_cluster.DeviceBackend, so the host logic can be checked on CPU against the reference goldens
+    and the CUDA kernels against the same restatement."""
+
+    def __init__(self):
+        import numpy as np
+        self.np = np
+        so = os.path.join(ROOT, 'oracle', '_build', 'libcluster_oracle.so')
+        src = os.path.join(ROOT, 'oracle', 'cluster_oracle.cpp')
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle')], stdout=subprocess.DEVNULL)
+        L = ctypes.CDLL(so)
+        self.L = L
+        V, P = ctypes.c_void_p, ctypes.POINTER
+        L.orc_cc_labels.argtypes = [ctypes.c_int64, ctypes.c_int64, V, V, V]
+        L.orc_apc.argtypes = [ctypes.c_int64, ctypes.c_int64, V, V, V, ctypes.c_double, ctypes.c_int, V]
+        L.orc_mcl.argtypes = [ctypes.c_int64, V, V, V, ctypes.c_double, ctypes.c_int, ctypes.c_int, P(V), P(V), P(V),
+                              P(ctypes.c_int)]
+        L.orc_cluster_free.argtypes = [V]
+
+    def cc_labels(self, n, eu, ev):
+        np = self.np
+        eu, ev = np.ascontiguousarray(eu, dtype=np.uint32), np.ascontiguousarray(ev, dtype=np.uint32)
+        lab = np.empty(n, dtype=np.uint32)
+        self.L.orc_cc_labels(n, len(eu), eu.ctypes.data, ev.ctypes.data, lab.ctypes.data)
+        return lab
+
+    def apc(self, ks, row, col, sim, damp, sweeps=100):
+        np = self.np
+        row, col = np.ascontiguousarray(row, dtype=np.uint32), np.ascontiguousarray(col, dtype=np.uint32)
+        sim = np.ascontiguousarray(sim, dtype=np.float32)
+        lab = np.empty(ks, dtype=np.int32)
+        self.L.orc_apc(len(row), ks, row.ctypes.data, col.ctypes.data, sim.ctypes.data, float(damp), int(sweeps), lab.ctypes.data)
+        return lab
+
+    def mcl(self, n, indptr, indices, data, inflation, max_iter=100, check_every=5):
+        np = self.np
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        op, oi, od, it = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int(0)
+        self.L.orc_mcl(n, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, float(inflation), int(max_iter),
+                       int(check_every), ctypes.byref(op), ctypes.byref(oi), ctypes.byref(od), ctypes.byref(it))
+        ptr = np.ctypeslib.as_array(ctypes.cast(op, ctypes.POINTER(ctypes.c_int64)), shape=(n + 1,)).copy()
+        nnz = int(ptr[n]) if n else 0
+        col = np.ctypeslib.as_array(ctypes.cast(oi, ctypes.POINTER(ctypes.c_uint32)), shape=(max(nnz, 1),))[:nnz].copy()
+        val = np.ctypeslib.as_array(ctypes.cast(od, ctypes.POINTER(ctypes.c_float)), shape=(max(nnz, 1),))[:nnz].copy()
+        for p in (op, oi, od):
+            self.L.orc_cluster_free(p)
+        return ptr, col, val, it.value
+
+
+@pytest.fixture(scope='session')
+def cluster_oracle():
+    return ClusterOracle()
