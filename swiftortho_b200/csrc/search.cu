@@ -805,6 +805,118 @@ __global__ void __launch_bounds__(256) k_cell_warp(const uint32_t *__restrict__ 
     }
 }
 
+// One warp per 32 consecutive cells of one query (cells of 1..kCellWarp hits; larger ones are queued for k_cell_block):
+// replaces k_cell_small + k_cell_warp.  The hits of consecutive cells are contiguous in `sub`, so a warp loads the whole
+// span coalesced into shared memory, every HIT ranks itself inside its cell (count of smaller keys: cells average a few
+// hits), and every sorted position emits its key / descriptor / cell id -- one lane per hit instead of one thread
+// (k_cell_small) or one warp (k_cell_warp) per cell, no divergence over the cell sizes.  Spans above kSpanCap hits are
+// processed as several groups of whole cells.
+enum { kSpanCap = 512 };
+__global__ void __launch_bounds__(256) k_cell_span(const uint32_t *__restrict__ cell_local, const uint32_t *__restrict__ ubase,
+                                                   uint32_t NB, uint32_t NBh, uint32_t nsplit, BlockGeom g,
+                                                   const uint64_t *__restrict__ qoff, const uint64_t *__restrict__ toff, uint64_t qa,
+                                                   const uint32_t *__restrict__ sub, uint32_t *__restrict__ ssub,
+                                                   uint2 *__restrict__ desc, uint32_t *__restrict__ cellid,
+                                                   uint32_t *__restrict__ blist, uint32_t *__restrict__ lcount) {
+    __shared__ uint32_t s_in[8][kSpanCap];
+    __shared__ uint32_t s_out[8][kSpanCap + 2];
+    __shared__ uint8_t s_cell[8][kSpanCap];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t qi = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = qi * NB + t;
+    uint32_t off = 0, n = 0;
+    if (t < NB) {
+        const uint32_t unit = nsplit == 1 ? qi : qi * nsplit + t / NBh;
+        const uint32_t ub = ubase[unit];
+        off = ub + cell_local[c];
+        const bool last = (t + 1 == NB) || (nsplit != 1 && (t + 1) % NBh == 0);
+        n = (last ? ubase[unit + 1] : ub + cell_local[c + 1]) - off;
+    }
+    {   // cells above kCellWarp hits are queued: one atomic per warp
+        const bool qb = n > (uint32_t)kCellWarp;
+        const unsigned mb = __ballot_sync(0xffffffffu, qb);
+        if (mb) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(lcount + 1, (uint32_t)__popc(mb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (qb) blist[base + __popc(mb & ((1u << lane) - 1u))] = c;
+        }
+    }
+    const uint32_t nn = n <= (uint32_t)kCellWarp ? n : 0u;
+    uint32_t pre = nn;  // inclusive prefix over the warp's cells, then exclusive
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += u;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+    if (total == 0) return;
+    pre -= nn;
+    const uint32_t tbase = nn ? (uint32_t)toff[g.c0 + (int)t - 1] : 0u;
+    const uint32_t qrel = (uint32_t)(qoff[g.qb0 + (int)qi] - qa);
+    uint32_t *si = s_in[warp], *so_ = s_out[warp];
+    uint8_t *sc = s_cell[warp];
+    int a = 0;
+    while (a < 32) {
+        // group of whole cells [a, b) with at most kSpanCap hits (a cell has at most kCellWarp <= kSpanCap)
+        const uint32_t pa = __shfl_sync(0xffffffffu, pre, a);
+        const unsigned fits = __ballot_sync(0xffffffffu, lane >= a && pre + nn - pa <= (uint32_t)kSpanCap);
+        const int b = a + __popc(fits);  // `fits` is a run of ones starting at lane a (prefixes are monotone)
+        const uint32_t pb = b < 32 ? __shfl_sync(0xffffffffu, pre, b & 31) : total;
+        const uint32_t gm = pb - pa;
+        // ---- load: hit i of the group belongs to the last cell whose prefix is <= pa + i
+        for (uint32_t i0 = 0; i0 < gm; i0 += 32) {
+            const uint32_t i = i0 + lane, gi = pa + i;
+            int lo = a, hi = b;  // invariant: pre[lo] <= gi < pre[hi] (pre[b] = pb)
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const int mid = (lo + hi) >> 1;
+                const uint32_t pm = __shfl_sync(0xffffffffu, pre, mid);
+                if (mid > lo && pm <= gi) lo = mid; else if (mid > lo) hi = mid;
+            }
+            // empty cells share their prefix with the next cell: the owner is the LAST cell with pre <= gi, found above
+            // because the search keeps lo at the highest index whose prefix is <= gi
+            const uint32_t coff = __shfl_sync(0xffffffffu, off, lo), cpre = __shfl_sync(0xffffffffu, pre, lo);
+            if (i < gm) {
+                si[i] = sub[coff + (gi - cpre)];
+                sc[i] = (uint8_t)lo;
+            }
+        }
+        __syncwarp();
+        // ---- rank inside the cell
+        for (uint32_t i0 = 0; i0 < gm; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const int cl = i < gm ? (int)sc[i] : a;
+            const uint32_t cs = __shfl_sync(0xffffffffu, pre, cl) - pa, cn = __shfl_sync(0xffffffffu, nn, cl);
+            if (i < gm) {
+                const uint32_t x = si[i];
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < cn; j++) {
+                    const uint32_t y = si[cs + j];
+                    rank += (y < x || (y == x && cs + j < i)) ? 1u : 0u;
+                }
+                so_[cs + rank] = x;
+            }
+        }
+        __syncwarp();
+        // ---- emit
+        for (uint32_t i0 = 0; i0 < gm; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const int cl = i < gm ? (int)sc[i] : a;
+            const uint32_t cs = __shfl_sync(0xffffffffu, pre, cl) - pa, cn = __shfl_sync(0xffffffffu, nn, cl);
+            const uint32_t coff = __shfl_sync(0xffffffffu, off, cl), ctb = __shfl_sync(0xffffffffu, tbase, cl);
+            if (i < gm) {
+                const uint32_t r = i - cs;
+                const uint32_t ct = t - (uint32_t)lane + (uint32_t)cl;
+                cell_emit(coff + r, so_[i], r > 0, r > 0 ? so_[i - 1] : 0u, r + 1 < cn, r + 1 < cn ? so_[i + 1] : 0u, r + 2 < cn,
+                          r + 2 < cn ? so_[i + 2] : 0u, ctb, qrel, (qi << 16) | ct, g, ssub, desc, cellid);
+            }
+        }
+        __syncwarp();
+        a = b;
+    }
+}
+
 // one CTA per queued cell (kCellWarp < hits <= kCellMax): shared-memory radix sort of the cell-local bits
 template <int THREADS, int ITEMS>
 __device__ __forceinline__ void cell_sort_tile(const uint32_t *__restrict__ sub, uint32_t off, uint32_t n, int Lb, void *smem) {
@@ -1990,6 +2102,7 @@ static const uint64_t kHitCap = 300000000ull;  // seed hits per sub-block (memor
 static int g_xdrop_refill = 24;
 static int g_xdrop_warps = 32;  // warps per k_xdrop<FAST> CTA: 16 (two CTAs per SM) or 32 (one, sharing one score table) (SO_XDROP_WARPS)
 static int g_xdrop_qs = 16;     // shifted copies of the query view: 0, 4 or 16 (SO_XDROP_QSHIFT)
+static int g_cell_span = 1;  // cells of up to kCellWarp hits: k_cell_span (1) or k_cell_small + k_cell_warp (0) (SO_CELL_SPAN)
 static int g_xdrop_ctas = 2;  // resident k_xdrop<FAST> CTAs per SM (SO_XDROP_CTAS: tuning hook; 1 leaves half the SM to the other lane's kernels)
 static uint32_t g_cell_max = kCellMax;  // cells above this many hits send the block to the general path (SO_CELL_MAX: test hook)
 static uint32_t g_cell_split = 0;  // target ranges per query in the cell passes; 0 = as few as fit shared memory (SO_CELL_SPLIT)  // idle lanes that trigger a refill in k_xdrop (SO_XDROP_REFILL: tuning hook)
@@ -1997,6 +2110,8 @@ static uint32_t g_cell_split = 0;  // target ranges per query in the cell passes
 int upload_search_config(so_ctx *c) {
     const char *e = getenv("SO_XDROP_REFILL");
     g_xdrop_refill = e ? atoi(e) : 24;
+    g_cell_span = 1;
+    if (const char *cs2 = getenv("SO_CELL_SPAN")) g_cell_span = atoi(cs2) != 0;
     g_xdrop_ctas = 2;
     if (const char *xc = getenv("SO_XDROP_CTAS")) g_xdrop_ctas = std::max(1, std::min(2, atoi(xc)));
     // default: one 1024-thread CTA per SM (one score table: 122 KB of shared memory, which leaves ~124 KB of L1 instead
@@ -2010,6 +2125,10 @@ int upload_search_config(so_ctx *c) {
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, true, 32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + 2 * kXdBufBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, true, 32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + 2 * kXdBufBytes));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<24, true, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + 2 * kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<16, true, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + 2 * kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<20, true, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + 2 * kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<28, true, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + 2 * kXdBufBytes));
+    SO_CUDA(cudaFuncSetAttribute(k_xdrop<32, true, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes + 2 * kXdBufBytes));
     g_cell_split = 0;
     if (const char *cs = getenv("SO_CELL_SPLIT")) g_cell_split = (uint32_t)std::max(0, std::min(8, atoi(cs)));
     SO_CUDA(cudaFuncSetAttribute(k_xdrop<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUngTabBytes));
@@ -2503,6 +2622,12 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
     if (xw == 32 || xqs != 0)  // layout variants (refill 24 only)
         kx = xw == 32 ? (xqs == 16 ? k_xdrop<24, true, 32, 16> : xqs == 4 ? k_xdrop<24, true, 32, 4> : k_xdrop<24, true, 32, 0>)
                       : (xqs == 16 ? k_xdrop<24, true, 16, 16> : k_xdrop<24, true, 16, 4>);
+    if (const char *r2 = getenv("SO_XDROP_REFILL2")) {  // tuning hook: refill threshold of the default layout
+        const int r = atoi(r2);
+        if (xw == 32 && xqs == 16)
+            kx = r <= 16 ? k_xdrop<16, true, 32, 16> : r <= 20 ? k_xdrop<20, true, 32, 16> : r <= 24 ? k_xdrop<24, true, 32, 16>
+                 : r <= 28 ? k_xdrop<28, true, 32, 16> : k_xdrop<32, true, 32, 16>;
+    }
     for (size_t si = 0; si < subs.size(); si++) {
         const Sub &sb = subs[si];
         const int nq = (int)(sb.s1 - sb.s0);
@@ -2581,10 +2706,16 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
             k_unit_scan<<<1, 1024, 0, st>>>(d_utot, U, d_ubase, d_ctl, d_flags);
             k_cell_pass<true><<<pblocks, 1024, NBh * 4, st>>>(d_slot_off, g, c->d_qoff, d_st, d_cnt, ix.d_hdsst, NB, nsplit, d_cloc,
                                                             nullptr, d_ubase, d_sub, g_cell_max, d_flags, d_lcount + 2);
-            k_cell_small<<<dim3((NB + 255) / 256, (unsigned)nq), 256, 0, st>>>(d_cloc, d_ubase, ncells, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa,
-                                                              d_sub, d_ssub, d_desc, d_cellid, d_wlist, d_blist, d_lcount, d_flags);
-            k_cell_warp<<<148 * 4, 256, 0, st>>>(d_cloc, d_ubase, d_wlist, d_lcount, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa, d_sub,
-                                                d_ssub, d_desc, d_cellid, d_flags);
+            if (g_cell_span) {
+                k_cell_span<<<dim3((NB + 255) / 256, (unsigned)nq), 256, 0, st>>>(d_cloc, d_ubase, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa,
+                                                                                 d_sub, d_ssub, d_desc, d_cellid, d_blist, d_lcount);
+            } else {
+                k_cell_small<<<dim3((NB + 255) / 256, (unsigned)nq), 256, 0, st>>>(d_cloc, d_ubase, ncells, NB, NBh, nsplit, g, c->d_qoff,
+                                                                                  c->d_toff, qa, d_sub, d_ssub, d_desc, d_cellid, d_wlist,
+                                                                                  d_blist, d_lcount, d_flags);
+                k_cell_warp<<<148 * 4, 256, 0, st>>>(d_cloc, d_ubase, d_wlist, d_lcount, NB, NBh, nsplit, g, c->d_qoff, c->d_toff, qa, d_sub,
+                                                    d_ssub, d_desc, d_cellid, d_flags);
+            }
             k_cell_block<<<148 * 2, 512, sizeof(CellBlockSmem), st>>>(d_cloc, d_ubase, d_blist, d_lcount, NB, NBh, nsplit, g, c->d_qoff,
                                                                      c->d_toff, qa, d_sub, d_ssub, d_desc, d_cellid, d_flags);
             stamp();

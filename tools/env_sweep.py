@@ -17,11 +17,7 @@ from swiftortho_b200 import search as so
 
 SETTINGS = [  # (name, production lanes, environment)
     ('baseline', 2, {}),
-    ('w32', 2, {'SO_XDROP_WARPS': '32'}),
-    ('w16_q4', 2, {'SO_XDROP_QSHIFT': '4'}),
-    ('w32_q4', 2, {'SO_XDROP_WARPS': '32', 'SO_XDROP_QSHIFT': '4'}),
-    ('w16_q16', 2, {'SO_XDROP_QSHIFT': '16'}),
-    ('w32_q16', 2, {'SO_XDROP_WARPS': '32', 'SO_XDROP_QSHIFT': '16'}),
+    ('cell_small_warp', 2, {'SO_CELL_SPAN': '0'}),
     ('baseline_again', 2, {}),
 ]
 HOOKS = sorted({k for _, _, e in SETTINGS for k in e})
