@@ -346,7 +346,7 @@ def run_full(args, rank, world, local, dist, fasta):
                                 'by residues over %d rank(s), 16-column parts written and concatenated by rank 0' % (int(nq), world)),
             'roofline': {'kernel': 'k_xdrop', 'bound': 'int32', 'achieved': ach, 'peak': int_peak['gops_measured'], 'unit': 'Gop/s',
                          'frac': ach / int_peak['gops_measured'], 'traffic': None,
-                         'timing': 'CUDA events on the launching streams (two production lanes share the GPU), max over ranks',
+                         'timing': 'CUDA events on the launching stream, max over ranks',
                          'peak_source': 'tools/int_peak.cu measured on this pool (profiles/int_peak.json)'},
             'e2e': {'value': value, 'unit': 'proteins/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'note': 'the job is end to end by construction: host FASTA file in, text table out'},
@@ -432,7 +432,7 @@ def run_ours(args, rank, world, local):
 
     # ---- kernel-timing pass: the same steps with ONE production lane, so the CUDA-event stage times
     #      inside so_search are not inflated by the second lane's kernels sharing the GPU.  The roofline
-    #      figures (kernel durations) come from this pass; `value` above is the two-lane pipeline.
+    #      figures (kernel durations) come from this pass; `value` above is the pipeline (candidate production overlapped with the alignment rounds).
     S.set_lanes(0)   # one lane, alignment rounds serialised with candidate production
     S.search(*block_of(args.warmup + args.steps))
     S.stats(reset=True)
@@ -442,7 +442,7 @@ def run_ours(args, rank, world, local):
     st = dict(st)
     stk = S.stats(reset=True)
     gcups_pipe = stk['dp_cells'] / (stk['ms_dp'] * 1e-3) / 1e9 if stk['ms_dp'] > 0 else 0.0
-    S.set_lanes(2)
+    S.set_lanes(1)
     for k in ('ms_ungap', 'ms_ungap_kernel', 'ms_sort', 'ms_seed', 'ms_select', 'ms_dp', 'ms_traceback'):
         st[k] = stk[k] * args.steps / ksteps      # same blocks as the first `ksteps` timed steps
 

@@ -228,7 +228,7 @@ typedef struct so_stats {
 } so_stats;
 int so_stats_get(const so_ctx *c, so_stats *s);
 /* tuning hooks (no reference counterpart): queries per seeding sub-block (0 = adaptive), and the number
- * of candidate-production lanes (streams) so_search overlaps (1 .. 4, default 2; 0 = one lane and alignment rounds
+ * of candidate-production lanes (streams) so_search overlaps (1 .. 4, default 1; 0 = one lane and alignment rounds
  * serialised with candidate production: measurement mode for per-kernel CUDA-event times) */
 int so_set_sub_block(so_ctx *c, int64_t n);
 int so_set_lanes(so_ctx *c, int n);

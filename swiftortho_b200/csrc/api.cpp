@@ -188,6 +188,7 @@ int so_ctx_create(int device, const so_params *p, so_ctx **out) {
     SO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SO_CUDA(cudaStreamCreateWithFlags(&c->stream_aln, cudaStreamNonBlocking));
     for (auto &st : c->stream_x) SO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto &e : c->ev_sync) SO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &evs : c->ev_x)
         for (auto &e : evs) SO_CUDA(cudaEventCreate(&e));
     for (auto &e : c->ev) SO_CUDA(cudaEventCreate(&e));
@@ -212,6 +213,8 @@ void so_ctx_destroy(so_ctx *c) {
             if (e) cudaEventDestroy(e);
     for (auto &st : c->stream_x)
         if (st) cudaStreamDestroy(st);
+    for (auto &e : c->ev_sync)
+        if (e) cudaEventDestroy(e);
     c->trace.release();
     if (c->d_tres) cudaFree(c->d_tres);
     if (c->d_qres) cudaFree(c->d_qres);
@@ -519,9 +522,11 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
     std::vector<so_hit> all_rows;
     const size_t nch = c->chunks.size();
     // query block size: the candidates of a block live in per-query device lists (select.cu)
-    i64 QB = 512;
+    i64 QB = 592;  // 4 x 148: the kernels that take one CTA per query (cell passes, candidate sort, selection) run whole waves
     if (const char *e = getenv("SO_QUERY_BLOCK")) QB = std::max<i64>(16, atoll(e));  // tuning hook
     const int nprod = std::max(1, std::min<int>(c->n_lanes, so_ctx::kMaxLanes));
+    c->shared_stream = true;  // SO_SHARED_STREAM=0: one stream per lane (kernels of two query blocks share the SMs)
+    if (const char *e = getenv("SO_SHARED_STREAM")) c->shared_stream = atoi(e) != 0;
     const int kSlots = 2 * nprod;  // a lane produces block k + nprod while the worker still orders block k
     // at most one candidate per (query, target): fixed per-query capacity of the device lists
     i64 capq = 0;
@@ -876,7 +881,8 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                 cudaMemcpyAsync(c->h_sel[slot], bs.sel.p, (size_t)nqb * (size_t)selcap * 8, cudaMemcpyDeviceToHost, st);
                 cudaMemcpyAsync(c->h_sel_n[slot], bs.sel_n.p, (size_t)nqb * 4, cudaMemcpyDeviceToHost, st);
                 cudaMemcpyAsync(flags, bs.count.p + nqb, 8, cudaMemcpyDeviceToHost, st);
-                cudaError_t e = cudaStreamSynchronize(st);
+                if (fast) so::enqueue_fast_ctl(c, pid);
+                cudaError_t e = c->lane_wait(pid);
                 if (e != cudaSuccess) {
                     so::set_error("CUDA error in the candidate selection: %s", cudaGetErrorString(e));
                     rc = SO_ENODEV;
@@ -900,7 +906,7 @@ int so_search(so_ctx *c, int64_t q_begin, int64_t q_end, so_hit **rows_out, int6
                             cudaMemcpyAsync(c->h_sel[slot], bs.sel.p, (size_t)nqb * (size_t)selcap * 8, cudaMemcpyDeviceToHost, st);
                             cudaMemcpyAsync(c->h_sel_n[slot], bs.sel_n.p, (size_t)nqb * 4, cudaMemcpyDeviceToHost, st);
                             cudaMemcpyAsync(flags, bs.count.p + nqb, 8, cudaMemcpyDeviceToHost, st);
-                            e = cudaStreamSynchronize(st);
+                            e = c->lane_wait(pid);
                             if (e != cudaSuccess) {
                                 so::set_error("CUDA error in the candidate selection: %s", cudaGetErrorString(e));
                                 rc = SO_ENODEV;

@@ -170,12 +170,22 @@ struct so_ctx {
     cudaStream_t stream_x[kMaxLanes - 1] = {};
     cudaEvent_t ev_x[kMaxLanes - 1][8] = {};
     so::DBuf<uint8_t> *lane_scratch(int lane) { return lane ? scratch_x[lane - 1] : scratch; }
-    cudaStream_t lane_stream(int lane) const { return lane ? stream_x[lane - 1] : stream; }
+    // shared_stream: every lane enqueues on ONE stream (kernels of different query blocks never run side by side; a lane
+    // waits for its own block through an event, so its host work still overlaps the other lanes' kernels)
+    bool shared_stream = false;
+    cudaEvent_t ev_sync[kMaxLanes] = {};
+    unsigned long long h_ctl[kMaxLanes][11] = {};  // control block of the lane's last sync-free block (copied before the wait)
+    cudaStream_t lane_stream(int lane) const { return (lane && !shared_stream) ? stream_x[lane - 1] : stream; }
+    // wait until everything this lane has enqueued so far is done
+    cudaError_t lane_wait(int lane) {
+        cudaError_t e = cudaEventRecord(ev_sync[lane], lane_stream(lane));
+        return e != cudaSuccess ? e : cudaEventSynchronize(ev_sync[lane]);
+    }
     cudaEvent_t *lane_ev(int lane) { return lane ? ev_x[lane - 1] : ev; }
     std::vector<cudaEvent_t> ev_pool[kMaxLanes];
     size_t ev_used[kMaxLanes] = {};  // per lane: stage events of the sync-free path, read at the end of a block
     so_stats stats_lane[kMaxLanes] = {};
-    int n_lanes = 2;
+    int n_lanes = 1;                 // measured: one production lane + the alignment worker beats two lanes (126 vs 129 ms / 4096 queries)
     double d2h_ms_lane[kMaxLanes] = {};
     so::DBuf<uint64_t> trace;
     void *h_pinned = nullptr;
@@ -208,6 +218,7 @@ int upload_search_config(so_ctx *c);
 // candidates are appended to `bs` with no host synchronisation; `eligible` = false when the block needs the general
 // path (nothing was launched); finish_fast_block reads the flags / counters after the block's stream sync
 int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, bool &eligible, int only_chunk = -1);
+int enqueue_fast_ctl(so_ctx *c, int lane);  // D2H of the block's flags / counters, enqueued behind its kernels
 int finish_fast_block(so_ctx *c, int lane, bool &redo);
 void merge_lane_stats(so_ctx *c);
 int ensure_pinned(so_ctx *c, size_t bytes);

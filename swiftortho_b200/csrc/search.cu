@@ -2736,15 +2736,19 @@ int block_candidates_fast(so_ctx *c, i64 b0, i64 b1, int lane, BlockStore &bs, b
     return SO_OK;
 }
 
-// after the block's stream synchronisation: flags, counters and stage times of block_candidates_fast
+// the block's control block (flags, counters) goes to the host behind the block's kernels, BEFORE the lane waits: on a
+// shared stream a copy enqueued after the wait would queue behind the next block of another lane
+int enqueue_fast_ctl(so_ctx *c, int lane) {
+    SO_CUDA(cudaMemcpyAsync(c->h_ctl[lane], c->lane_scratch(lane)[SC_CTL].p, sizeof c->h_ctl[lane], cudaMemcpyDeviceToHost,
+                            c->lane_stream(lane)));
+    return SO_OK;
+}
+
+// after the lane's wait: flags, counters and stage times of block_candidates_fast
 int finish_fast_block(so_ctx *c, int lane, bool &redo) {
-    so::DBuf<uint8_t> *scratch = c->lane_scratch(lane);
     so_stats &stats = c->stats_lane[lane];
-    cudaStream_t st = c->lane_stream(lane);
     redo = false;
-    unsigned long long h[11] = {};
-    SO_CUDA(cudaMemcpyAsync(h, scratch[SC_CTL].p, sizeof h, cudaMemcpyDeviceToHost, st));
-    SO_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long *h = c->h_ctl[lane];
     const uint32_t f0 = (uint32_t)h[10], f1 = (uint32_t)(h[10] >> 32);
     if (f1) {
         set_error("candidate production failed on the device (flag %u)", f1);
@@ -2770,7 +2774,7 @@ int finish_fast_block(so_ctx *c, int lane, bool &redo) {
     }
     stats.ungap_steps += (i64)h[1], stats.multi_groups += (i64)h[3], stats.groups += (i64)h[4];
     stats.candidates += (i64)h[5], stats.seed_hits += (i64)h[6];
-    stats.d2h_bytes += (i64)sizeof h;
+    stats.d2h_bytes += (i64)sizeof c->h_ctl[lane];
     return SO_OK;
 }
 

@@ -216,3 +216,17 @@ def test_find_cluster_cli_against_reference_goldens(golden, tmp_path):
         lines = [l for l in r.stdout.split('\n') if l]
         assert _canon(lines) == c['partition'], (c['input'], c['args'])
         assert [sorted(l.split('\t')) for l in lines] == [sorted(l.split('\t')) for l in c['raw']]
+
+
+@pytest.mark.gpu
+def test_find_cluster_device_equals_oracle_on_a_larger_table(device_backend, cluster_oracle, tmp_path):
+    """400 families x 20 taxa (~70 000 lines) with weak links between families: the CUDA-backed and the oracle-backed
+    host give the same lines, in the same order, for both algorithms."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import bench_cluster
+    p = str(tmp_path / 'fam.orth')
+    bench_cluster.make_table(p, 400, 20, seed=3)
+    for alg in ('mcl', 'apc'):
+        a = fc.cluster(p, alg, backend=device_backend)
+        b = fc.cluster(p, alg, backend=cluster_oracle)
+        assert a == b and len(a) >= 390

@@ -1,5 +1,5 @@
 """Tuning-hook sweep on config 2: one process, the index built once, every setting timed over the same query
-blocks (two warm-up steps, three timed steps of 4096 queries, two production lanes = the bench.py `value`
+blocks (two warm-up steps, six timed steps of 4096 queries, two production lanes = the bench.py `value`
 pipeline), then one measurement-mode step for the per-stage CUDA-event times and the in-pipeline DP rate.
 
     python tools/env_sweep.py [out.json] [B] [--stages]
@@ -16,16 +16,24 @@ import bench
 from swiftortho_b200 import search as so
 
 SETTINGS = [  # (name, production lanes, environment)
-    ('baseline', 2, {}),
-    ('cell_small_warp', 2, {'SO_CELL_SPAN': '0'}),
-    ('baseline_again', 2, {}),
+    ('l1', 1, {}),
+    ('l1_qb592', 1, {'SO_QUERY_BLOCK': '592'}),
+    ('l1_qb1024', 1, {'SO_QUERY_BLOCK': '1024'}),
+    ('l1_qb2048', 1, {'SO_QUERY_BLOCK': '2048'}),
+    ('l1_qb256', 1, {'SO_QUERY_BLOCK': '256'}),
+    ('l1_align1024', 1, {'SO_ALIGN_BATCH': '1024'}),
+    ('l1_own', 1, {'SO_SHARED_STREAM': '0'}),
+    ('l2_own', 2, {'SO_SHARED_STREAM': '0'}),
+    ('l2', 2, {}),
+    ('l1_b', 1, {}),
 ]
 HOOKS = sorted({k for _, _, e in SETTINGS for k in e})
 
 
 def main():
-    out = sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/env_sweep.json'
-    B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+    pos = [a for a in sys.argv[1:] if not a.startswith('--')]
+    out = pos[0] if pos else 'gpurun_out/env_sweep.json'
+    B = int(pos[1]) if len(pos) > 1 else 4096
     p = bench.dataset(100000, 20)
     F = so.Fasta(p)
     S = so.Searcher(device=0, **bench.FLAGS)
@@ -46,13 +54,13 @@ def main():
             t0 = time.perf_counter()
             nrows = 0
             md5 = hashlib.md5()
-            for s in range(3):
+            for s in range(6):
                 r = S.search((2 + s) * B, (3 + s) * B)
                 nrows += r.n
                 md5.update(r.as_array().tobytes())
             dt = time.perf_counter() - t0
             st = S.stats(reset=True)
-            rec.update(ms_per_step=1e3 * dt / 3, proteins_per_s=3 * B / dt, rows=nrows, rows_md5=md5.hexdigest(),
+            rec.update(ms_per_step=1e3 * dt / 6, proteins_per_s=6 * B / dt, rows=nrows, rows_md5=md5.hexdigest(),
                        alignments=st['alignments'], alignments_used=st.get('alignments_used'))
             if '--no-stages' not in sys.argv:
                 S.set_lanes(0)
