@@ -522,7 +522,7 @@ def run_ours(args, rank, world, local):
     dev_ms = max(1e-9, ms_ungap + ms_sort + ms_seed + ms_select + ms_dp + ms_tb)
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_xdrop_r02.json')))
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_xdrop_r02b.json')))
     except Exception:  # noqa: BLE001
         pass
     roof = {'kernel': 'k_xdrop', 'bound': 'int32', 'achieved': ach, 'peak': int_peak['gops_measured'],
@@ -541,7 +541,7 @@ def run_ours(args, rank, world, local):
     # Algorithmic bytes per seed hit: 2 x 8 B index entry reads (count + scatter pass), 4 B cell-local key write,
     # 4 B read + 8 B key write in the cell sorts = 32 B
     sort_bytes = seed_hits / max(world, 1) * 40.0
-    hbm = {'kernel': 'k_cell_pass<0/1> + k_unit_scan + k_cell_small/warp/block', 'bound': 'hbm',
+    hbm = {'kernel': 'k_cell_pass<0/1> + k_unit_scan + k_cell_span / k_cell_block', 'bound': 'hbm',
            'achieved': sort_bytes / (ms_sort * 1e-3) / 1e9 if ms_sort else 0,
            'peak': peaks.get('hbm_gbs', 6650.0), 'unit': 'GB/s', 'ms_per_step': ms_sort / args.steps,
            'algorithmic_bytes': '40 B per seed hit (2 x 8 B index entry reads, 4 B key write + 4 B read, 4 + 8 + 4 B sorted key / '

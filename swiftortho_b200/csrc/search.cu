@@ -50,6 +50,7 @@ struct SeedCfg {
 __constant__ SeedCfg c_cfg;
 __constant__ uint16_t c_alpha[4 * 256];
 __constant__ int8_t c_score2[kClasses * kClasses];
+__device__ int g_xdrop_tab[26 * 32];  // k_xdrop's step table, one entry per (target class, query class): upload_cfg
 __constant__ uint8_t c_code2[256];
 
 static int upload_cfg(const Params &P) {
@@ -78,6 +79,15 @@ static int upload_cfg(const Params &P) {
     SO_CUDA(cudaMemcpyToSymbol(c_alpha, al, sizeof al));
     SO_CUDA(cudaMemcpyToSymbol(c_score2, tbl, sizeof tbl));
     SO_CUDA(cudaMemcpyToSymbol(c_code2, code, sizeof code));
+    // k_xdrop's packed step entries (see the kernel's header comment): 1 - score * 8192, 2^29 for a terminator (class 24) or a
+    // class outside the table, 0 for the skip class (25).  Built once here: every CTA then copies 832 words 32 times
+    // instead of deriving each lane-private entry from a divergent constant-memory read.
+    int xt[26 * 32];
+    for (int e = 0; e < 26 * 32; e++) {
+        const int ct = e >> 5, cq = e & 31;
+        xt[e] = ct == 25 ? 0 : (ct < 24 && cq < 24) ? 1 - (int)tbl[cq * kClasses + ct] * 8192 : 1 << 29;
+    }
+    SO_CUDA(cudaMemcpyToSymbol(g_xdrop_tab, xt, sizeof xt));
     return SO_OK;
 }
 
@@ -889,12 +899,12 @@ __global__ void __launch_bounds__(256) k_cell_span(const uint32_t *__restrict__ 
             const int cl = i < gm ? (int)sc[i] : a;
             const uint32_t cs = __shfl_sync(0xffffffffu, pre, cl) - pa, cn = __shfl_sync(0xffffffffu, nn, cl);
             if (i < gm) {
+                // (the keys of a cell are distinct: one pattern, one alphabet -> one hit per (qst, sst))
                 const uint32_t x = si[i];
-                uint32_t rank = 0;
-                for (uint32_t j = 0; j < cn; j++) {
-                    const uint32_t y = si[cs + j];
-                    rank += (y < x || (y == x && cs + j < i)) ? 1u : 0u;
-                }
+                const uint32_t *sk = si + cs;
+                uint32_t rank = 0, j = 0;
+                for (; j + 4 <= cn; j += 4) rank += (sk[j] < x) + (sk[j + 1] < x) + (sk[j + 2] < x) + (sk[j + 3] < x);
+                for (; j < cn; j++) rank += sk[j] < x;
                 so_[cs + rank] = x;
             }
         }
@@ -1433,15 +1443,7 @@ __global__ void __launch_bounds__(kWarps * 32, kWarps == 16 ? 2 : 1) k_xdrop(con
 #define XD_WQI (XD_SBASE + (uint32_t)kWarps * (kXdBuf * 8u) + (threadIdx.x >> 5) * (kXdBuf * 2u))
 #define XD_WIDX (XD_SBASE + (uint32_t)kWarps * (kXdBuf * 10u) + (threadIdx.x >> 5) * 32u)
     int wcount = 0;  // warp-uniform
-    for (int k = threadIdx.x; k < kUngRows * 32 * 32; k += blockDim.x) {
-        const int e = k >> 5, ct = e >> 5, cq = e & 31;
-        int val = 1 << 29;
-        if (ct == kUngSkip)
-            val = 0;
-        else if (ct < 24 && cq < 24)
-            val = 1 - (int)c_score2[cq * kClasses + ct] * 8192;
-        s_tab[k] = val;
-    }
+    for (int k = threadIdx.x; k < kUngRows * 32 * 32; k += blockDim.x) s_tab[k] = g_xdrop_tab[k >> 5];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t lanebase = (uint32_t)__cvta_generic_to_shared(s_tab) + (uint32_t)lane * 4u;

@@ -16,16 +16,9 @@ import bench
 from swiftortho_b200 import search as so
 
 SETTINGS = [  # (name, production lanes, environment)
-    ('l1', 1, {}),
-    ('l1_qb592', 1, {'SO_QUERY_BLOCK': '592'}),
-    ('l1_qb1024', 1, {'SO_QUERY_BLOCK': '1024'}),
-    ('l1_qb2048', 1, {'SO_QUERY_BLOCK': '2048'}),
-    ('l1_qb256', 1, {'SO_QUERY_BLOCK': '256'}),
-    ('l1_align1024', 1, {'SO_ALIGN_BATCH': '1024'}),
-    ('l1_own', 1, {'SO_SHARED_STREAM': '0'}),
-    ('l2_own', 2, {'SO_SHARED_STREAM': '0'}),
-    ('l2', 2, {}),
-    ('l1_b', 1, {}),
+    ('default', 1, {}),
+    ('cell_small_warp', 1, {'SO_CELL_SPAN': '0'}),
+    ('default_again', 1, {}),
 ]
 HOOKS = sorted({k for _, _, e in SETTINGS for k in e})
 
