@@ -454,22 +454,17 @@ def run_ours(args, rank, world, local):
     shm = '/dev/shm' if os.path.isdir('/dev/shm') else CACHE
     outp = os.path.join(shm, 'swiftortho_b200_bench_%d.sc' % rank)
 
-    class Sub:  # a FASTA view restricted to one query block (headers come from the full container)
-        pass
-    e2e_q = 0
-    for s in range(args.warmup + args.steps):
-        a, b = block_of(1000 + s)
-        if s == args.warmup:
-            S.stats(reset=True)
-            barrier()
-            t1 = time.perf_counter()
-        off = np.ascontiguousarray(F.offsets[a:b + 1])
-        so.check(lib.so_set_queries(S.h, C.c_void_p(res_ptr), off.ctypes.data, b - a))
-        rows = S.search(0, b - a)
-        rows.view()['query'] += a  # result records are host memory already (D2H happened inside so_search)
-        so.check(lib.so_write_rows(rows.ptr, rows.n, F.h, F.h, outp.encode(), 0))
-        if s >= args.warmup:
-            e2e_q += b - a
+    # Searcher.search_stream is the streaming call of the public API (swiftortho_b200/search.py): per block it prepares
+    # the queries on the host (seg, S3 order), copies them to the device, searches, copies the rows back and formats the
+    # text; the host preparation of block i + 1 and the formatting of block i - 1 overlap block i's device work.  The
+    # timed call covers exactly `steps` blocks, pipeline fill and drain included.
+    S.search_stream(F, [block_of(1000 + s) for s in range(args.warmup)], outp, append=False)
+    S.stats(reset=True)
+    barrier()
+    t1 = time.perf_counter()
+    timed = [block_of(1000 + args.warmup + s) for s in range(args.steps)]
+    S.search_stream(F, timed, outp, append=False)
+    e2e_q = sum(b - a for a, b in timed)
     barrier()
     dt2 = time.perf_counter() - t1
     st2 = S.stats()

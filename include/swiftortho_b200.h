@@ -103,6 +103,14 @@ void so_ctx_destroy(so_ctx *c);
  * `n_db` is D = len(DB), the e-value database size (fsearch.py:2979). */
 int so_set_targets(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, int64_t n);
 int so_set_queries(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, int64_t n);
+/* The same in two halves, for callers that stream query blocks (the reference recomputes seg and the position order per
+ * query inside its loop, fsearch.py:2995-2998, 2647-2668): so_queries_prepare does the host work (seg masks, S3 position
+ * order) without touching the device or the context's query state -- it may run on another thread while so_search works
+ * on the previous block -- and so_set_queries_prepared makes the prepared set the context's query set (H2D). */
+typedef struct so_qprep so_qprep;
+int so_queries_prepare(const so_ctx *c, const uint8_t *residues, const uint64_t *offsets, int64_t n, so_qprep **out);
+int so_set_queries_prepared(so_ctx *c, so_qprep *p);
+void so_qprep_free(so_qprep *p);
 
 /* K1-K3  build the index of every target chunk — replaces Fasta.makedb / build_msav
  * (lib/fsearch.py:2283-2295, 2208-2280: generate_nr_tbl 406-422, spseeds_fnv 519-556,

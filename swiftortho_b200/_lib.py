@@ -81,6 +81,9 @@ SYMBOLS = {
     'so_ctx_destroy': (None, [C.c_void_p]),
     'so_set_targets': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     'so_set_queries': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    'so_queries_prepare': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_void_p)]),
+    'so_set_queries_prepared': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'so_qprep_free': (None, [C.c_void_p]),
     'so_index_build': (C.c_int, [C.c_void_p]),
     'so_index_chunks': (C.c_int64, [C.c_void_p]),
     'so_index_info_get': (C.c_int, [C.c_void_p, C.c_int64, _P(so_index_info)]),

@@ -275,28 +275,42 @@ int so_set_targets(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, 
     return SO_OK;
 }
 
-int so_set_queries(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, int64_t n) {
-    if (!c || !offsets || n < 0 || (!residues && n > 0 && offsets[n] > 0)) {
-        set_error("so_set_queries: bad argument");
+// host half of so_set_queries: seg masks and the S3 position order of a query set, computed without touching the device
+// or the context's query state, so a caller can prepare block i + 1 on another thread while so_search runs on block i
+struct so_qprep {
+    int64_t n = 0;
+    uint32_t max_qlen = 0;
+    double t_host = 0;
+    std::vector<uint64_t> q_off;
+    std::vector<uint8_t> masked;
+    std::vector<uint32_t> perm;
+};
+
+int so_queries_prepare(const so_ctx *c, const uint8_t *residues, const uint64_t *offsets, int64_t n, so_qprep **out) {
+    if (!c || !out || !offsets || n < 0 || (!residues && n > 0 && offsets[n] > 0)) {
+        set_error("so_queries_prepare: bad argument");
         return SO_EINVAL;
     }
-    SO_CUDA(cudaSetDevice(c->device));
-    int rc = check_offsets(offsets, n, c->max_qlen, "query");
-    if (rc != SO_OK) return rc;
+    so_qprep *p = new so_qprep();
+    int rc = check_offsets(offsets, n, p->max_qlen, "query");
+    if (rc != SO_OK) {
+        delete p;
+        return rc;
+    }
     Timer tm;
-    c->n_q = n;
-    c->q_off.assign(offsets, offsets + n + 1);
+    p->n = n;
+    p->q_off.assign(offsets, offsets + n + 1);
     const uint64_t base = offsets[0];
-    for (auto &v : c->q_off) v -= base;
-    const size_t bytes = (size_t)c->q_off[(size_t)n];
-    c->q_masked.resize(bytes);
-    std::vector<uint32_t> &perm = c->q_perm_host;
+    for (auto &v : p->q_off) v -= base;
+    const size_t bytes = (size_t)p->q_off[(size_t)n];
+    p->masked.resize(bytes);
+    std::vector<uint32_t> &perm = p->perm;
     perm.resize(bytes);
     const bool flt = c->P.flt;
     const int mink = c->P.mink;
     const uint8_t *src = residues + base;
-    uint8_t *dst = c->q_masked.data();
-    const uint64_t *qo = c->q_off.data();
+    uint8_t *dst = p->masked.data();
+    const uint64_t *qo = p->q_off.data();
     // H1 (seg) and the S3 position order: kscs = sliding BLOSUM62 self score over the shortest seed
     // span, positions sorted with the reference quicksort by -kscs (fsearch.py:2647-2656, 2668)
     so::parallel_for(n, [&](i64 q) {
@@ -321,7 +335,48 @@ int so_set_queries(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, 
         uint32_t *pp = perm.data() + qo[q];
         for (i64 i = 0; i < P; i++) pp[i] = (uint32_t)v[(size_t)i];
     });
-    const double t_host = tm.ms();
+    p->t_host = tm.ms();
+    *out = p;
+    return SO_OK;
+}
+
+void so_qprep_free(so_qprep *p) { delete p; }
+
+int so_set_queries(so_ctx *c, const uint8_t *residues, const uint64_t *offsets, int64_t n) {
+    if (!c) {
+        set_error("so_set_queries: bad argument");
+        return SO_EINVAL;
+    }
+    so_qprep *p = nullptr;
+    int rc = so_queries_prepare(c, residues, offsets, n, &p);
+    if (rc != SO_OK) return rc;
+    rc = so_set_queries_prepared(c, p);
+    so_qprep_free(p);
+    return rc;
+}
+
+// device half: the prepared set becomes the context's query set (H2D of the masked residues, offsets and position
+// order, residue classes computed on the device); `p` is left empty
+int so_set_queries_prepared(so_ctx *c, so_qprep *p) {
+    if (!c || !p) {
+        set_error("so_set_queries_prepared: bad argument");
+        return SO_EINVAL;
+    }
+    SO_CUDA(cudaSetDevice(c->device));
+    int rc;
+    Timer tm;
+    const int64_t n = p->n;
+    c->n_q = n;
+    c->max_qlen = p->max_qlen;
+    c->q_off.swap(p->q_off);
+    c->q_masked.swap(p->masked);
+    c->q_perm_host.swap(p->perm);
+    const size_t bytes = (size_t)c->q_off[(size_t)n];
+    std::vector<uint32_t> &perm = c->q_perm_host;
+    uint8_t *dst = c->q_masked.data();
+    const uint64_t *qo = c->q_off.data();
+    const double t_host0 = p->t_host;
+    const double t_host = t_host0;
     // device buffers grow only: so_set_queries is called once per query block on the end-to-end path
     if (bytes > c->q_cap_bytes || !c->d_qres) {
         if (c->d_qres) cudaFree(c->d_qres);

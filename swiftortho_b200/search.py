@@ -171,6 +171,73 @@ class Searcher:
             raise err[0]
         return nrows[0]
 
+    def search_stream(self, fasta, ranges, path, append=True):
+        """Stream the query blocks `ranges` = [(a, b), ...] of `fasta` (a host FASTA container) through the search and
+        append their rows to `path`.  Three threads: the host preparation of block i + 1 (seg masks, S3 position order:
+        so_queries_prepare) and the text formatting of block i - 1 (so_write_rows) overlap the device work of block i
+        (so_set_queries_prepared: H2D, so_search: kernels + D2H of the rows); the library calls release the GIL.
+        Returns the number of rows written."""
+        import queue
+        import threading
+        lib = self.lib
+        pq, wq, err, nrows = queue.Queue(maxsize=2), queue.Queue(maxsize=2), [], [0]
+        if not append:
+            open(path, 'wb').close()
+
+        def preparer():
+            try:
+                for a, b in ranges:
+                    if err:
+                        break
+                    off = np.ascontiguousarray(fasta.offsets[a:b + 1])
+                    h = C.c_void_p()
+                    check(lib.so_queries_prepare(self.h, fasta._res, off.ctypes.data, b - a, C.byref(h)))
+                    pq.put((a, b, h))
+            except BaseException as e:  # noqa: BLE001
+                err.append(e)
+            finally:
+                pq.put(None)
+
+        def writer():
+            while True:
+                rows = wq.get()
+                if rows is None:
+                    return
+                try:
+                    if not err:
+                        check(lib.so_write_rows(rows.ptr, rows.n, fasta.h, self.targets.h, str(path).encode(), 1))
+                        nrows[0] += rows.n
+                except BaseException as e:  # noqa: BLE001
+                    err.append(e)
+
+        tp, tw = threading.Thread(target=preparer), threading.Thread(target=writer)
+        tp.start()
+        tw.start()
+        try:
+            while True:
+                item = pq.get()
+                if item is None:
+                    break
+                a, b, h = item
+                try:
+                    if not err:
+                        check(lib.so_set_queries_prepared(self.h, h))
+                        rows = self.search(0, b - a)
+                        rows.view()['query'] += a
+                        wq.put(rows)
+                except BaseException as e:  # noqa: BLE001
+                    err.append(e)
+                finally:
+                    lib.so_qprep_free(h)
+        finally:
+            wq.put(None)
+            tp.join()
+            tw.join()
+        self.queries = None  # the context now holds the last block only
+        if err:
+            raise err[0]
+        return nrows[0]
+
     def stats(self, reset=False):
         s = so_stats()
         check(self.lib.so_stats_get(self.h, C.byref(s)))
