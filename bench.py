@@ -257,10 +257,8 @@ def full_job(args, rank, world, local, fasta, barrier, out_dir):
     lib = S.lib
     nrows = 0
     if b > a:
-        off = np.ascontiguousarray(F.offsets[a:b + 1])
-        so.check(lib.so_set_queries(S.h, C.c_void_p(F._res.value), off.ctypes.data, b - a))
         S.stats(reset=True)
-        nrows = S.search_to_file(0, b - a, part, block=args.full_block, query_base=a, fasta=F)
+        nrows = S.search_stream(F, [(x, min(b, x + args.full_block)) for x in range(a, b, args.full_block)], part)
     st = S.stats()
     t_part = time.perf_counter() - t0
     barrier()
@@ -630,7 +628,7 @@ def main():
     ap.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS), help='BASELINE.json config (default 2 = headline)')
     ap.add_argument('--mode', default='steps', choices=['steps', 'full'],
                     help='steps: timed query blocks against the resident index (default); full: one whole job, strong scaling')
-    ap.add_argument('--full-block', type=int, default=65536, help='queries per so_search call of the whole-job run')
+    ap.add_argument('--full-block', type=int, default=16384, help='queries per so_search call of the whole-job run')
     ap.add_argument('--full-check-rows', type=int, default=2000000)
     ap.add_argument('--no-full', action='store_true', help='skip the whole-job record of the default run')
     ap.add_argument('--parity-out', default=None, help=argparse.SUPPRESS)

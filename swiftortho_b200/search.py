@@ -288,7 +288,7 @@ class _Rows:
 
 
 def blastp(qry, ref, out, expect=1e-5, v=500, max_miss=1e-3, st=-1, ed=-1, rst=-1, red=-1, thr=-1, flt='T',
-           ssd='111111', nr=AA9, step=4, ht=-1, chk=50000, wrt='w', device=0, block=65536):
+           ssd='111111', nr=AA9, step=4, ht=-1, chk=50000, wrt='w', device=0, block=16384):
     """Drop-in for the `fsearch-c -p blastp` run (lib/fsearch.py:2968 + 3231-3256): searches queries
     [st, ed) of `qry` against `ref` and writes the 16-column rows to `out`.  Returns the stats dict."""
     if ht < 2:
@@ -301,12 +301,12 @@ def blastp(qry, ref, out, expect=1e-5, v=500, max_miss=1e-3, st=-1, ed=-1, rst=-
     S = Searcher(device=device, ssd=ssd, nr=nr, ht=ht, step=step, expect=expect, v=v, max_miss=max_miss, thr=thr,
                  flt=flt, chk=chk, rst=rst, red=red)
     S.set_targets(T)
-    S.set_queries(Q)
     S.build_index()
     first = 'a' not in wrt
     if first:
         open(out, 'wb').close()
-    S.search_to_file(st, ed, out, block=block)
+    # query blocks are prepared (seg, S3 order), searched and written as a three-stage pipeline; only [st, ed) is prepared
+    S.search_stream(Q, [(a, min(ed, a + block)) for a in range(st, ed, block)], out)
     stats = S.stats()
     S.close()
     return stats
