@@ -476,6 +476,11 @@ int so_candidates(so_ctx *c, int64_t chunk, int64_t q_begin, int64_t q_end, uint
         bool fast = false, redo = false;
         rc = bs.prepare(c, nqc, capc, 1, c->stream);
         if (rc == SO_OK) rc = so::block_candidates_fast(c, q_begin, q_end, 0, bs, fast, (int)chunk);
+        if (rc == SO_OK && fast) rc = so::enqueue_fast_ctl(c, 0);
+        if (rc == SO_OK && fast && c->lane_wait(0) != cudaSuccess) {
+            set_error("CUDA error in so_candidates");
+            rc = SO_ENODEV;
+        }
         if (rc == SO_OK && fast) rc = so::finish_fast_block(c, 0, redo);
         if (rc == SO_OK && fast && !redo) {
             std::vector<uint32_t> cnt((size_t)nqc);
