@@ -478,7 +478,8 @@ def run_ours(args, rank, world, local):
     offs = F.offsets
     for i in range(npairs):
         qi, ti = (i * 3 + rank) % n, (i * 7919 + 13) % n
-        Pp[i] = so.so_pair(qi, ti, 0, int(offs[qi + 1] - offs[qi]), 0, int(offs[ti + 1] - offs[ti]), 0, 0)
+        # (sequences of 4096+ residues -- config 5 -- enter as their first 4095-residue tile: so_align_batch takes tiles)
+        Pp[i] = so.so_pair(qi, ti, 0, min(4095, int(offs[qi + 1] - offs[qi])), 0, min(4095, int(offs[ti + 1] - offs[ti])), 0, 0)
     Aa = (so.so_aln * npairs)()
     so.check(lib.so_set_queries(S.h, F._res, F._off, F.N))
     so.check(lib.so_align_batch(S.h, Pp, npairs, Aa))
