@@ -87,7 +87,7 @@ def test_host_logic_against_reference_goldens(cluster_oracle, golden):
     """find_cluster's host side (parsing, the two clustering rounds of `cnc` with their falsy-zero quirks, sort and
     batches, fc2mat's table, output) on top of the oracle's numeric kernels = the reference's partition; the clusters
     also come out in the reference's order."""
-    assert len(golden['cases']) == 15
+    assert len(golden["cases"]) == 25
     for c in golden['cases']:
         a = dict(zip(c['args'][::2], c['args'][1::2]))
         lines = fc.cluster(os.path.join(GOLDEN, c['input']), a['-a'], float(a.get('-d', 0.5)), float(a.get('-I', 1.5)),
