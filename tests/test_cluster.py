@@ -3,7 +3,7 @@
 CPU (`-m "not gpu"`): oracle/cluster_oracle.cpp against the known answers of the reference's own functions
 (`mcl`, `apclust_blk`, exec'ed from the reference source by tests/golden/make_cluster_golden.py) and the host logic
 of swiftortho_b200.find_cluster -- driven by that oracle through its backend seam -- against the reference script's
-output on three inputs x five parameter sets.
+output on five inputs x five parameter sets.
 GPU (`-m gpu`): the CUDA kernels through the C ABI against the oracle (bit-exact: labels, float32 matrices) and the
 CLI against the reference goldens.
 
