@@ -32,14 +32,18 @@ def opcode(text):
     return re.sub(r'^@!?U?P\d\s+', '', text).split()[0].split('.')[0]
 
 
-print('# SASS excerpts, round 2\n')
+print('# SASS excerpts, round 2 (final build)\n')
 print('`cuobjdump -sass swiftortho_b200/libswiftortho_b200.so` (sm_100a cubins, CUDA 12.9), summarised by '
       '`tools/sass_excerpt.py`.  DESIGN.md 4.1 / 4.3 argue from these instruction mixes: an X-drop step is '
       '`VIADDMNMX` + `ISETP` + `PRMT` on the alu pipe, `IMAD` forms on the fma pipe and one `LDS`; a banded-DP cell uses '
       'the DPX min/max forms (`VIMNMX3`, `VIADDMNMX.RELU`, `VIMNMX.RELU`) with `PRMT`-spliced table addresses.  No kernel '
       'contains a tensor-core or TMA instruction (`UTCMMA`, `UTMALDG`, `LDTM`): no stage of this path is a dense '
       'contraction (BASELINE.json north_star).\n')
-for name, title in (('k_xdropILi24ELb1', 'k_xdrop<24, FAST> (sync-free cell path)'), ('k_banded_dp', 'k_banded_dp'),
+for name, title in (('k_xdropILi24ELb1ELi32ELi16', 'k_xdrop<24, FAST, 32 warps, 16 query views> (default layout)'),
+                    ('k_xdropILi24ELb1ELi16ELi0', 'k_xdrop<24, FAST, 16 warps, 1 query view> (first half of round 2)'),
+                    ('k_cell_span', 'k_cell_span'), ('k_banded_dp_wave', 'k_banded_dp_wave (16 lanes per alignment)'),
+                    ('k_banded_dpEPK', 'k_banded_dp'), ('k_mcl_spgemm_warpILb1', 'k_mcl_spgemm_warp<write>'),
+                    ('k_apc_rows', 'k_apc_rows'),
                     ('k_traceback', 'k_traceback'), ('k_h3_select', 'k_h3_select (H3 on the device)'), ('k_cand_sort', 'k_cand_sort'),
                     ('k_cell_passILb1', 'k_cell_pass<true>'), ('k_cell_small', 'k_cell_small'), ('k_orth_classify', 'k_orth_classify')):
     st, en = func_range(name)
@@ -68,7 +72,7 @@ def excerpt(name, pred, width, title):
     print('```\n')
 
 
-excerpt('k_xdropILi24ELb1', lambda t: 'VIADDMNMX' in t, 26,
+excerpt('k_xdropILi24ELb1ELi32ELi16', lambda t: 'VIADDMNMX' in t, 26,
         'k_xdrop<24, FAST>: consecutive extension steps of the unrolled 16-step body (VIADDMNMX = d = max(d + e, 0), '
         'predicated IMAD forms = the v / d updates on the fma pipe, ISETP = X-drop test)')
 excerpt('k_banded_dp', lambda t: 'VIMNMX3' in t or 'VIADDMNMX' in t, 30,
