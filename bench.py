@@ -558,7 +558,11 @@ def run_ours(args, rank, world, local):
             'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic', 'config': workload_config(args, B),
             'roofline': roof, 'roofline_grouping': hbm, 'roofline_dp': dp_roof, 'gapped_gcups': gcups_alone,
             'e2e': {'value': e2e_q / dt2, 'unit': 'proteins/s', 'h2d_bytes_per_step': h2d / args.steps,
-                    'd2h_bytes_per_step': d2h / args.steps},
+                    'd2h_bytes_per_step': d2h / args.steps,
+                    'api': 'Searcher.search_stream: per step so_queries_prepare (host: seg, position order) -> '
+                           'so_set_queries_prepared (H2D) -> so_search (kernels, rows D2H) -> so_write_rows (text); the '
+                           'preparation of step i+1 and the text of step i-1 overlap step i; the timed call covers exactly '
+                           '`steps` steps, pipeline fill and drain included'},
             'gpu_launches': int(launches), 'clocks': clk,
             'stage_ms_per_step': {k: v / args.steps for k, v in dict(seed=ms_seed, grouping=ms_sort, ungap=ms_ungap,
                                                                       select=ms_select, dp=ms_dp, traceback=ms_tb,
