@@ -15,9 +15,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from swiftortho_b200 import search as so
 
-SETTINGS = [  # (name, production lanes, environment)
+SETTINGS = [  # (name, production lanes, environment); edit for the experiment at hand
     ('default', 1, {}),
-    ('cell_small_warp', 1, {'SO_CELL_SPAN': '0'}),
+    ('xdrop_16_warps_1_view', 1, {'SO_XDROP_WARPS': '16', 'SO_XDROP_QSHIFT': '0'}),     # layout of the first half of round 2
+    ('cell_small_warp', 1, {'SO_CELL_SPAN': '0'}),                                       # k_cell_small + k_cell_warp
+    ('both_old', 1, {'SO_XDROP_WARPS': '16', 'SO_XDROP_QSHIFT': '0', 'SO_CELL_SPAN': '0'}),
+    ('query_block_512', 1, {'SO_QUERY_BLOCK': '512'}),
+    ('lanes_2', 2, {}),
+    ('lanes_2_own_streams', 2, {'SO_SHARED_STREAM': '0'}),
     ('default_again', 1, {}),
 ]
 HOOKS = sorted({k for _, _, e in SETTINGS for k in e})
