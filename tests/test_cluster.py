@@ -215,9 +215,19 @@ def test_gpu_mcl_rejects_unsorted_rows(device_backend):
 
 
 @pytest.mark.gpu
-def test_find_cluster_cli_against_reference_goldens(golden, tmp_path):
-    """`python -m swiftortho_b200.find_cluster` (CUDA kernels) = the reference script's partition on every golden case."""
+def test_find_cluster_against_reference_goldens(golden, device_backend):
+    """find_cluster on the CUDA kernels = the reference script's partition and cluster order on every golden case
+    (in process: the call `main` makes), and through the command line on four of them."""
     for c in golden['cases']:
+        a = dict(zip(c['args'][::2], c['args'][1::2]))
+        lines = fc.cluster(os.path.join(GOLDEN, c['input']), a['-a'], float(a.get('-d', 0.5)), float(a.get('-I', 1.5)),
+                           backend=device_backend)
+        assert _canon(lines) == c['partition'], (c['input'], c['args'])
+        assert [sorted(l.split('\t')) for l in lines] == [sorted(l.split('\t')) for l in c['raw']]
+    cli = [c for c in golden['cases'] if c['input'] in ('synth600.orth', 'cluster_quirks.xyz')
+           and c['args'] in (['-a', 'mcl', '-I', '1.5'], ['-a', 'apc'])]
+    assert len(cli) == 4
+    for c in cli:
         r = subprocess.run([sys.executable, '-m', 'swiftortho_b200.find_cluster', '-i', os.path.join(GOLDEN, c['input'])] + c['args'],
                            cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert r.returncode == 0, r.stderr
